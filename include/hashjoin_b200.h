@@ -1,0 +1,144 @@
+/*
+ * hashjoin_b200.h — C ABI of libhashjoin_b200.so, the B200-native replacement for the build + probe path of
+ * deveshv-99/mlir-HashJoin.  The library sits in the slot of the reference's shared_stuff/shared.so: it is loaded by
+ * `mlir-cpu-runner --shared-libs=...` (run_test.sh:14,33) and its symbols are resolved by name from MLIR `func.call`s.
+ *
+ * Three groups of entry points (citations are file:line in the reference):
+ *
+ *  A. The six legacy helper symbols, bit-compatible with shared_stuff/shared.cpp:18-172 (expanded memref ABI,
+ *     five scalars per rank-1 memref: allocated, aligned, offset, size, stride — shared.cpp:35, join_v1.ll:1262-1265).
+ *
+ *  B. The join entry points with the reference's own names and argument lists — the MLIR host wrappers
+ *     @initializeHashTable / @buildTable / @countRows / @probeRelation (join_v1.mlir:54,77,110,149) — so the
+ *     reference's @main (join_v1.mlir:525-649) runs unchanged once those four func.funcs are turned into
+ *     `func.func private` declarations.  Each exists in the expanded ABI (plain name) and in the
+ *     llvm.emit_c_interface ABI (`_mlir_ciface_<name>`, pointers to StridedMemRefType<T,1> descriptors).
+ *
+ *  C. The native B200 surface (`hashJoin*` for MLIR callers, `hj*` for C/C++/ctypes callers with explicit streams):
+ *     opaque table/scratch workspaces sized by query, i32 and i64 keys, payload columns, radix partition, digest.
+ *
+ * All relation / table / scratch / result pointers are DEVICE pointers unless a name says Host.  The library uses the
+ * CUDA runtime API on the current device (primary context), so pointers from mgpuMemAlloc / cudaMalloc / torch are
+ * valid.  Entry points of groups A and B and the `hashJoin*` functions are synchronous on return; `hj*` functions
+ * are asynchronous on the stream they are given unless documented otherwise.  Nothing throws across this boundary:
+ * failures return a negative status (and print one line to stderr); hjLastErrorString() has the text.
+ * There is NO CPU fallback: without a CUDA device every join entry point fails with HJ_ERR_CUDA.
+ */
+#ifndef HASHJOIN_B200_H
+#define HASHJOIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HJ_OK 0
+#define HJ_ERR_ARG (-22)     /* bad argument: null pointer, non-unit stride, misaligned or too-small workspace */
+#define HJ_ERR_CUDA (-5)     /* CUDA runtime error (no device, launch failure, out of memory) */
+#define HJ_ERR_STATE (-2)    /* legacy surface: countRows/probeRelation on a table that was never built */
+
+/* StridedMemRefType<T,1> as passed by llvm.emit_c_interface (Experiments/passing-memrefs.mlir:10, join_v1.ll:106-111) */
+typedef struct { void* allocated; void* aligned; int64_t offset; int64_t sizes[1]; int64_t strides[1]; } HjMemRef1D;
+
+/* ---- A. legacy helper symbols (shared_stuff/shared.cpp) -------------------------------------------------- */
+void startTimer(void);                                                                   /* shared.cpp:18-20 */
+void endTimer(void);                      /* prints "For <n>, time taken: <us> microseconds"  shared.cpp:23-31 */
+void initRelationIndex(int32_t* allocated, int32_t* aligned, int64_t offset, int64_t size, int64_t stride); /* :35-41 */
+void initRelationR(int32_t* allocated, int32_t* aligned, int64_t offset, int64_t size, int64_t stride);     /* :59-80 */
+void initRelationS(int32_t* allocated, int32_t* aligned, int64_t offset, int64_t size, int64_t stride);     /* :83-116 */
+/* HOST memrefs. 1 = result equals the nested-loop join, 0 = differs, -1 = more matches than result rows. :129-172 */
+int32_t check(int32_t* rAlloc, int32_t* rAligned, int64_t rOff, int64_t rSize, int64_t rStride,
+              int32_t* sAlloc, int32_t* sAligned, int64_t sOff, int64_t sSize, int64_t sStride,
+              int32_t* orAlloc, int32_t* orAligned, int64_t orOff, int64_t orSize, int64_t orStride,
+              int32_t* osAlloc, int32_t* osAligned, int64_t osOff, int64_t osSize, int64_t osStride);
+/* Seeds for initRelationR / initRelationS (the reference's are unseeded, shared.cpp:62,86-87). Also read from the
+ * environment variables HASHJOIN_SEED_R / HASHJOIN_SEED_S; unset = time-based like the reference. */
+void hashJoinSetSeeds(uint64_t seedR, uint64_t seedS);
+
+/* ---- B. the reference's join entry points, expanded ABI ---------------------------------------------------- */
+#define HJ_MEMREF(T, n) T* n##Alloc, T* n##Aligned, int64_t n##Off, int64_t n##Size, int64_t n##Stride
+/* join_v1.mlir:54   @initializeHashTable(index, memref<?xi32>) */
+void initializeHashTable(int64_t hashTableSize, HJ_MEMREF(int32_t, head));
+/* join_v1.mlir:77   @buildTable(memref<?xi32>, index, memref<?xi32>, memref<?xi32>, memref<?xindex>, memref<?xindex>, i32) */
+void buildTable(HJ_MEMREF(int32_t, R), int64_t nR, HJ_MEMREF(int32_t, head), HJ_MEMREF(int32_t, lkey),
+                HJ_MEMREF(int64_t, lrow), HJ_MEMREF(int64_t, lnext), int32_t hashTableSize);
+/* join_v1.mlir:110  @countRows(...) -> index   (result size; the one mandatory host sync, :140-146) */
+int64_t countRows(HJ_MEMREF(int32_t, S), int64_t nS, HJ_MEMREF(int32_t, head), HJ_MEMREF(int32_t, lkey),
+                  HJ_MEMREF(int64_t, lrow), HJ_MEMREF(int64_t, lnext), HJ_MEMREF(int64_t, prefix), int32_t hashTableSize);
+/* join_v1.mlir:149  @probeRelation(...) */
+void probeRelation(HJ_MEMREF(int32_t, S), int64_t nS, int32_t hashTableSize, HJ_MEMREF(int32_t, head), HJ_MEMREF(int32_t, lkey),
+                   HJ_MEMREF(int64_t, lrow), HJ_MEMREF(int64_t, lnext), HJ_MEMREF(int64_t, prefix),
+                   HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS));
+/* join_v1.mlir:43   @calculateNumberOfBlocks(index, index) -> index */
+int64_t calculateNumberOfBlocks(int64_t totalThreads, int64_t threadsPerBlock);
+/* releases every table the legacy surface cached (the reference never frees anything, join_v1.mlir:646) */
+void hashJoinRelease(void);
+
+/* same, llvm.emit_c_interface ABI */
+void _mlir_ciface_initializeHashTable(int64_t hashTableSize, HjMemRef1D* head);
+void _mlir_ciface_buildTable(HjMemRef1D* R, int64_t nR, HjMemRef1D* head, HjMemRef1D* lkey, HjMemRef1D* lrow, HjMemRef1D* lnext, int32_t hashTableSize);
+int64_t _mlir_ciface_countRows(HjMemRef1D* S, int64_t nS, HjMemRef1D* head, HjMemRef1D* lkey, HjMemRef1D* lrow, HjMemRef1D* lnext,
+                               HjMemRef1D* prefix, int32_t hashTableSize);
+void _mlir_ciface_probeRelation(HjMemRef1D* S, int64_t nS, int32_t hashTableSize, HjMemRef1D* head, HjMemRef1D* lkey, HjMemRef1D* lrow,
+                                HjMemRef1D* lnext, HjMemRef1D* prefix, HjMemRef1D* outR, HjMemRef1D* outS);
+int32_t _mlir_ciface_check(HjMemRef1D* R, HjMemRef1D* S, HjMemRef1D* outR, HjMemRef1D* outS);
+void _mlir_ciface_initRelationIndex(HjMemRef1D* a);
+void _mlir_ciface_initRelationR(HjMemRef1D* a);
+void _mlir_ciface_initRelationS(HjMemRef1D* a);
+
+/* ---- C1. native MLIR surface: opaque workspaces (memref<?xi8>), sizes from the memref descriptors ---------- */
+int64_t hashJoinTableBytes(int64_t nR);          /* i32 keys */
+int64_t hashJoinTableBytesI64(int64_t nR);
+int64_t hashJoinScratchBytes(int64_t nS);
+int64_t hashJoinScratchBytesI64(int64_t nS);
+int32_t hashJoinBuild(HJ_MEMREF(int32_t, R), HJ_MEMREF(int8_t, table));
+int64_t hashJoinCount(HJ_MEMREF(int32_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch));
+int32_t hashJoinWrite(HJ_MEMREF(int32_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch),
+                      HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS));
+int32_t hashJoinBuildI64(HJ_MEMREF(int64_t, R), HJ_MEMREF(int8_t, table));
+int64_t hashJoinCountI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch));
+int32_t hashJoinWriteI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch),
+                         HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS));
+int32_t _mlir_ciface_hashJoinBuild(HjMemRef1D* R, HjMemRef1D* table);
+int64_t _mlir_ciface_hashJoinCount(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch);
+int32_t _mlir_ciface_hashJoinWrite(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS);
+int32_t _mlir_ciface_hashJoinBuildI64(HjMemRef1D* R, HjMemRef1D* table);
+int64_t _mlir_ciface_hashJoinCountI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch);
+int32_t _mlir_ciface_hashJoinWriteI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS);
+
+/* ---- C2. native C surface: device pointers + explicit stream (cudaStream_t passed as void*) ---------------- */
+int64_t hjTableBytes(int64_t nR, int32_t keyBytes);            /* keyBytes: 4 or 8 */
+int64_t hjScratchBytes(int64_t nS, int32_t keyBytes);
+/* K0+K1. payload == NULL: build row id = rowBase + i (join_v1.mlir:232). Asynchronous. */
+int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase,
+                void* dTable, int64_t tableBytes, void* stream);
+/* K2+K3, asynchronous; hjCountResult copies the total back and synchronises the stream; hjCount does both. */
+int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream);
+int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream);
+int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream);
+/* K4. Writes exactly the pairs counted by the preceding hjCount on the same (S, table, scratch). probePayload == NULL:
+ * probe row id = probeRowBase + j (join_v1.mlir:499-500 stores the thread index). Asynchronous. */
+int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
+                int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+/* K5. Radix partition on the key hash into nParts (<= 256) contiguous ranges; dOffsets: u64[nParts+1]. Asynchronous. */
+int64_t hjPartitionWorkspaceBytes(int64_t n, int32_t nParts);
+int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
+                    void* dOutKeys, uint32_t* dOutRows, uint64_t* dOffsets, void* dWorkspace, int64_t workspaceBytes, void* stream);
+/* K6. Order-independent digest of a pair stream: hostOut2[0] = sum, hostOut2[1] = xor of mix64(r << 32 | s). Synchronous. */
+int32_t hjPairDigest(const int32_t* dOutR, const int32_t* dOutS, int64_t n, uint64_t* hostOut2, void* stream);
+/* Seeded device generators, bit-identical to the oracle's (kinds: 0 index, 1 unique, 2 uniform, 3 mixed, 4 fk, 5 zipf). */
+int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64_t seed, int64_t lo, uint64_t domain,
+                   uint32_t p16, uint64_t keyMul, int64_t indexBase, uint64_t nTotal, void* stream);
+/* End-to-end convenience with HOST buffers (what the reference's @main does around the kernels, join_v1.mlir:558-615):
+ * H2D of both relations, build, count, write, D2H of the pairs. Returns the result size; pairs are copied only when
+ * hOutR/hOutS are non-NULL and capacity >= result size. Synchronous. */
+int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes,
+                   int32_t* hOutR, int32_t* hOutS, int64_t capacity);
+const char* hjLastErrorString(void);
+const char* hjVersion(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASHJOIN_B200_H */

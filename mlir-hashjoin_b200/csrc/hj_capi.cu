@@ -1,0 +1,440 @@
+// hj_capi.cu — the C-ABI boundary (include/hashjoin_b200.h): legacy helper symbols, the reference's join entry
+// points (expanded + llvm.emit_c_interface ABIs) and the native hj* surface.  No torch types, no C++ in signatures.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/hashjoin_b200.h"
+#include "hj_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int32_t fail(int32_t code, const char* where, const char* what) {
+  g_last_error = std::string(where) + ": " + what;
+  fprintf(stderr, "[hashjoin_b200] %s\n", g_last_error.c_str());
+  return code;
+}
+int32_t cuda_fail(const char* where, cudaError_t e) { return fail(HJ_ERR_CUDA, where, cudaGetErrorString(e)); }
+
+#define HJ_CUDA(where, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(where, e_); } while (0)
+
+inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline bool key_ok(int32_t kb) { return kb == 4 || kb == 8; }
+
+// pinned 8-byte landing zone for the result-size readback
+unsigned long long* pinned_total() {
+  static unsigned long long* p = nullptr;
+  if (!p && cudaMallocHost(&p, 64) != cudaSuccess) p = nullptr;
+  return p;
+}
+
+// ---- legacy surface state: B200 tables cached per caller-visible head pointer -----------------------------
+struct LegacyTable { void* table = nullptr; int64_t table_bytes = 0; void* scratch = nullptr; int64_t scratch_bytes = 0; bool built = false; };
+std::mutex g_mu;
+std::map<const void*, LegacyTable> g_tables;
+
+// ---- hjJoinHost cache -------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr; int64_t bytes = 0;
+  cudaError_t ensure(int64_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, (size_t)need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+DevBuf g_hR, g_hS, g_hT, g_hSc, g_hOr, g_hOs;
+
+std::chrono::high_resolution_clock::time_point g_timer_start;
+uint64_t g_seed_r = 0, g_seed_s = 0;
+bool g_seed_r_set = false, g_seed_s_set = false;
+
+inline uint64_t mix64h(uint64_t z) { z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 27; z *= 0x94D049BB133111EBULL; z ^= z >> 31; return z; }
+
+void fill_random(int32_t* a, int64_t n, uint64_t seed) {
+  // values in [1, 1e9] like shared.cpp:13-14,68 — but from a seedable counter-based generator
+  const uint64_t range = 1000000000ULL;
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t r = mix64h(seed * 0x9E3779B97F4A7C15ULL + mix64h((uint64_t)i + 0xD1B54A32D192ED03ULL));
+    a[i] = (int32_t)(1 + (uint64_t)(((unsigned __int128)r * range) >> 64));
+  }
+}
+
+template <typename T> inline T* mr_ptr(T* aligned, int64_t off) { return aligned ? aligned + off : nullptr; }
+inline bool mr_ok(int64_t size, int64_t stride) { return size <= 1 || stride == 1; }
+
+}  // namespace
+
+extern "C" {
+
+const char* hjLastErrorString(void) { return g_last_error.c_str(); }
+const char* hjVersion(void) { return "hashjoin_b200 0.1 (sm_100a)"; }
+
+// =========================================================================================================
+// A. legacy helper symbols
+// =========================================================================================================
+void startTimer(void) { g_timer_start = std::chrono::high_resolution_clock::now(); }
+
+void endTimer(void) {
+  auto stop = std::chrono::high_resolution_clock::now();
+  static int n = 0;
+  long long us = std::chrono::duration_cast<std::chrono::microseconds>(stop - g_timer_start).count();
+  printf("For %d, time taken: %lld microseconds\n", n, us);
+  fflush(stdout);
+  n++;
+}
+
+void hashJoinSetSeeds(uint64_t seedR, uint64_t seedS) { g_seed_r = seedR; g_seed_s = seedS; g_seed_r_set = g_seed_s_set = true; }
+
+void initRelationIndex(int32_t*, int32_t* aligned, int64_t offset, int64_t size, int64_t) {
+  int32_t* a = mr_ptr(aligned, offset);
+  for (int64_t i = 0; i < size; i++) a[i] = (int32_t)i;
+}
+void initRelationR(int32_t*, int32_t* aligned, int64_t offset, int64_t size, int64_t) {
+  uint64_t seed = g_seed_r;
+  if (!g_seed_r_set) { const char* e = getenv("HASHJOIN_SEED_R"); seed = e ? strtoull(e, nullptr, 0) : (uint64_t)time(nullptr); }
+  fill_random(mr_ptr(aligned, offset), size, seed);
+}
+void initRelationS(int32_t*, int32_t* aligned, int64_t offset, int64_t size, int64_t) {
+  uint64_t seed = g_seed_s;
+  if (!g_seed_s_set) { const char* e = getenv("HASHJOIN_SEED_S"); seed = e ? strtoull(e, nullptr, 0) : (uint64_t)std::random_device{}(); }
+  fill_random(mr_ptr(aligned, offset), size, seed);
+}
+
+// Same verdicts as the reference's nested loop + sort + compare (shared.cpp:129-172), computed in
+// O((n+m) log m + out log out): -1 when the true join has more pairs than the result holds (:158-160); otherwise the
+// expected vector is the true pairs padded with (0,0) up to result_size (the reference value-initialises it, :140-141).
+int32_t check(int32_t*, int32_t* rAligned, int64_t rOff, int64_t rSize, int64_t,
+              int32_t*, int32_t* sAligned, int64_t sOff, int64_t sSize, int64_t,
+              int32_t*, int32_t* orAligned, int64_t orOff, int64_t orSize, int64_t,
+              int32_t*, int32_t* osAligned, int64_t osOff, int64_t osSize, int64_t) {
+  if (orSize != osSize) { fail(HJ_ERR_ARG, "check", "result columns differ in length (the reference asserts here, shared.cpp:134)"); return 0; }
+  const int32_t* R = mr_ptr(rAligned, rOff); const int32_t* S = mr_ptr(sAligned, sOff);
+  const int32_t* oR = mr_ptr(orAligned, orOff); const int32_t* oS = mr_ptr(osAligned, osOff);
+  const int64_t result_size = orSize;
+  std::vector<std::pair<int32_t, int32_t>> skeys((size_t)sSize);           // (key, probe row) sorted by key then row
+  for (int64_t j = 0; j < sSize; j++) skeys[(size_t)j] = {S[j], (int32_t)j};
+  std::sort(skeys.begin(), skeys.end());
+  std::vector<std::pair<int32_t, int32_t>> expect;
+  expect.reserve((size_t)result_size);
+  for (int64_t i = 0; i < rSize; i++) {
+    auto lo = std::lower_bound(skeys.begin(), skeys.end(), std::make_pair(R[i], INT32_MIN));
+    for (; lo != skeys.end() && lo->first == R[i]; ++lo) {
+      if ((int64_t)expect.size() >= result_size) return -1;
+      expect.emplace_back((int32_t)i, lo->second);
+    }
+  }
+  expect.resize((size_t)result_size, std::make_pair(0, 0));
+  std::vector<std::pair<int32_t, int32_t>> got((size_t)result_size);
+  for (int64_t k = 0; k < result_size; k++) got[(size_t)k] = {oR[k], oS[k]};
+  std::sort(expect.begin(), expect.end());
+  std::sort(got.begin(), got.end());
+  return expect == got ? 1 : 0;
+}
+
+// =========================================================================================================
+// C2. native C surface
+// =========================================================================================================
+int64_t hjTableBytes(int64_t nR, int32_t keyBytes) { return (nR < 0 || !key_ok(keyBytes)) ? HJ_ERR_ARG : hj::table_bytes(nR, keyBytes); }
+int64_t hjScratchBytes(int64_t nS, int32_t keyBytes) { return (nS < 0 || !key_ok(keyBytes)) ? HJ_ERR_ARG : hj::scratch_bytes(nS, keyBytes); }
+
+int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase, void* dTable, int64_t tableBytes, void* stream) {
+  if (!key_ok(keyBytes) || nR < 0 || (nR > 0 && !dR) || !dTable) return fail(HJ_ERR_ARG, "hjBuild", "null pointer or bad key width");
+  if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, "hjBuild", "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
+  if (reinterpret_cast<uintptr_t>(dTable) & 15) return fail(HJ_ERR_ARG, "hjBuild", "table workspace must be 16-byte aligned");
+  if (tableBytes < hj::HEADER_BYTES + (nR + nR / 4 + 1) * (keyBytes == 4 ? 8 : 16)) return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
+  HJ_CUDA("hjBuild", hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, S_(stream)));
+  return HJ_OK;
+}
+
+int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {
+  if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjCount", "null pointer or bad key width");
+  if (reinterpret_cast<uintptr_t>(dScratch) & 15) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 16-byte aligned");
+  if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
+  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, S_(stream)));
+  return HJ_OK;
+}
+
+int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream) {
+  if (!dScratch || !key_ok(keyBytes) || nS < 0) return fail(HJ_ERR_ARG, "hjCountResult", "bad argument");
+  unsigned long long* host = pinned_total();
+  if (!host) return fail(HJ_ERR_CUDA, "hjCountResult", "cudaMallocHost failed");
+  hj::ScratchView sv = hj::scratch_view(const_cast<void*>(dScratch), nS, keyBytes);
+  HJ_CUDA("hjCountResult", cudaMemcpyAsync(host, sv.tile_offsets + sv.ntiles, 8, cudaMemcpyDeviceToHost, S_(stream)));
+  HJ_CUDA("hjCountResult", cudaStreamSynchronize(S_(stream)));
+  return (int64_t)*host;
+}
+
+int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {
+  int32_t rc = hjCountAsync(dS, nS, keyBytes, dTable, dScratch, scratchBytes, stream);
+  if (rc != HJ_OK) return rc;
+  return hjCountResult(dScratch, nS, keyBytes, stream);
+}
+
+int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
+                int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+  if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjWrite", "null pointer or bad key width");
+  HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, S_(stream)));
+  return HJ_OK;
+}
+
+int64_t hjPartitionWorkspaceBytes(int64_t n, int32_t nParts) { return hj::partition_workspace_bytes(n, nParts); }
+
+int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
+                    void* dOutKeys, uint32_t* dOutRows, uint64_t* dOffsets, void* dWorkspace, int64_t workspaceBytes, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && (!dKeys || !dOutKeys || !dOutRows)) || !dOffsets || !dWorkspace)
+    return fail(HJ_ERR_ARG, "hjPartition", "null pointer or bad key width");
+  HJ_CUDA("hjPartition", hj::radix_partition(dKeys, dRows, rowBase, n, keyBytes, nParts, dOutKeys, dOutRows,
+                                             reinterpret_cast<unsigned long long*>(dOffsets), dWorkspace, workspaceBytes, S_(stream)));
+  return HJ_OK;
+}
+
+int32_t hjPairDigest(const int32_t* dOutR, const int32_t* dOutS, int64_t n, uint64_t* hostOut2, void* stream) {
+  if (!hostOut2 || n < 0 || (n > 0 && (!dOutR || !dOutS))) return fail(HJ_ERR_ARG, "hjPairDigest", "bad argument");
+  static unsigned long long* d = nullptr;
+  if (!d) HJ_CUDA("hjPairDigest", cudaMalloc(&d, 16));
+  HJ_CUDA("hjPairDigest", hj::pair_digest(dOutR, dOutS, n, d, S_(stream)));
+  HJ_CUDA("hjPairDigest", cudaMemcpyAsync(hostOut2, d, 16, cudaMemcpyDeviceToHost, S_(stream)));
+  HJ_CUDA("hjPairDigest", cudaStreamSynchronize(S_(stream)));
+  return HJ_OK;
+}
+
+int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64_t seed, int64_t lo, uint64_t domain,
+                   uint32_t p16, uint64_t keyMul, int64_t indexBase, uint64_t nTotal, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dOut) || kind < 0 || kind > 5) return fail(HJ_ERR_ARG, "hjGenerate", "bad argument");
+  if (nTotal == 0) nTotal = (uint64_t)(indexBase + n);
+  HJ_CUDA("hjGenerate", hj::generate_keys_total(dOut, n, keyBytes, kind, seed, lo, domain, p16, keyMul, indexBase, nTotal, S_(stream)));
+  return HJ_OK;
+}
+
+int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes, int32_t* hOutR, int32_t* hOutS, int64_t capacity) {
+  if (!key_ok(keyBytes) || nR < 0 || nS < 0 || (nR > 0 && !hR) || (nS > 0 && !hS)) return fail(HJ_ERR_ARG, "hjJoinHost", "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int64_t tb = hj::table_bytes(nR, keyBytes), sb = hj::scratch_bytes(nS, keyBytes);
+  HJ_CUDA("hjJoinHost", g_hR.ensure(std::max<int64_t>(nR * keyBytes, 16)));
+  HJ_CUDA("hjJoinHost", g_hS.ensure(std::max<int64_t>(nS * keyBytes, 16)));
+  HJ_CUDA("hjJoinHost", g_hT.ensure(tb));
+  HJ_CUDA("hjJoinHost", g_hSc.ensure(sb));
+  cudaStream_t st = nullptr;
+  if (nR) HJ_CUDA("hjJoinHost", cudaMemcpyAsync(g_hR.p, hR, (size_t)nR * keyBytes, cudaMemcpyHostToDevice, st));   // join_v1.mlir:558-561
+  if (nS) HJ_CUDA("hjJoinHost", cudaMemcpyAsync(g_hS.p, hS, (size_t)nS * keyBytes, cudaMemcpyHostToDevice, st));
+  int32_t rc = hjBuild(g_hR.p, nR, keyBytes, nullptr, 0, g_hT.p, tb, st);
+  if (rc != HJ_OK) return rc;
+  int64_t total = hjCount(g_hS.p, nS, keyBytes, g_hT.p, g_hSc.p, sb, st);
+  if (total <= 0 || !hOutR || !hOutS || capacity < total) return total;                                           // :600-601
+  HJ_CUDA("hjJoinHost", g_hOr.ensure(total * 4));
+  HJ_CUDA("hjJoinHost", g_hOs.ensure(total * 4));
+  rc = hjWrite(g_hS.p, nS, keyBytes, g_hT.p, g_hSc.p, (int32_t*)g_hOr.p, (int32_t*)g_hOs.p, nullptr, 0, st);
+  if (rc != HJ_OK) return rc;
+  HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutR, g_hOr.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));          // :614-615
+  HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutS, g_hOs.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  HJ_CUDA("hjJoinHost", cudaStreamSynchronize(st));
+  return total;
+}
+
+// =========================================================================================================
+// C1. native MLIR surface (expanded ABI); synchronous on return
+// =========================================================================================================
+int64_t hashJoinTableBytes(int64_t nR) { return hjTableBytes(nR, 4); }
+int64_t hashJoinTableBytesI64(int64_t nR) { return hjTableBytes(nR, 8); }
+int64_t hashJoinScratchBytes(int64_t nS) { return hjScratchBytes(nS, 4); }
+int64_t hashJoinScratchBytesI64(int64_t nS) { return hjScratchBytes(nS, 8); }
+
+#define MR_ARGS_OK(n) mr_ok(n##Size, n##Stride)
+
+static int32_t mlir_build(const void* R, int64_t nR, bool ok, int32_t kb, int8_t* table, int64_t tableBytes) {
+  if (!ok) return fail(HJ_ERR_ARG, "hashJoinBuild", "non-unit stride memref");
+  int32_t rc = hjBuild(R, nR, kb, nullptr, 0, table, tableBytes, nullptr);
+  if (rc != HJ_OK) return rc;
+  cudaError_t e = cudaStreamSynchronize(nullptr);
+  return e == cudaSuccess ? HJ_OK : cuda_fail("hashJoinBuild", e);
+}
+static int32_t mlir_write(const void* S, int64_t nS, bool ok, int32_t kb, const int8_t* table, const int8_t* scratch, int32_t* outR, int32_t* outS) {
+  if (!ok) return fail(HJ_ERR_ARG, "hashJoinWrite", "non-unit stride memref");
+  int32_t rc = hjWrite(S, nS, kb, table, scratch, outR, outS, nullptr, 0, nullptr);
+  if (rc != HJ_OK) return rc;
+  cudaError_t e = cudaStreamSynchronize(nullptr);
+  return e == cudaSuccess ? HJ_OK : cuda_fail("hashJoinWrite", e);
+}
+
+int32_t hashJoinBuild(HJ_MEMREF(int32_t, R), HJ_MEMREF(int8_t, table)) {
+  (void)RAlloc; (void)tableAlloc;
+  return mlir_build(mr_ptr(RAligned, ROff), RSize, MR_ARGS_OK(R) && MR_ARGS_OK(table), 4, mr_ptr(tableAligned, tableOff), tableSize);
+}
+int32_t hashJoinBuildI64(HJ_MEMREF(int64_t, R), HJ_MEMREF(int8_t, table)) {
+  (void)RAlloc; (void)tableAlloc;
+  return mlir_build(mr_ptr(RAligned, ROff), RSize, MR_ARGS_OK(R) && MR_ARGS_OK(table), 8, mr_ptr(tableAligned, tableOff), tableSize);
+}
+int64_t hashJoinCount(HJ_MEMREF(int32_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch)) {
+  (void)SAlloc; (void)tableAlloc; (void)scratchAlloc; (void)tableSize;
+  if (!(MR_ARGS_OK(S) && MR_ARGS_OK(table) && MR_ARGS_OK(scratch))) return fail(HJ_ERR_ARG, "hashJoinCount", "non-unit stride memref");
+  return hjCount(mr_ptr(SAligned, SOff), SSize, 4, mr_ptr(tableAligned, tableOff), mr_ptr(scratchAligned, scratchOff), scratchSize, nullptr);
+}
+int64_t hashJoinCountI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch)) {
+  (void)SAlloc; (void)tableAlloc; (void)scratchAlloc; (void)tableSize;
+  if (!(MR_ARGS_OK(S) && MR_ARGS_OK(table) && MR_ARGS_OK(scratch))) return fail(HJ_ERR_ARG, "hashJoinCountI64", "non-unit stride memref");
+  return hjCount(mr_ptr(SAligned, SOff), SSize, 8, mr_ptr(tableAligned, tableOff), mr_ptr(scratchAligned, scratchOff), scratchSize, nullptr);
+}
+int32_t hashJoinWrite(HJ_MEMREF(int32_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch), HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS)) {
+  (void)SAlloc; (void)tableAlloc; (void)scratchAlloc; (void)outRAlloc; (void)outSAlloc; (void)tableSize; (void)scratchSize;
+  const bool ok = MR_ARGS_OK(S) && MR_ARGS_OK(table) && MR_ARGS_OK(scratch) && MR_ARGS_OK(outR) && MR_ARGS_OK(outS);
+  return mlir_write(mr_ptr(SAligned, SOff), SSize, ok, 4, mr_ptr(tableAligned, tableOff), mr_ptr(scratchAligned, scratchOff), mr_ptr(outRAligned, outROff), mr_ptr(outSAligned, outSOff));
+}
+int32_t hashJoinWriteI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch), HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS)) {
+  (void)SAlloc; (void)tableAlloc; (void)scratchAlloc; (void)outRAlloc; (void)outSAlloc; (void)tableSize; (void)scratchSize;
+  const bool ok = MR_ARGS_OK(S) && MR_ARGS_OK(table) && MR_ARGS_OK(scratch) && MR_ARGS_OK(outR) && MR_ARGS_OK(outS);
+  return mlir_write(mr_ptr(SAligned, SOff), SSize, ok, 8, mr_ptr(tableAligned, tableOff), mr_ptr(scratchAligned, scratchOff), mr_ptr(outRAligned, outROff), mr_ptr(outSAligned, outSOff));
+}
+
+// =========================================================================================================
+// B. the reference's join entry points (join_v1.mlir:43-176), expanded ABI.
+// The caller's chained-table arrays (head / lkey / lrow / lnext, join_v1.mlir:25-39) are only a HANDLE here: the
+// B200 table lives in a workspace this library owns, keyed by the head pointer.  The caller's prefixSumArray
+// (8 bytes per probe row, join_v1.mlir:588) is big enough for the match cache and is used as scratch when it is.
+// Timer prints are kept where the reference's wrappers have them (join_v1.mlir:65,72,97,105,128,137,164,174).
+// =========================================================================================================
+int64_t calculateNumberOfBlocks(int64_t totalThreads, int64_t threadsPerBlock) {             // join_v1.mlir:43-52
+  return threadsPerBlock > 0 ? (int64_t)(((uint64_t)totalThreads + (uint64_t)threadsPerBlock - 1) / (uint64_t)threadsPerBlock) : 0;
+}
+
+void initializeHashTable(int64_t hashTableSize, HJ_MEMREF(int32_t, head)) {                  // join_v1.mlir:54-75
+  (void)headAlloc; (void)headStride;
+  startTimer();
+  int32_t* h = mr_ptr(headAligned, headOff);
+  int64_t n = std::min<int64_t>(hashTableSize, headSize);
+  if (h && n > 0) {
+    cudaError_t e = cudaMemsetAsync(h, 0xFF, (size_t)n * 4, nullptr);                         // head[i] = -1  (:197)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) cuda_fail("initializeHashTable", e);
+  }
+  { std::lock_guard<std::mutex> lk(g_mu); g_tables[h].built = false; }
+  endTimer();
+}
+
+void buildTable(HJ_MEMREF(int32_t, R), int64_t nR, HJ_MEMREF(int32_t, head), HJ_MEMREF(int32_t, lkey), HJ_MEMREF(int64_t, lrow),
+                HJ_MEMREF(int64_t, lnext), int32_t hashTableSize) {                          // join_v1.mlir:77-108
+  (void)RAlloc; (void)headAlloc; (void)headSize; (void)headStride; (void)lkeyAlloc; (void)lkeyAligned; (void)lkeyOff; (void)lkeySize; (void)lkeyStride;
+  (void)lrowAlloc; (void)lrowAligned; (void)lrowOff; (void)lrowSize; (void)lrowStride; (void)lnextAlloc; (void)lnextAligned; (void)lnextOff; (void)lnextSize;
+  (void)lnextStride; (void)hashTableSize;
+  if (!mr_ok(RSize, RStride) || nR < 0 || nR > RSize) { fail(HJ_ERR_ARG, "buildTable", "bad build relation memref"); return; }
+  std::lock_guard<std::mutex> lk(g_mu);
+  LegacyTable& t = g_tables[mr_ptr(headAligned, headOff)];
+  const int64_t need = hj::table_bytes(nR, 4);
+  if (t.table_bytes < need) {
+    if (t.table) cudaFree(t.table);
+    t.table = nullptr; t.table_bytes = 0;
+    cudaError_t e = cudaMalloc(&t.table, (size_t)need);
+    if (e != cudaSuccess) { cuda_fail("buildTable", e); return; }
+    t.table_bytes = need;
+  }
+  startTimer();
+  int32_t rc = hjBuild(mr_ptr(RAligned, ROff), nR, 4, nullptr, 0, t.table, t.table_bytes, nullptr);
+  if (rc == HJ_OK) { cudaError_t e = cudaStreamSynchronize(nullptr); if (e != cudaSuccess) rc = cuda_fail("buildTable", e); }
+  t.built = rc == HJ_OK;
+  endTimer();
+}
+
+int64_t countRows(HJ_MEMREF(int32_t, S), int64_t nS, HJ_MEMREF(int32_t, head), HJ_MEMREF(int32_t, lkey), HJ_MEMREF(int64_t, lrow),
+                  HJ_MEMREF(int64_t, lnext), HJ_MEMREF(int64_t, prefix), int32_t hashTableSize) {   // join_v1.mlir:110-147
+  (void)SAlloc; (void)headAlloc; (void)headSize; (void)headStride; (void)lkeyAlloc; (void)lkeyAligned; (void)lkeyOff; (void)lkeySize; (void)lkeyStride;
+  (void)lrowAlloc; (void)lrowAligned; (void)lrowOff; (void)lrowSize; (void)lrowStride; (void)lnextAlloc; (void)lnextAligned; (void)lnextOff; (void)lnextSize;
+  (void)lnextStride; (void)prefixAlloc; (void)hashTableSize;
+  if (!mr_ok(SSize, SStride) || nS < 0 || nS > SSize) return fail(HJ_ERR_ARG, "countRows", "bad probe relation memref");
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_tables.find(mr_ptr(headAligned, headOff));
+  if (it == g_tables.end() || !it->second.built) return fail(HJ_ERR_STATE, "countRows", "hash table was never built (call buildTable first)");
+  LegacyTable& t = it->second;
+  const int64_t need = hj::scratch_bytes(nS, 4);
+  void* scratch = nullptr; int64_t sbytes = 0;
+  int64_t* pfx = mr_ptr(prefixAligned, prefixOff);
+  if (pfx && mr_ok(prefixSize, prefixStride) && prefixSize * 8 >= need && (reinterpret_cast<uintptr_t>(pfx) & 15) == 0) { scratch = pfx; sbytes = prefixSize * 8; }
+  else {
+    if (t.scratch_bytes < need) {
+      if (t.scratch) cudaFree(t.scratch);
+      t.scratch = nullptr; t.scratch_bytes = 0;
+      cudaError_t e = cudaMalloc(&t.scratch, (size_t)need);
+      if (e != cudaSuccess) return cuda_fail("countRows", e);
+      t.scratch_bytes = need;
+    }
+    scratch = t.scratch; sbytes = t.scratch_bytes;
+  }
+  startTimer();
+  int64_t total = hjCount(mr_ptr(SAligned, SOff), nS, 4, t.table, scratch, sbytes, nullptr);
+  endTimer();
+  return total;
+}
+
+void probeRelation(HJ_MEMREF(int32_t, S), int64_t nS, int32_t hashTableSize, HJ_MEMREF(int32_t, head), HJ_MEMREF(int32_t, lkey),
+                   HJ_MEMREF(int64_t, lrow), HJ_MEMREF(int64_t, lnext), HJ_MEMREF(int64_t, prefix), HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS)) {
+  (void)SAlloc; (void)hashTableSize; (void)headAlloc; (void)headSize; (void)headStride; (void)lkeyAlloc; (void)lkeyAligned; (void)lkeyOff; (void)lkeySize;
+  (void)lkeyStride; (void)lrowAlloc; (void)lrowAligned; (void)lrowOff; (void)lrowSize; (void)lrowStride; (void)lnextAlloc; (void)lnextAligned; (void)lnextOff;
+  (void)lnextSize; (void)lnextStride; (void)prefixAlloc; (void)outRAlloc; (void)outSAlloc; (void)outRSize; (void)outSSize;
+  if (!mr_ok(SSize, SStride) || !mr_ok(outRSize, outRStride) || !mr_ok(outSSize, outSStride) || nS < 0 || nS > SSize) { fail(HJ_ERR_ARG, "probeRelation", "bad memref"); return; }
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_tables.find(mr_ptr(headAligned, headOff));
+  if (it == g_tables.end() || !it->second.built) { fail(HJ_ERR_STATE, "probeRelation", "hash table was never built"); return; }
+  LegacyTable& t = it->second;
+  const int64_t need = hj::scratch_bytes(nS, 4);
+  int64_t* pfx = mr_ptr(prefixAligned, prefixOff);
+  const void* scratch = (pfx && mr_ok(prefixSize, prefixStride) && prefixSize * 8 >= need && (reinterpret_cast<uintptr_t>(pfx) & 15) == 0) ? (const void*)pfx : (const void*)t.scratch;
+  if (!scratch) { fail(HJ_ERR_STATE, "probeRelation", "countRows was not called on this table"); return; }
+  startTimer();
+  int32_t rc = hjWrite(mr_ptr(SAligned, SOff), nS, 4, t.table, scratch, mr_ptr(outRAligned, outROff), mr_ptr(outSAligned, outSOff), nullptr, 0, nullptr);
+  if (rc == HJ_OK) { cudaError_t e = cudaStreamSynchronize(nullptr); if (e != cudaSuccess) cuda_fail("probeRelation", e); }
+  endTimer();
+}
+
+void hashJoinRelease(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_tables) { if (kv.second.table) cudaFree(kv.second.table); if (kv.second.scratch) cudaFree(kv.second.scratch); }
+  g_tables.clear();
+  g_hR.release(); g_hS.release(); g_hT.release(); g_hSc.release(); g_hOr.release(); g_hOs.release();
+}
+
+// =========================================================================================================
+// llvm.emit_c_interface wrappers: descriptors by pointer
+// =========================================================================================================
+#define MR(T, d) (T*)(d)->allocated, (T*)(d)->aligned, (d)->offset, (d)->sizes[0], (d)->strides[0]
+
+void _mlir_ciface_initializeHashTable(int64_t H, HjMemRef1D* head) { initializeHashTable(H, MR(int32_t, head)); }
+void _mlir_ciface_buildTable(HjMemRef1D* R, int64_t nR, HjMemRef1D* head, HjMemRef1D* lkey, HjMemRef1D* lrow, HjMemRef1D* lnext, int32_t H) {
+  buildTable(MR(int32_t, R), nR, MR(int32_t, head), MR(int32_t, lkey), MR(int64_t, lrow), MR(int64_t, lnext), H);
+}
+int64_t _mlir_ciface_countRows(HjMemRef1D* S, int64_t nS, HjMemRef1D* head, HjMemRef1D* lkey, HjMemRef1D* lrow, HjMemRef1D* lnext, HjMemRef1D* prefix, int32_t H) {
+  return countRows(MR(int32_t, S), nS, MR(int32_t, head), MR(int32_t, lkey), MR(int64_t, lrow), MR(int64_t, lnext), MR(int64_t, prefix), H);
+}
+void _mlir_ciface_probeRelation(HjMemRef1D* S, int64_t nS, int32_t H, HjMemRef1D* head, HjMemRef1D* lkey, HjMemRef1D* lrow, HjMemRef1D* lnext,
+                                HjMemRef1D* prefix, HjMemRef1D* outR, HjMemRef1D* outS) {
+  probeRelation(MR(int32_t, S), nS, H, MR(int32_t, head), MR(int32_t, lkey), MR(int64_t, lrow), MR(int64_t, lnext), MR(int64_t, prefix), MR(int32_t, outR), MR(int32_t, outS));
+}
+int32_t _mlir_ciface_check(HjMemRef1D* R, HjMemRef1D* S, HjMemRef1D* outR, HjMemRef1D* outS) {
+  return check(MR(int32_t, R), MR(int32_t, S), MR(int32_t, outR), MR(int32_t, outS));
+}
+void _mlir_ciface_initRelationIndex(HjMemRef1D* a) { initRelationIndex(MR(int32_t, a)); }
+void _mlir_ciface_initRelationR(HjMemRef1D* a) { initRelationR(MR(int32_t, a)); }
+void _mlir_ciface_initRelationS(HjMemRef1D* a) { initRelationS(MR(int32_t, a)); }
+int32_t _mlir_ciface_hashJoinBuild(HjMemRef1D* R, HjMemRef1D* table) { return hashJoinBuild(MR(int32_t, R), MR(int8_t, table)); }
+int64_t _mlir_ciface_hashJoinCount(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch) { return hashJoinCount(MR(int32_t, S), MR(int8_t, table), MR(int8_t, scratch)); }
+int32_t _mlir_ciface_hashJoinWrite(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS) {
+  return hashJoinWrite(MR(int32_t, S), MR(int8_t, table), MR(int8_t, scratch), MR(int32_t, outR), MR(int32_t, outS));
+}
+int32_t _mlir_ciface_hashJoinBuildI64(HjMemRef1D* R, HjMemRef1D* table) { return hashJoinBuildI64(MR(int64_t, R), MR(int8_t, table)); }
+int64_t _mlir_ciface_hashJoinCountI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch) { return hashJoinCountI64(MR(int64_t, S), MR(int8_t, table), MR(int8_t, scratch)); }
+int32_t _mlir_ciface_hashJoinWriteI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS) {
+  return hashJoinWriteI64(MR(int64_t, S), MR(int8_t, table), MR(int8_t, scratch), MR(int32_t, outR), MR(int32_t, outS));
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// hj_kernels.cuh — host-side launch interface of the sm_100a join kernels (implemented in hj_kernels.cu).
+// Everything here takes DEVICE pointers and an explicit stream; nothing synchronises except count_rows().
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hj {
+
+constexpr int HEADER_BYTES = 256;              // table workspace = header + slots
+
+// tile geometry shared by count/scan/write (must agree between the two probe passes)
+constexpr int BLOCK_THREADS = 256;
+constexpr int VECS_PER_THREAD = 2;
+__host__ __device__ constexpr int keys_per_vec(int key_bytes) { return 16 / key_bytes; }
+__host__ __device__ constexpr int tile_keys(int key_bytes) { return BLOCK_THREADS * VECS_PER_THREAD * keys_per_vec(key_bytes); }
+
+int64_t preferred_slots(int64_t n_rows);
+int64_t table_bytes(int64_t n_rows, int key_bytes);
+int64_t scratch_bytes(int64_t n_probe, int key_bytes);
+int64_t num_tiles(int64_t n_probe, int key_bytes);
+
+// Scratch layout (device): [ match cache: u32 x round_up(n_probe, tile) ][ tile offsets: u64 x (ntiles + 1) ]
+struct ScratchView {
+  uint32_t* mcache;
+  unsigned long long* tile_offsets;   // after scan: exclusive offsets; [ntiles] = total
+  int64_t ntiles;
+};
+ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
+
+// K0+K1: clear + build.  payload == nullptr -> row id = row_base + i  (join_v1.mlir:232 stores the thread index).
+cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
+                        void* table, int64_t table_bytes_, cudaStream_t stream);
+// K2+K3: count + scan (async).  Total lands in tile_offsets[ntiles].
+cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, cudaStream_t stream);
+// K4: write pairs.
+cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base,
+                        cudaStream_t stream);
+
+// K5: radix partition by the key hash (multi-GPU shuffle feed).  Two launches: histogram, scatter.
+//   counts: u64[n_parts] (device, zeroed by the call); offsets computed on device; keys/rows scattered so that
+//   partition p occupies [offsets[p], offsets[p+1]) of out_keys/out_rows.  offsets: u64[n_parts+1] device.
+cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
+                            void* out_keys, uint32_t* out_rows, unsigned long long* offsets, void* workspace, int64_t workspace_bytes,
+                            cudaStream_t stream);
+int64_t partition_workspace_bytes(int64_t n, int n_parts);
+
+// K6: verification helpers — order-independent digest of a pair stream: out[0] += sum(mix64(pair)), out[1] ^= xor.
+cudaError_t pair_digest(const int32_t* outR, const int32_t* outS, int64_t n, unsigned long long* out2, cudaStream_t stream);
+
+// seeded generators, bit-identical to oracle/oracle_join.c (kinds documented there)
+cudaError_t generate_keys(void* out, int64_t n, int key_bytes, int kind, uint64_t seed, int64_t lo, uint64_t domain,
+                          uint32_t p16, uint64_t key_mul, int64_t index_base, cudaStream_t stream);
+cudaError_t generate_keys_total(void* out, int64_t n, int key_bytes, int kind, uint64_t seed, int64_t lo, uint64_t domain,
+                                uint32_t p16, uint64_t key_mul, int64_t index_base, uint64_t n_total, cudaStream_t stream);
+
+}  // namespace hj

@@ -1,0 +1,305 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact bar: identical multiset of (build_row, probe_row) i32 pairs after a canonical sort (shared.cpp:168-171)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle.binding import sorted_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+def _join_np(R, S, cuda):
+    import torch
+    from mlir_hashjoin_b200 import join
+    dR = torch.from_numpy(np.ascontiguousarray(R)).to(cuda)
+    dS = torch.from_numpy(np.ascontiguousarray(S)).to(cuda)
+    a, b = join.hash_join(dR, dS)
+    torch.cuda.synchronize()
+    return a.cpu().numpy(), b.cpu().numpy()
+
+
+def _assert_parity(oracle, R, S, a, b, H=None):
+    oa, ob = oracle.join(R, S, H=H)
+    assert a.size == oa.size, f"count differs: gpu {a.size} oracle {oa.size}"
+    assert np.array_equal(sorted_pairs(a, b), sorted_pairs(oa, ob))
+
+
+def test_golden_fixtures(lib, cuda, oracle, golden, ref_check):
+    """Every fixture the reference's check() accepted: the GPU join reproduces the accepted multiset exactly."""
+    n = 0
+    for c in golden:
+        if c["verdict"] != 1 or "padded" in c["name"] or "nonempty" in c["name"]:
+            continue
+        R, S = np.array(c["R"], np.int32), np.array(c["S"], np.int32)
+        a, b = _join_np(R, S, cuda)
+        assert np.array_equal(sorted_pairs(a, b), sorted_pairs(c["outR"], c["outS"])), c["name"]
+        assert oracle.check(R, S, a, b) == 1
+        if ref_check is not None:
+            assert ref_check(R, S, a, b) == 1, c["name"]
+        n += 1
+    assert n >= 15
+
+
+def test_c1_config(lib, cuda, oracle, ref_check):
+    """BASELINE.json config 1: 1K x 4K, i32 unique build keys; GPU generators are bit-identical to the oracle's."""
+    import torch
+    from mlir_hashjoin_b200 import datagen, join
+    cfg = datagen.config("C1")
+    dR, dS = datagen.generate(cfg.build), datagen.generate(cfg.probe)
+    R = oracle.generate(1024, 4, 1, 1, 0, 1024); S = oracle.generate(4096, 4, 2, 2, 0, 2048)
+    assert np.array_equal(dR.cpu().numpy(), R) and np.array_equal(dS.cpu().numpy(), S)
+    a, b = join.hash_join(dR, dS)
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    _assert_parity(oracle, R, S, a, b, H=5)
+    assert oracle.check(R, S, a, b) == 1
+    if ref_check is not None:
+        assert ref_check(R, S, a, b) == 1
+    assert join.check(dR.cpu(), dS.cpu(), torch.from_numpy(a), torch.from_numpy(b)) == 1
+
+
+@pytest.mark.parametrize("nR,nS,dom", [(1, 1, 1), (1, 5000, 3), (5000, 1, 3), (2047, 2049, 4000), (2048, 4096, 100), (100000, 300001, 150000),
+                                       (3, 7, 2), (65, 6145, 64)])
+def test_ragged_sizes_i32(lib, cuda, oracle, nR, nS, dom):
+    rng = np.random.default_rng(nR * 31 + nS)
+    R = rng.integers(-dom, dom, nR).astype(np.int32)            # duplicates on both sides, negative keys
+    S = rng.integers(-dom, dom, nS).astype(np.int32)
+    a, b = _join_np(R, S, cuda)
+    _assert_parity(oracle, R, S, a, b)
+
+
+def test_unique_build_partial_hits(lib, cuda, oracle):
+    rng = np.random.default_rng(5)
+    R = rng.permutation(200000).astype(np.int32)[:120000]
+    S = rng.integers(0, 400000, 777777).astype(np.int32)
+    a, b = _join_np(R, S, cuda)
+    _assert_parity(oracle, R, S, a, b)
+
+
+def test_empty_inputs(lib, cuda, oracle):
+    e = np.empty(0, np.int32)
+    for R, S in ((e, np.arange(10, dtype=np.int32)), (np.arange(10, dtype=np.int32), e), (e, e)):
+        a, b = _join_np(R, S, cuda)
+        assert a.size == 0 and b.size == 0
+    a, b = _join_np(np.full(12, 10, np.int32), np.full(12, 1, np.int32), cuda)       # KAT-none: resultSize == 0 (join_v1.mlir:635-644)
+    assert a.size == 0
+
+
+def test_extreme_keys_no_reserved_value(lib, cuda, oracle):
+    """The reference reserves no key value (its -1 sentinel is a node index, join_v1.mlir:197,333): 0xFFFFFFFF etc. must join."""
+    R = np.array([-1, -1, -2**31, 2**31 - 1, 0, -1], np.int32)
+    S = np.array([-1, 0, 2**31 - 1, -2**31, 5, -1, -1], np.int32)
+    a, b = _join_np(R, S, cuda)
+    _assert_parity(oracle, R, S, a, b)
+    R64 = np.array([-1, 2**63 - 1, -2**63, 0, -1, 1 << 32, 1], np.int64)
+    S64 = np.array([1 << 32, -1, 1, 2**63 - 1, -2**63, 0x100000001], np.int64)
+    a, b = _join_np(R64, S64, cuda)
+    _assert_parity(oracle, R64, S64, a, b)
+
+
+@pytest.mark.parametrize("nR,nS", [(1, 3), (1023, 1025), (50000, 200003)])
+def test_i64_keys(lib, cuda, oracle, nR, nS):
+    rng = np.random.default_rng(nR + nS)
+    base = rng.integers(0, max(2, nR // 2), nR).astype(np.int64)
+    R = base * np.int64(0x9E3779B97F4A7C15 - (1 << 64))           # spread over the full 64-bit space (wraps)
+    S = rng.integers(0, max(2, nR), nS).astype(np.int64) * np.int64(0x9E3779B97F4A7C15 - (1 << 64))
+    a, b = _join_np(R, S, cuda)
+    _assert_parity(oracle, R, S, a, b)
+
+
+def test_heavy_duplicates(lib, cuda, oracle):
+    """join-performances.md shape in miniature: few distinct keys, many matches per probe row (output-heavy)."""
+    rng = np.random.default_rng(9)
+    R = rng.integers(1, 101, 20000).astype(np.int32)
+    S = rng.integers(1, 101, 5000).astype(np.int32)
+    a, b = _join_np(R, S, cuda)
+    assert a.size > 900000
+    oa, ob = oracle.join(R, S, H=100, threads=4)
+    assert a.size == oa.size
+    assert oracle.pair_digest(a, b) == oracle.pair_digest(oa, ob)
+    assert np.array_equal(sorted_pairs(a, b), sorted_pairs(oa, ob))
+
+
+def test_unaligned_relation_pointers(lib, cuda, oracle):
+    """memref offset != 0 (aligned + offset is only 4-byte aligned): the scalar-load variants must give the same result."""
+    import torch
+    from mlir_hashjoin_b200 import join
+    rng = np.random.default_rng(21)
+    R = rng.integers(0, 3000, 5001).astype(np.int32); S = rng.integers(0, 3000, 9003).astype(np.int32)
+    dR = torch.from_numpy(R).to(cuda)[1:]; dS = torch.from_numpy(S).to(cuda)[3:]
+    assert dR.data_ptr() % 16 != 0 and dS.data_ptr() % 16 != 0
+    a, b = join.hash_join(dR.contiguous() if not dR.is_contiguous() else dR, dS)
+    _assert_parity(oracle, R[1:], S[3:], a.cpu().numpy(), b.cpu().numpy())
+
+
+def test_payload_columns_and_row_base(lib, cuda, oracle):
+    """Row ids carried as payload columns (the radix-partitioned plan) and probe row bases (the broadcast plan)."""
+    import torch
+    from mlir_hashjoin_b200 import join
+    rng = np.random.default_rng(33)
+    R = rng.integers(0, 500, 3000).astype(np.int32); S = rng.integers(0, 500, 7000).astype(np.int32)
+    pr = rng.permutation(3000).astype(np.int32) + 100000; ps = rng.permutation(7000).astype(np.int32) + 500000
+    dR, dS = torch.from_numpy(R).to(cuda), torch.from_numpy(S).to(cuda)
+    a, b = join.hash_join(dR, dS, buildPayload=torch.from_numpy(pr).to(cuda), probePayload=torch.from_numpy(ps).to(cuda))
+    oa, ob = oracle.join(R, S)
+    assert np.array_equal(sorted_pairs(a.cpu().numpy(), b.cpu().numpy()), sorted_pairs(pr[oa], ps[ob]))
+    a, b = join.hash_join(dR, dS, rowBase=1000, probeRowBase=2000000)
+    assert np.array_equal(sorted_pairs(a.cpu().numpy(), b.cpu().numpy()), sorted_pairs(oa + 1000, ob + 2000000))
+
+
+def _dev_memref(t):
+    return [t.data_ptr(), t.data_ptr(), 0, t.numel(), 1]
+
+
+def test_reference_entry_points_expanded_abi(lib, cuda, oracle, capfd):
+    """The reference's own call sequence (join_v1.mlir:565-615) through the expanded memref ABI with the reference's
+    argument lists: caller-allocated chained-table arrays are only a handle; the result passes check()."""
+    import torch
+    rng = np.random.default_rng(77)
+    nR, nS, H = 6000, 20000, 1000
+    R = rng.integers(1, 4000, nR).astype(np.int32); S = rng.integers(1, 4000, nS).astype(np.int32)
+    dR, dS = torch.from_numpy(R).to(cuda), torch.from_numpy(S).to(cuda)
+    lkey = torch.empty(nR, dtype=torch.int32, device=cuda); lrow = torch.empty(nR, dtype=torch.int64, device=cuda)
+    lnext = torch.empty(nR, dtype=torch.int64, device=cuda); head = torch.empty(H, dtype=torch.int32, device=cuda)
+    prefix = torch.empty(nS, dtype=torch.int64, device=cuda)
+    table = _dev_memref(head) + _dev_memref(lkey) + _dev_memref(lrow) + _dev_memref(lnext)
+    lib.initializeHashTable(H, *_dev_memref(head))
+    assert int(head.min()) == -1 and int(head.max()) == -1                           # join_v1.mlir:197
+    lib.buildTable(*_dev_memref(dR), nR, *table, H)
+    n = lib.countRows(*_dev_memref(dS), nS, *table, *_dev_memref(prefix), H)
+    oa, ob = oracle.join(R, S, H=H)
+    assert n == oa.size
+    outR = torch.empty(n, dtype=torch.int32, device=cuda); outS = torch.empty(n, dtype=torch.int32, device=cuda)
+    lib.probeRelation(*_dev_memref(dS), nS, H, *table, *_dev_memref(prefix), *_dev_memref(outR), *_dev_memref(outS))
+    a, b = outR.cpu().numpy(), outS.cpu().numpy()
+    assert np.array_equal(sorted_pairs(a, b), sorted_pairs(oa, ob))
+    args = []
+    for arr in (R, S, a, b):
+        p = arr.ctypes.data_as(C.c_void_p); args += [p, p, 0, arr.size, 1]
+    assert lib.check(*args) == 1
+    out = capfd.readouterr().out
+    assert out.count("time taken:") >= 4                                             # the four timer prints (For 0..3)
+    # countRows on a table that was never built fails loudly
+    other = torch.empty(8, dtype=torch.int32, device=cuda)
+    bad = _dev_memref(other) + _dev_memref(lkey) + _dev_memref(lrow) + _dev_memref(lnext)
+    assert lib.countRows(*_dev_memref(dS), nS, *bad, *_dev_memref(prefix), H) < 0
+    lib.hashJoinRelease()
+
+
+def test_native_mlir_surface_ciface(lib, cuda, oracle):
+    """hashJoinBuild/Count/Write through llvm.emit_c_interface descriptors, i32 and i64."""
+    import torch
+    from mlir_hashjoin_b200._lib import HjMemRef1D
+    rng = np.random.default_rng(99)
+
+    def desc(t, off=0):
+        return HjMemRef1D(t.data_ptr(), t.data_ptr(), off, (C.c_int64 * 1)(t.numel() - off), (C.c_int64 * 1)(1))
+    for kd, suf in ((np.int32, ""), (np.int64, "I64")):
+        R = rng.integers(0, 900, 2500).astype(kd); S = rng.integers(0, 900, 8100).astype(kd)
+        dR, dS = torch.from_numpy(R).to(cuda), torch.from_numpy(S).to(cuda)
+        tb = getattr(lib, "hashJoinTableBytes" + suf)(R.size); sb = getattr(lib, "hashJoinScratchBytes" + suf)(S.size)
+        table = torch.empty(tb, dtype=torch.uint8, device=cuda); scratch = torch.empty(sb, dtype=torch.uint8, device=cuda)
+        dsc = [desc(dR), desc(dS), desc(table), desc(scratch)]
+        pR, pS, pT, pSc = [C.addressof(d) for d in dsc]
+        assert getattr(lib, "_mlir_ciface_hashJoinBuild" + suf)(pR, pT) == 0
+        n = getattr(lib, "_mlir_ciface_hashJoinCount" + suf)(pS, pT, pSc)
+        oa, ob = oracle.join(R, S)
+        assert n == oa.size
+        outR = torch.empty(n, dtype=torch.int32, device=cuda); outS = torch.empty(n, dtype=torch.int32, device=cuda)
+        dR_, dS_ = desc(outR), desc(outS)
+        assert getattr(lib, "_mlir_ciface_hashJoinWrite" + suf)(pS, pT, pSc, C.addressof(dR_), C.addressof(dS_)) == 0
+        assert np.array_equal(sorted_pairs(outR.cpu().numpy(), outS.cpu().numpy()), sorted_pairs(oa, ob))
+    # too-small workspaces are rejected, not overrun
+    small = torch.empty(64, dtype=torch.uint8, device=cuda)
+    ds = desc(small)
+    assert lib._mlir_ciface_hashJoinBuild(pR, C.addressof(ds)) < 0
+
+
+def test_join_host_e2e(lib, cuda, oracle):
+    import torch
+    from mlir_hashjoin_b200 import join
+    rng = np.random.default_rng(13)
+    R = rng.permutation(50000).astype(np.int32); S = rng.integers(0, 80000, 200000).astype(np.int32)
+    a, b, n = join.join_host(torch.from_numpy(R), torch.from_numpy(S))
+    _assert_parity(oracle, R, S, a.numpy(), b.numpy())
+    hR, hS, ok = join.main(torch.from_numpy(R), torch.from_numpy(S))
+    assert ok == 1 and hR.numel() == n
+
+
+def test_generators_bit_identical(lib, cuda, oracle):
+    from mlir_hashjoin_b200 import datagen
+    specs = [datagen.RelationSpec(10007, 4, datagen.KIND_UNIQUE, 42, 5, 20000), datagen.RelationSpec(10007, 4, datagen.KIND_UNIFORM, 43, -9, 777),
+             datagen.RelationSpec(10007, 4, datagen.KIND_MIXED, 45, 0, 4096, 6554), datagen.RelationSpec(8192, 8, datagen.KIND_FK, 46, 0, 2048, 0, datagen.ODD_MUL64),
+             datagen.RelationSpec(10007, 8, datagen.KIND_ZIPF, 47, 0, 1 << 12, 0, datagen.ODD_MUL64), datagen.RelationSpec(4099, 4, datagen.KIND_INDEX, 0),
+             datagen.RelationSpec(10007, 8, datagen.KIND_UNIQUE, 48, 0, 10007, 0, datagen.ODD_MUL64), datagen.RelationSpec(5000, 4, datagen.KIND_UNIQUE, 5, 0, 5000, 0, 0x9E3779B1)]
+    for s in specs:
+        g = datagen.generate(s).cpu().numpy()
+        o = oracle.generate(s.n, s.key_bytes, s.kind, s.seed, s.lo, s.domain, s.p16, s.key_mul)
+        assert np.array_equal(g, o), s
+        half = datagen.generate(s, index_base=1000, n_local=2000).cpu().numpy()     # sharded generation = slice of the whole
+        assert np.array_equal(half, o[1000:3000]), s
+
+
+def test_pair_digest_matches_oracle(lib, cuda, oracle):
+    import torch
+    from mlir_hashjoin_b200 import join
+    rng = np.random.default_rng(1)
+    a = rng.integers(-2**31, 2**31, 100003).astype(np.int32); b = rng.integers(-2**31, 2**31, 100003).astype(np.int32)
+    assert join.pair_digest(torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)) == oracle.pair_digest(a, b)
+
+
+def test_radix_partition(lib, cuda, oracle):
+    """K5: every key lands in exactly one partition, equal keys in the same one, (key,row) pairs preserved."""
+    import torch
+    rng = np.random.default_rng(8)
+    for kd, kb in ((np.int32, 4), (np.int64, 8)):
+        n, parts = 100003, 8
+        keys = rng.integers(0, 5000, n).astype(kd)
+        d = torch.from_numpy(keys).to(cuda)
+        ok = torch.empty_like(d); orow = torch.empty(n, dtype=torch.int32, device=cuda)
+        offs = torch.empty(parts + 1, dtype=torch.int64, device=cuda)
+        ws = torch.empty(lib.hjPartitionWorkspaceBytes(n, parts), dtype=torch.uint8, device=cuda)
+        rc = lib.hjPartition(d.data_ptr(), None, 7, n, kb, parts, ok.data_ptr(), orow.data_ptr(), offs.data_ptr(), ws.data_ptr(), ws.numel(), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        offs = offs.cpu().numpy(); pk = ok.cpu().numpy(); prow = orow.cpu().numpy()
+        assert offs[0] == 0 and offs[-1] == n and np.all(np.diff(offs) >= 0)
+        assert np.array_equal(keys[prow - 7], pk)                                  # rows carried with their keys
+        assert np.array_equal(np.sort(prow - 7), np.arange(n))                      # a permutation of the input
+        owner = {}
+        for p in range(parts):
+            for k in np.unique(pk[offs[p]:offs[p + 1]]):
+                assert owner.setdefault(int(k), p) == p                             # equal keys -> same partition
+        sizes = np.diff(offs)
+        assert sizes.min() > 0.5 * n / parts
+
+
+def test_mid_size_vs_oracle(lib, cuda, oracle):
+    """1M x 16M unique build, 50 % hits: count and order-independent digest against the OpenMP oracle."""
+    import torch
+    from mlir_hashjoin_b200 import datagen, join
+    b = datagen.RelationSpec(1 << 20, 4, datagen.KIND_UNIQUE, 42, 0, 1 << 20)
+    p = datagen.RelationSpec(1 << 24, 4, datagen.KIND_UNIFORM, 43, 0, 1 << 21)
+    dR, dS = datagen.generate(b), datagen.generate(p)
+    a, bb = join.hash_join(dR, dS)
+    oa, ob = oracle.join(dR.cpu().numpy(), dS.cpu().numpy(), threads=0)
+    assert a.numel() == oa.size
+    assert join.pair_digest(a, bb) == oracle.pair_digest(oa, ob)
+    # size-independent properties: every pair joins equal keys; probe rows are distinct (unique build)
+    assert bool((dR[a.long()] == dS[bb.long()]).all())
+    assert torch.unique(bb).numel() == bb.numel()
+
+
+@pytest.mark.slow
+def test_c2_full_size_properties(lib, cuda):
+    """BASELINE.json config 2 at full size (2^24 x 2^28): analytic count, key equality of every pair, probe rows a permutation."""
+    import torch
+    from mlir_hashjoin_b200 import datagen, join
+    cfg = datagen.config("C2")
+    dR, dS = datagen.generate(cfg.build), datagen.generate(cfg.probe)
+    a, b = join.hash_join(dR, dS)
+    assert a.numel() == cfg.expected_out
+    assert bool((dR[a.long()] == dS[b.long()]).all())
+    bs, _ = torch.sort(b)
+    assert bool((bs == torch.arange(cfg.probe.n, dtype=torch.int32, device=cuda)).all())
