@@ -68,6 +68,7 @@ _SIGNATURES = {
     "hjPairDigest": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "hjGenerate": (_i32, [_vp, _i64, _i32, _i32, _u64, _i64, _u64, _u32, _u64, _i64, _u64, _vp]),
     "hjJoinHost": (_i64, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64]),
+    "hjSetAllowDense": (None, [_i32]),
     "hjLastErrorString": (C.c_char_p, []),
     "hjVersion": (C.c_char_p, []),
 }

@@ -81,7 +81,8 @@ inline bool mr_ok(int64_t size, int64_t stride) { return size <= 1 || stride == 
 extern "C" {
 
 const char* hjLastErrorString(void) { return g_last_error.c_str(); }
-const char* hjVersion(void) { return "hashjoin_b200 0.1 (sm_100a)"; }
+const char* hjVersion(void) { return "hashjoin_b200 0.2 (sm_100a)"; }
+void hjSetAllowDense(int32_t on) { hj::set_allow_dense(on); }
 
 // =========================================================================================================
 // A. legacy helper symbols
@@ -155,7 +156,8 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
   if (!key_ok(keyBytes) || nR < 0 || (nR > 0 && !dR) || !dTable) return fail(HJ_ERR_ARG, "hjBuild", "null pointer or bad key width");
   if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, "hjBuild", "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
   if (reinterpret_cast<uintptr_t>(dTable) & 15) return fail(HJ_ERR_ARG, "hjBuild", "table workspace must be 16-byte aligned");
-  if (tableBytes < hj::HEADER_BYTES + (nR + nR / 4 + 1) * (keyBytes == 4 ? 8 : 16)) return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
+  if (tableBytes < hj::HEADER_BYTES + 64 || (tableBytes - hj::HEADER_BYTES) / 64 * (keyBytes == 4 ? 8 : 4) * 9 < nR * 10)
+    return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
   HJ_CUDA("hjBuild", hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, S_(stream)));
   return HJ_OK;
 }
@@ -173,7 +175,7 @@ int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* 
   unsigned long long* host = pinned_total();
   if (!host) return fail(HJ_ERR_CUDA, "hjCountResult", "cudaMallocHost failed");
   hj::ScratchView sv = hj::scratch_view(const_cast<void*>(dScratch), nS, keyBytes);
-  HJ_CUDA("hjCountResult", cudaMemcpyAsync(host, sv.tile_offsets + sv.ntiles, 8, cudaMemcpyDeviceToHost, S_(stream)));
+  HJ_CUDA("hjCountResult", cudaMemcpyAsync(host, sv.chunk_offsets + sv.nchunks, 8, cudaMemcpyDeviceToHost, S_(stream)));
   HJ_CUDA("hjCountResult", cudaStreamSynchronize(S_(stream)));
   return (int64_t)*host;
 }

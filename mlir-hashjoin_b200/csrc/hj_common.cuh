@@ -2,8 +2,13 @@
 //
 // Replaces, for the hot path of deveshv-99/mlir-HashJoin:
 //   @hash                      join_v1.mlir:206-210   (uint32)key % H  -> multiplicative mix + fast range reduction
-//   chained node arrays        join_v1.mlir:25-39     head/lkey/lrow/lnext -> ONE open-addressing slot array
+//   chained node arrays        join_v1.mlir:25-39     head/lkey/lrow/lnext -> ONE bucketised open-addressing table
 // The result contract (join_v1.mlir:498-500, shared.cpp:139-171) is unchanged: (build_row, probe_row) i32 pairs.
+//
+// Table layout (decided by tools/membench*.cu): an SM can issue about one 32-byte L2 sector
+// request per clock and DRAM fetches 64 bytes per miss, so the unit of probing is ONE 32-byte bucket (one LDG.256):
+// 4 slots of (key:32 | row:32) for i32 keys, 2 slots of (key:64, row:32 + pad) for i64 keys.  Buckets are paired into
+// 64-byte groups; an overflowing bucket spills first into its sibling (same DRAM atom), then into the next pair.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -12,17 +17,26 @@
 namespace hj {
 
 constexpr uint32_t ROW_NONE = 0xFFFFFFFFu;     // never a valid row id: EMPTY marker lives in the row half of a slot
-constexpr uint32_t HJ_MAGIC = 0x424A4832u;     // "2HJB"
+constexpr uint32_t HJ_MAGIC = 0x424A4833u;
+constexpr uint32_t MODE_HASH = 0, MODE_DENSE = 1;
 
-// Device-resident table header (first HEADER_BYTES of the table workspace).
+// Device-resident table header (first HEADER_BYTES of the table workspace). Written by the build kernels, read
+// (uniformly) by count/write, so no host round trip is needed to pick the layout.
 struct TableHeader {
   uint32_t magic;
   uint32_t key_bytes;
-  unsigned long long n_slots;
+  uint32_t mode;                  // MODE_HASH | MODE_DENSE
+  uint32_t has_dups;              // two build rows carry the same key
+  uint32_t need_fallback;         // dense build met a duplicate: rebuild as hash
+  uint32_t all_present;           // dense, unique and every key of [kmin, kmax] present
+  unsigned long long n_pairs;     // hash: number of 64-byte bucket pairs
   unsigned long long n_rows;
-  uint32_t has_dups;        // set by build when two build rows carry the same key
-  uint32_t reserved;
+  long long kmin, kmax;           // build key range (dense decision)
+  unsigned long long dense_range; // kmax - kmin + 1 when dense
+  unsigned long long body_bytes;  // capacity behind the header
+  unsigned long long pairs_cap;   // pairs the caller's workspace can hold
 };
+static_assert(sizeof(TableHeader) <= HEADER_BYTES, "header too large");
 
 // ---------------------------------------------------------------------------------------------------------
 // hashing
@@ -34,30 +48,37 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {          // spl
   z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 27; z *= 0x94D049BB133111EBULL; z ^= z >> 31; return z;
 }
 
-// Key traits: slot type, packing, hashing.  i32 keys: 8-byte slot  (key << 32 | row).
-//                                            i64 keys: 16-byte slot {key, row | 0xFFFFFFFF00000000-free tag}.
 template <typename K> struct KeyTraits;
 
 template <> struct KeyTraits<int32_t> {
-  using Slot = unsigned long long;
-  static constexpr int SLOT_BYTES = 8;
-  static constexpr int KEYS_PER_VEC = 4;      // one 16-byte vector load
-  // slot index in [0, n_slots): top bits of the mixed key, n_slots <= 2^32
-  __device__ __forceinline__ static uint64_t index(int32_t key, uint64_t n_slots) {
-    return ((uint64_t)mix32((uint32_t)key) * n_slots) >> 32;
+  static constexpr int SLOTS = 4;             // slots per 32-byte bucket
+  static constexpr int KEYS_PER_VEC = 4;      // keys per 16-byte vector load
+  // (pair index, home half): top bits of the mixed key pick the pair, the low bit picks the half
+  __device__ __forceinline__ static void home(int32_t key, uint64_t n_pairs, uint64_t& pair, uint32_t& half) {
+    const uint32_t h = mix32((uint32_t)key);
+    pair = ((uint64_t)h * n_pairs) >> 32;     // n_pairs <= 2^32
+    half = h & 1u;
   }
   __device__ __forceinline__ static uint32_t part_hash(int32_t key) { return mix32((uint32_t)key ^ 0x9E3779B9u); }
 };
 
 template <> struct KeyTraits<int64_t> {
-  using Slot = ulonglong2;
-  static constexpr int SLOT_BYTES = 16;
+  static constexpr int SLOTS = 2;
   static constexpr int KEYS_PER_VEC = 2;
-  __device__ __forceinline__ static uint64_t index(int64_t key, uint64_t n_slots) {
-    return __umul64hi(mix64((uint64_t)key), n_slots);
+  __device__ __forceinline__ static void home(int64_t key, uint64_t n_pairs, uint64_t& pair, uint32_t& half) {
+    const uint64_t h = mix64((uint64_t)key);
+    pair = __umul64hi(h, n_pairs);
+    half = (uint32_t)h & 1u;
   }
   __device__ __forceinline__ static uint32_t part_hash(int64_t key) { return (uint32_t)(mix64((uint64_t)key ^ 0x9E3779B97F4A7C15ULL) >> 32); }
 };
+
+// t-th bucket of a probe sequence: home half, sibling half, then the next pair (home half first again) ...
+__device__ __forceinline__ uint64_t probe_bucket(uint64_t pair, uint32_t half, uint32_t t, uint64_t n_pairs) {
+  uint64_t p = pair + (t >> 1);
+  if (p >= n_pairs) p -= n_pairs;             // t stays far below n_pairs (load factor < 1)
+  return 2 * p + ((half ^ t) & 1u);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // cache-hinted memory access (PTX): streams are evict-first and skip L1, the table is evict-last
@@ -75,18 +96,24 @@ __device__ __forceinline__ void st_stream_v4(void* p, int4 v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void st_stream_v2(void* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st_stream_u32(void* p, uint32_t v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_table(const unsigned long long* p, uint64_t pol) {
-  unsigned long long r;
-  asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+__device__ __forceinline__ uint32_t ld_keep_u32(const uint32_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ ulonglong2 ld_table(const ulonglong2* p, uint64_t pol) {
-  ulonglong2 r;
-  asm volatile("ld.global.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(pol));
-  return r;
+
+// One 32-byte bucket as four 64-bit words (SASS: LDG.E.ELL2.256).
+struct Bucket { unsigned long long w[4]; };
+__device__ __forceinline__ Bucket ld_bucket(const void* p) {
+  Bucket b;
+  asm volatile("ld.global.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.w[0]), "=l"(b.w[1]), "=l"(b.w[2]), "=l"(b.w[3]) : "l"(p));
+  return b;
 }
 
 // 128-bit compare-and-swap for the 16-byte (int64-key) slot: SASS ATOMG.E.CAS.128
@@ -99,22 +126,32 @@ __device__ __forceinline__ ulonglong2 atom_cas128(ulonglong2* addr, ulonglong2 c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// slot helpers
+// slot views of a bucket
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long make_slot(int32_t key, uint32_t row) { return ((unsigned long long)(uint32_t)key << 32) | row; }
-__device__ __forceinline__ ulonglong2 make_slot(int64_t key, uint32_t row) { return make_ulonglong2((unsigned long long)key, (unsigned long long)row); }
-__device__ __forceinline__ bool slot_empty(unsigned long long s) { return (uint32_t)s == ROW_NONE; }
-__device__ __forceinline__ bool slot_empty(const ulonglong2& s) { return (uint32_t)s.y == ROW_NONE; }
-__device__ __forceinline__ uint32_t slot_row(unsigned long long s) { return (uint32_t)s; }
-__device__ __forceinline__ uint32_t slot_row(const ulonglong2& s) { return (uint32_t)s.y; }
-__device__ __forceinline__ bool slot_key_eq(unsigned long long s, int32_t key) { return (uint32_t)(s >> 32) == (uint32_t)key; }
-__device__ __forceinline__ bool slot_key_eq(const ulonglong2& s, int64_t key) { return s.x == (unsigned long long)key; }
-
-__device__ __forceinline__ unsigned long long slot_cas(unsigned long long* p, unsigned long long v) {
-  return atomicCAS(p, ~0ULL, v);
+// i32: slot e = w[e] = key << 32 | row.   i64: slot e = (w[2e] = key, w[2e+1] = row | 0xFFFFFFFF-tag in the low half).
+__device__ __forceinline__ bool slot_empty(const Bucket& b, int e, int32_t) { return (uint32_t)b.w[e] == ROW_NONE; }
+__device__ __forceinline__ bool slot_empty(const Bucket& b, int e, int64_t) { return (uint32_t)b.w[2 * e + 1] == ROW_NONE; }
+__device__ __forceinline__ uint32_t slot_row(const Bucket& b, int e, int32_t) { return (uint32_t)b.w[e]; }
+__device__ __forceinline__ uint32_t slot_row(const Bucket& b, int e, int64_t) { return (uint32_t)b.w[2 * e + 1]; }
+// true only for an OCCUPIED slot holding `key` (an EMPTY i32 slot has key bits 0xFFFFFFFF, which is a legal key)
+__device__ __forceinline__ bool slot_match(const Bucket& b, int e, int32_t key) {
+  return (uint32_t)(b.w[e] >> 32) == (uint32_t)key && (uint32_t)b.w[e] != ROW_NONE;
 }
-__device__ __forceinline__ ulonglong2 slot_cas(ulonglong2* p, ulonglong2 v) {
-  return atom_cas128(p, make_ulonglong2(~0ULL, ~0ULL), v);
+__device__ __forceinline__ bool slot_match(const Bucket& b, int e, int64_t key) {
+  return b.w[2 * e] == (unsigned long long)key && (uint32_t)b.w[2 * e + 1] != ROW_NONE;
+}
+// Claim slot e of the bucket at `bp` if it is EMPTY; writes the occupant found (or EMPTY on success) back into b.
+__device__ __forceinline__ bool slot_claim(void* bp, Bucket& b, int e, int32_t key, uint32_t row) {
+  const unsigned long long mine = ((unsigned long long)(uint32_t)key << 32) | row;
+  const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(bp) + e, ~0ULL, mine);
+  b.w[e] = old;
+  return (uint32_t)old == ROW_NONE;
+}
+__device__ __forceinline__ bool slot_claim(void* bp, Bucket& b, int e, int64_t key, uint32_t row) {
+  const ulonglong2 old = atom_cas128(reinterpret_cast<ulonglong2*>(bp) + e, make_ulonglong2(~0ULL, ~0ULL),
+                                     make_ulonglong2((unsigned long long)key, (unsigned long long)row));
+  b.w[2 * e] = old.x; b.w[2 * e + 1] = old.y;
+  return (uint32_t)old.y == ROW_NONE;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -134,7 +171,7 @@ __device__ __forceinline__ T warp_reduce_sum(T v) {
   return v;
 }
 // exclusive scan of one value per thread over the block; returns the thread's exclusive prefix, *total = block sum.
-// smem: at least 33 elements of T.
+// smem: at least 33 elements of T. Ends with a barrier, so smem may be reused immediately.
 template <typename T>
 __device__ __forceinline__ T block_exclusive_scan(T v, T* smem, T* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
@@ -150,8 +187,19 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* smem, T* total) {
   __syncthreads();
   T base = smem[warp];
   *total = smem[32];
-  __syncthreads();                        // smem may be reused by the caller
+  __syncthreads();
   return base + inc - v;
+}
+template <typename T>
+__device__ __forceinline__ T block_reduce_sum(T v, T* smem) {            // result valid in every thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warp_reduce_sum(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T w = lane < nwarps ? smem[lane] : T(0);
+  w = warp_reduce_sum(w);
+  __syncthreads();
+  return w;
 }
 
 }  // namespace hj

@@ -10,6 +10,7 @@
 // Data structure: one open-addressing table, linear probing, EMPTY = row half 0xFFFFFFFF, insertion by a single
 // packed CAS (8-byte slot for i32 keys, 16-byte slot + ATOMG.CAS.128 for i64 keys).  Output contract is the
 // reference's: two i32 columns (build_row, probe_row), any order (join_v1.mlir:498-500, shared.cpp:168-171).
+#include <algorithm>
 #include "hj_common.cuh"
 #include "hj_kernels.cuh"
 
@@ -20,262 +21,347 @@ namespace hj {
 // =========================================================================================================
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-int64_t preferred_slots(int64_t n_rows) {
-  int64_t s = 2 * n_rows;                 // load factor <= 0.5
-  if (s < 64) s = 64;
-  return round_up(s, 16);
+// 64-byte bucket pairs for n_rows build rows. Small tables (<= 32 MB at load 0.5) take load factor 0.5: they are
+// L2-resident anyway and short probe sequences matter (misses stop at the first non-full bucket). Big tables take 0.8:
+// every byte of footprint beyond L2 costs a 64-byte DRAM fetch per lookup.
+int64_t preferred_pairs(int64_t n_rows, int key_bytes) {
+  const int64_t slots_per_pair = key_bytes == 4 ? 8 : 4;
+  const int64_t small_cap = ((int64_t)32 << 20) / 64;
+  int64_t pairs = (2 * n_rows + slots_per_pair - 1) / slots_per_pair;                        // load factor 0.5
+  if (pairs > small_cap) pairs = std::max(small_cap, (5 * n_rows / 4 + slots_per_pair - 1) / slots_per_pair);   // 0.8, never below 32 MB
+  return pairs < 4 ? 4 : pairs;
 }
-int64_t table_bytes(int64_t n_rows, int key_bytes) {
-  const int slot_bytes = key_bytes == 4 ? 8 : 16;
-  return HEADER_BYTES + preferred_slots(n_rows) * slot_bytes;
-}
-int64_t num_tiles(int64_t n_probe, int key_bytes) {
-  const int64_t t = tile_keys(key_bytes);
-  return (n_probe + t - 1) / t;
+int64_t table_bytes(int64_t n_rows, int key_bytes) { return HEADER_BYTES + preferred_pairs(n_rows, key_bytes) * 64; }
+int64_t num_chunks(int64_t n_probe, int key_bytes) {
+  const int64_t c = chunk_keys(key_bytes);
+  return (n_probe + c - 1) / c;
 }
 int64_t scratch_bytes(int64_t n_probe, int key_bytes) {
-  const int64_t nt = num_tiles(n_probe, key_bytes);
-  return round_up(nt * tile_keys(key_bytes) * 4, 256) + (nt + 1) * 8 + 256;
+  const int64_t nc = num_chunks(n_probe, key_bytes);
+  return round_up(nc * chunk_keys(key_bytes) * 4, 256) + (nc + 1) * 8 + 256;
 }
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   ScratchView v;
-  v.ntiles = num_tiles(n_probe, key_bytes);
+  v.nchunks = num_chunks(n_probe, key_bytes);
   v.mcache = reinterpret_cast<uint32_t*>(scratch);
-  v.tile_offsets = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + round_up(v.ntiles * tile_keys(key_bytes) * 4, 256));
+  v.chunk_offsets = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256));
   return v;
 }
 
 // =========================================================================================================
-// K0/K1  build
+// K0/K1  build:  init header -> min/max of the build keys -> decide layout -> clear -> dense build
+//                -> (duplicate in dense mode: switch to hash, clear again) -> hash build.
+// Every decision is taken on the device and read back by later kernels through the header: no host round trip.
 // =========================================================================================================
-__global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned long long n_slots, unsigned long long n_rows) {
-  hdr->magic = HJ_MAGIC; hdr->key_bytes = key_bytes; hdr->n_slots = n_slots; hdr->n_rows = n_rows; hdr->has_dups = 0; hdr->reserved = 0;
+constexpr int DENSE_MAX_FACTOR = 4;     // direct addressing when (kmax - kmin + 1) <= 4 x build rows and it fits
+
+__global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned long long n_rows, unsigned long long body_bytes, unsigned long long pairs) {
+  hdr->magic = HJ_MAGIC; hdr->key_bytes = key_bytes; hdr->mode = MODE_HASH; hdr->has_dups = 0; hdr->need_fallback = 0; hdr->all_present = 0;
+  hdr->n_pairs = pairs; hdr->n_rows = n_rows; hdr->kmin = 0x7FFFFFFFFFFFFFFFLL; hdr->kmax = -0x7FFFFFFFFFFFFFFFLL - 1;
+  hdr->dense_range = 0; hdr->body_bytes = body_bytes; hdr->pairs_cap = body_bytes / 64;
 }
 
 template <typename K>
-__device__ __forceinline__ bool insert_one(typename KeyTraits<K>::Slot* slots, uint64_t n_slots, K key, uint32_t row) {
-  using T = KeyTraits<K>;
-  uint64_t idx = T::index(key, n_slots);
-  const typename T::Slot mine = make_slot(key, row);
-  bool dup = false;
-  while (true) {
-    typename T::Slot old = slot_cas(slots + idx, mine);       // one atomic per step: claims if empty, else returns occupant
-    if (slot_empty(old)) break;
-    dup |= slot_key_eq(old, key);                              // occupants are final: every earlier slot was compared
-    if (++idx == n_slots) idx = 0;
+__global__ void __launch_bounds__(BLOCK_THREADS) k_minmax(const K* __restrict__ R, int64_t nR, TableHeader* hdr) {
+  __shared__ long long smin[32], smax[32];
+  long long lo = 0x7FFFFFFFFFFFFFFFLL, hi = -0x7FFFFFFFFFFFFFFFLL - 1;
+  for (int64_t i = blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x; i < nR; i += (int64_t)gridDim.x * BLOCK_THREADS) {
+    const long long k = (long long)R[i];
+    lo = k < lo ? k : lo; hi = k > hi ? k : hi;
   }
-  return dup;
+  #pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, lo, d), b = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BLOCK_THREADS / 32; w++) { lo = smin[w] < lo ? smin[w] : lo; hi = smax[w] > hi ? smax[w] : hi; }
+    atomicMin(&hdr->kmin, lo); atomicMax(&hdr->kmax, hi);
+  }
+}
+
+__global__ void k_decide(TableHeader* hdr, int allow_dense) {
+  const unsigned long long n = hdr->n_rows;
+  if (n == 0 || !allow_dense) return;
+  const unsigned long long range = (unsigned long long)hdr->kmax - (unsigned long long)hdr->kmin + 1ULL;   // wraps to 0 on the full 64-bit span
+  if (range != 0 && range <= DENSE_MAX_FACTOR * n && range * 4 <= hdr->body_bytes && range <= 0xFFFFFFFFULL) {
+    hdr->mode = MODE_DENSE; hdr->dense_range = range;
+  }
+}
+
+// fallback_pass == 0: clear what the decided layout needs. fallback_pass == 1: only after a dense build hit a duplicate.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_clear(TableHeader* hdr, int4* body, int fallback_pass) {
+  if (fallback_pass) {
+    if (!hdr->need_fallback) return;
+  }
+  const bool dense = !fallback_pass && hdr->mode == MODE_DENSE;
+  const unsigned long long bytes = dense ? ((hdr->dense_range * 4 + 15) & ~15ULL) : hdr->n_pairs * 64;
+  const unsigned long long n16 = bytes / 16;
+  const int4 ff = make_int4(-1, -1, -1, -1);
+  for (unsigned long long i = blockIdx.x * (unsigned long long)BLOCK_THREADS + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * BLOCK_THREADS) body[i] = ff;
+}
+
+__global__ void k_fallback_prepare(TableHeader* hdr) {
+  if (hdr->need_fallback) { hdr->mode = MODE_HASH; hdr->dense_range = 0; hdr->has_dups = 0; }
+  else if (hdr->mode == MODE_DENSE && hdr->dense_range == hdr->n_rows) hdr->all_present = 1;   // unique + range == rows
 }
 
 template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_build(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ payload, uint32_t row_base,
-                                                         typename KeyTraits<K>::Slot* slots, TableHeader* hdr) {
+__device__ __forceinline__ void load_vec_keys(const K* __restrict__ src, int64_t n, int64_t i0, uint64_t pol, K* key) {
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
-  const uint64_t n_slots = hdr->n_slots;
+  if (VEC && i0 + KPV <= n) {
+    int4 x = ld_stream_v4(src + i0, pol);
+    memcpy(key, &x, 16);
+  } else {
+    #pragma unroll
+    for (int e = 0; e < KPV; e++) key[e] = (i0 + e < n) ? src[i0 + e] : K(0);
+  }
+}
+
+template <typename K, bool VEC>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_build_dense(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ payload, uint32_t row_base,
+                                                               uint32_t* __restrict__ tab, TableHeader* hdr) {
+  if (hdr->mode != MODE_DENSE) return;
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  const long long kmin = hdr->kmin;
   const uint64_t pol = policy_evict_first();
   const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
   K key[KPV];
-  if (VEC && i0 + KPV <= nR) {
-    int4 v = ld_stream_v4(R + i0, pol);
-    memcpy(key, &v, 16);
-  } else {
-    #pragma unroll
-    for (int e = 0; e < KPV; e++) key[e] = (i0 + e < nR) ? R[i0 + e] : K(0);
-  }
+  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
   bool dup = false;
   #pragma unroll
   for (int e = 0; e < KPV; e++) {
     if (i0 + e < nR) {
       const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
-      dup |= insert_one<K>(slots, n_slots, key[e], row);
+      const uint32_t old = atomicExch(tab + (unsigned long long)((long long)key[e] - kmin), row);
+      dup |= old != ROW_NONE;
     }
   }
-  const unsigned any = __ballot_sync(0xffffffffu, dup);
-  if (any && (threadIdx.x & 31) == 0) atomicOr(&hdr->has_dups, 1u);
+  if (__ballot_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) atomicOr(&hdr->need_fallback, 1u);
+}
+
+// Insert into the bucketised table: read the bucket once, CAS the first slot seen EMPTY; a failed CAS returns the
+// occupant, which is final, so every earlier slot of the probe sequence has been compared with `key` by the time the
+// insert lands -> duplicate detection is exact (the later of two equal keys always sees the earlier one).
+template <typename K>
+__device__ __forceinline__ bool insert_one(char* body, uint64_t n_pairs, K key, uint32_t row) {
+  using T = KeyTraits<K>;
+  uint64_t pair; uint32_t half;
+  T::home(key, n_pairs, pair, half);
+  bool dup = false;
+  for (uint32_t t = 0;; t++) {
+    char* bp = body + probe_bucket(pair, half, t, n_pairs) * 32;
+    Bucket b = ld_bucket(bp);
+    #pragma unroll
+    for (int e = 0; e < T::SLOTS; e++) {
+      if (slot_empty(b, e, key)) { if (slot_claim(bp, b, e, key, row)) return dup; }
+      dup |= slot_match(b, e, key);
+    }
+  }
+}
+
+template <typename K, bool VEC>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ payload, uint32_t row_base,
+                                                              char* body, TableHeader* hdr) {
+  if (hdr->mode != MODE_HASH) return;
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  const uint64_t n_pairs = hdr->n_pairs;
+  const uint64_t pol = policy_evict_first();
+  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
+  K key[KPV];
+  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+  bool dup = false;
+  #pragma unroll
+  for (int e = 0; e < KPV; e++) {
+    if (i0 + e < nR) {
+      const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
+      dup |= insert_one<K>(body, n_pairs, key[e], row);
+    }
+  }
+  if (__ballot_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) atomicOr(&hdr->has_dups, 1u);
+}
+
+static int g_allow_dense = 1;
+void set_allow_dense(int on) { g_allow_dense = on; }
+
+template <typename K>
+static void launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32_t row_base, char* body, TableHeader* hdr, int64_t pairs, cudaStream_t stream) {
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  const int64_t threads = (nR + KPV - 1) / KPV;
+  const unsigned grid = (unsigned)((threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
+  const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0;
+  const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
+  if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
+  k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
+  k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 0);
+  if (nR == 0) return;
+  if (vec) k_build_dense<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
+  else     k_build_dense<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
+  k_fallback_prepare<<<1, 1, 0, stream>>>(hdr);
+  k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
+  if (vec) k_build_hash<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  else     k_build_hash<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
 }
 
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
                         void* table, int64_t table_bytes_, cudaStream_t stream) {
-  const int slot_bytes = key_bytes == 4 ? 8 : 16;
-  int64_t cap = (table_bytes_ - HEADER_BYTES) / slot_bytes;
-  int64_t n_slots = preferred_slots(nR);
-  if (cap < n_slots) n_slots = cap;                                  // caller gave less than preferred: accept down to 80 % load
-  if (n_slots < nR + nR / 4 + 1 || n_slots < 1) return cudaErrorInvalidValue;
-  if (key_bytes == 4 && n_slots > (int64_t)1 << 32) return cudaErrorInvalidValue;
+  const int64_t slots_per_pair = key_bytes == 4 ? 8 : 4;
+  const int64_t cap = (table_bytes_ - HEADER_BYTES) / 64;
+  int64_t pairs = preferred_pairs(nR, key_bytes);
+  if (cap < pairs) pairs = cap;                                  // caller gave less than preferred: accept up to ~90 % load
+  if (pairs < 1 || pairs * slots_per_pair * 9 < nR * 10) return cudaErrorInvalidValue;
+  if (pairs > (int64_t)1 << 32) return cudaErrorInvalidValue;
   TableHeader* hdr = reinterpret_cast<TableHeader*>(table);
-  char* slots = reinterpret_cast<char*>(table) + HEADER_BYTES;
-  cudaError_t e = cudaMemsetAsync(slots, 0xFF, (size_t)n_slots * slot_bytes, stream);     // K0: every slot EMPTY
-  if (e != cudaSuccess) return e;
-  k_init_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)key_bytes, (unsigned long long)n_slots, (unsigned long long)nR);
-  if (nR > 0) {
-    const int kpv = keys_per_vec(key_bytes);
-    const int64_t threads = (nR + kpv - 1) / kpv;
-    const unsigned grid = (unsigned)((threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
-    const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0;
-    if (key_bytes == 4) {
-      auto* s = reinterpret_cast<unsigned long long*>(slots);
-      if (vec) k_build<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)R, nR, payload, row_base, s, hdr);
-      else     k_build<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)R, nR, payload, row_base, s, hdr);
-    } else {
-      auto* s = reinterpret_cast<ulonglong2*>(slots);
-      if (vec) k_build<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)R, nR, payload, row_base, s, hdr);
-      else     k_build<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)R, nR, payload, row_base, s, hdr);
-    }
-  }
+  char* body = reinterpret_cast<char*>(table) + HEADER_BYTES;
+  k_init_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)key_bytes, (unsigned long long)nR, (unsigned long long)(table_bytes_ - HEADER_BYTES), (unsigned long long)pairs);
+  if (key_bytes == 4) launch_build<int32_t>((const int32_t*)R, nR, payload, row_base, body, hdr, pairs, stream);
+  else                launch_build<int64_t>((const int64_t*)R, nR, payload, row_base, body, hdr, pairs, stream);
   return cudaGetLastError();
 }
 
 // =========================================================================================================
 // K2  count   (per probe row: unique build -> matched build row into the match cache; duplicates -> match count)
 // =========================================================================================================
+// element index of key k (0 .. KPT-1) of this thread inside a tile: (vec, thread, elem) order, coalesced 16-byte vectors
+template <int KPV>
+__device__ __forceinline__ int64_t elem_index(int64_t tile_base, int k) {
+  return tile_base + ((int64_t)(k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV);
+}
+
+// u32 per probe row, same layout as the keys; the cache is padded to whole chunks so vector accesses never run out.
+template <int KPV>
+__device__ __forceinline__ void store_vec_u32(uint32_t* __restrict__ dst, int64_t i0, uint64_t pol, const uint32_t* m) {
+  if (KPV == 4) st_stream_v4(dst + i0, make_int4(m[0], m[1], m[2], m[3]), pol);
+  else st_stream_v2(dst + i0, make_uint2(m[0], m[1]), pol);
+}
+template <int KPV>
+__device__ __forceinline__ void load_vec_u32(const uint32_t* __restrict__ src, int64_t i0, uint64_t pol, uint32_t* m) {
+  if (KPV == 4) { int4 x = ld_stream_v4(src + i0, pol); m[0] = x.x; m[1] = x.y; m[2] = x.z; m[3] = x.w; }
+  else { uint2 x = *reinterpret_cast<const uint2*>(src + i0); m[0] = x.x; m[1] = x.y; }
+}
+
+// first match of `key` (unique build): row id or ROW_NONE
+template <typename K>
+__device__ __forceinline__ uint32_t finish_probe_unique(const char* __restrict__ body, uint64_t n_pairs, K key, uint64_t pair, uint32_t half, Bucket b) {
+  using T = KeyTraits<K>;
+  for (uint32_t t = 0;; ) {
+    #pragma unroll
+    for (int e = 0; e < T::SLOTS; e++) if (slot_match(b, e, key)) return slot_row(b, e, key);
+    if (slot_empty(b, T::SLOTS - 1, key)) return ROW_NONE;        // bucket not full: the sequence ends here
+    b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
+  }
+}
+// number of matches of `key` (duplicates): scan to the first non-full bucket
+template <typename K>
+__device__ __forceinline__ uint32_t finish_probe_count(const char* __restrict__ body, uint64_t n_pairs, K key, uint64_t pair, uint32_t half, Bucket b) {
+  using T = KeyTraits<K>;
+  uint32_t c = 0;
+  for (uint32_t t = 0;; ) {
+    #pragma unroll
+    for (int e = 0; e < T::SLOTS; e++) c += slot_match(b, e, key);
+    if (slot_empty(b, T::SLOTS - 1, key)) return c;
+    b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
+  }
+}
+
 template <typename K, bool VEC>
-__device__ __forceinline__ void load_tile_keys(const K* __restrict__ S, int64_t nS, int64_t tile_base, uint64_t pol,
-                                               K (&key)[VECS_PER_THREAD * KeyTraits<K>::KEYS_PER_VEC]) {
-  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
-  #pragma unroll
-  for (int v = 0; v < VECS_PER_THREAD; v++) {
-    const int64_t i0 = tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV;
-    if (VEC && i0 + KPV <= nS) {
-      int4 x = ld_stream_v4(S + i0, pol);
-      memcpy(&key[v * KPV], &x, 16);
+__global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
+                                                         const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
+                                                         unsigned long long* __restrict__ chunk_totals) {
+  using T = KeyTraits<K>;
+  constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
+  __shared__ unsigned long long red[33];
+  const uint32_t mode = hdr->mode;
+  const bool dups = hdr->has_dups != 0;
+  const uint64_t n_pairs = hdr->n_pairs;
+  const long long kmin = hdr->kmin;
+  const unsigned long long drange = hdr->dense_range;
+  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
+  unsigned long long cnt = 0;
+
+  #pragma unroll 1
+  for (int tile = 0; tile < CHUNK_TILES; tile++) {
+    const int64_t tile_base = chunk_base + (int64_t)tile * TILE;
+    if (tile_base >= nS) break;
+    K key[KPT];
+    #pragma unroll
+    for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
+    uint32_t m[KPT];
+    if (mode == MODE_DENSE) {
+      // direct addressing: one 4-byte load per in-range key, all KPT in flight
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
+        m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
+      }
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) cnt += (m[k] != ROW_NONE);
     } else {
       #pragma unroll
-      for (int e = 0; e < KPV; e++) key[v * KPV + e] = (i0 + e < nS) ? S[i0 + e] : K(0);
-    }
-  }
-}
-
-// u32 per probe row, same (vec, thread, elem) layout as the keys; the cache is padded to whole tiles.
-template <int KPV>
-__device__ __forceinline__ void store_tile_u32(uint32_t* __restrict__ dst, int64_t tile_base, uint64_t pol, const uint32_t (&m)[VECS_PER_THREAD * KPV]) {
-  #pragma unroll
-  for (int v = 0; v < VECS_PER_THREAD; v++) {
-    const int64_t i0 = tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV;
-    if (KPV == 4) st_stream_v4(dst + i0, make_int4(m[v * 4], m[v * 4 + 1], m[v * 4 + 2], m[v * 4 + 3]), pol);
-    else { uint2 x = make_uint2(m[v * KPV], m[v * KPV + 1]); *reinterpret_cast<uint2*>(dst + i0) = x; }
-  }
-}
-template <int KPV>
-__device__ __forceinline__ void load_tile_u32(const uint32_t* __restrict__ src, int64_t tile_base, uint64_t pol, uint32_t (&m)[VECS_PER_THREAD * KPV]) {
-  #pragma unroll
-  for (int v = 0; v < VECS_PER_THREAD; v++) {
-    const int64_t i0 = tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV;
-    if (KPV == 4) { int4 x = ld_stream_v4(src + i0, pol); m[v * 4] = x.x; m[v * 4 + 1] = x.y; m[v * 4 + 2] = x.z; m[v * 4 + 3] = x.w; }
-    else { uint2 x = *reinterpret_cast<const uint2*>(src + i0); m[v * KPV] = x.x; m[v * KPV + 1] = x.y; }
-  }
-}
-
-template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const typename KeyTraits<K>::Slot* __restrict__ slots,
-                                                         const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
-                                                         unsigned long long* __restrict__ tile_totals) {
-  using T = KeyTraits<K>;
-  using Slot = typename T::Slot;
-  constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
-  __shared__ unsigned long long red[32];
-  const uint64_t n_slots = hdr->n_slots;
-  const bool dups = hdr->has_dups != 0;
-  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
-  const int64_t tile_base = (int64_t)blockIdx.x * TILE;
-
-  K key[KPT];
-  load_tile_keys<K, VEC>(S, nS, tile_base, pol_s, key);
-  bool valid[KPT];
-  #pragma unroll
-  for (int k = 0; k < KPT; k++) valid[k] = tile_base + ((int64_t)(k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV) < nS;
-
-  uint32_t m[KPT];
-  unsigned long long cnt = 0;
-  uint64_t idx[KPT];
-  Slot s[KPT];
-  #pragma unroll
-  for (int k = 0; k < KPT; k++) idx[k] = T::index(key[k], n_slots);
-  #pragma unroll
-  for (int k = 0; k < KPT; k++) if (valid[k]) s[k] = ld_table(slots + idx[k], pol_t);   // KPT independent loads in flight
-
-  if (!dups) {
-    #pragma unroll
-    for (int k = 0; k < KPT; k++) {
-      uint32_t r = ROW_NONE;
-      if (valid[k]) {
-        Slot cur = s[k]; uint64_t i = idx[k];
-        while (!slot_empty(cur)) {
-          if (slot_key_eq(cur, key[k])) { r = slot_row(cur); break; }       // unique build: first match is the only match
-          if (++i == n_slots) i = 0;
-          cur = ld_table(slots + i, pol_t);
+      for (int v = 0; v < VECS_PER_THREAD; v++) {
+        uint64_t pair[KPV]; uint32_t half[KPV]; Bucket b[KPV]; bool valid[KPV];
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) {
+          valid[e] = elem_index<KPV>(tile_base, v * KPV + e) < nS;
+          T::home(key[v * KPV + e], n_pairs, pair[e], half[e]);
+        }
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) if (valid[e]) b[e] = ld_bucket(body + probe_bucket(pair[e], half[e], 0, n_pairs) * 32);   // KPV buckets in flight
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) {
+          const int k = v * KPV + e;
+          if (!dups) { m[k] = valid[e] ? finish_probe_unique<K>(body, n_pairs, key[k], pair[e], half[e], b[e]) : ROW_NONE; cnt += (m[k] != ROW_NONE); }
+          else       { m[k] = valid[e] ? finish_probe_count<K>(body, n_pairs, key[k], pair[e], half[e], b[e]) : 0u; cnt += m[k]; }
         }
       }
-      m[k] = r;
-      cnt += (r != ROW_NONE);
     }
-  } else {
     #pragma unroll
-    for (int k = 0; k < KPT; k++) {
-      uint32_t c = 0;
-      if (valid[k]) {
-        Slot cur = s[k]; uint64_t i = idx[k];
-        while (!slot_empty(cur)) {                                          // duplicates: scan to the first EMPTY
-          c += slot_key_eq(cur, key[k]);
-          if (++i == n_slots) i = 0;
-          cur = ld_table(slots + i, pol_t);
-        }
-      }
-      m[k] = c;
-      cnt += c;
-    }
+    for (int v = 0; v < VECS_PER_THREAD; v++) store_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
   }
-  store_tile_u32<KPV>(mcache, tile_base, pol_s, m);
-
-  // block reduction of cnt -> tile total
-  cnt = warp_reduce_sum(cnt);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    unsigned long long v = threadIdx.x < (BLOCK_THREADS / 32) ? red[threadIdx.x] : 0ULL;
-    v = warp_reduce_sum(v);
-    if (threadIdx.x == 0) tile_totals[blockIdx.x] = v;
-  }
+  cnt = block_reduce_sum(cnt, red);
+  if (threadIdx.x == 0) chunk_totals[blockIdx.x] = cnt;
 }
 
 // =========================================================================================================
-// K3  scan of tile totals -> exclusive tile offsets, total at [ntiles]      (replaces join_v1.mlir:371-420)
+// K3  scan of chunk totals -> exclusive chunk offsets, total at [nchunks]      (replaces join_v1.mlir:371-420)
 // =========================================================================================================
 constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 8;
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned long long* __restrict__ t, int64_t ntiles) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunks(unsigned long long* __restrict__ t, int64_t n) {
   __shared__ unsigned long long sm[33];
   unsigned long long running = 0;
-  for (int64_t base = 0; base < ntiles; base += (int64_t)SCAN_THREADS * SCAN_ITEMS) {
+  for (int64_t base = 0; base < n; base += (int64_t)SCAN_THREADS * SCAN_ITEMS) {
     const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_ITEMS;
     unsigned long long v[SCAN_ITEMS], sum = 0;
     #pragma unroll
-    for (int e = 0; e < SCAN_ITEMS; e++) { v[e] = (i0 + e < ntiles) ? t[i0 + e] : 0ULL; sum += v[e]; }
+    for (int e = 0; e < SCAN_ITEMS; e++) { v[e] = (i0 + e < n) ? t[i0 + e] : 0ULL; sum += v[e]; }
     unsigned long long total, ex = block_exclusive_scan(sum, sm, &total);
     unsigned long long acc = running + ex;
     #pragma unroll
-    for (int e = 0; e < SCAN_ITEMS; e++) { if (i0 + e < ntiles) t[i0 + e] = acc; acc += v[e]; }
+    for (int e = 0; e < SCAN_ITEMS; e++) { if (i0 + e < n) t[i0 + e] = acc; acc += v[e]; }
     running += total;
   }
-  if (threadIdx.x == 0) t[ntiles] = running;
+  if (threadIdx.x == 0) t[n] = running;
 }
 
 cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, cudaStream_t stream) {
   ScratchView sv = scratch_view(scratch, nS, key_bytes);
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
-  const char* slots = reinterpret_cast<const char*>(table) + HEADER_BYTES;
-  if (sv.ntiles > 0) {
-    const unsigned grid = (unsigned)sv.ntiles;
+  const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
+  if (sv.nchunks > 0) {
+    const unsigned grid = (unsigned)sv.nchunks;
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
     if (key_bytes == 4) {
-      auto* s = reinterpret_cast<const unsigned long long*>(slots);
-      if (vec) k_count<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets);
-      else     k_count<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets);
+      if (vec) k_count<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      else     k_count<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
     } else {
-      auto* s = reinterpret_cast<const ulonglong2*>(slots);
-      if (vec) k_count<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets);
-      else     k_count<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets);
+      if (vec) k_count<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      else     k_count<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
     }
   }
-  k_scan_tiles<<<1, SCAN_THREADS, 0, stream>>>(sv.tile_offsets, sv.ntiles);
+  k_scan_chunks<<<1, SCAN_THREADS, 0, stream>>>(sv.chunk_offsets, sv.nchunks);
   return cudaGetLastError();
 }
 
@@ -283,75 +369,86 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
 // K4  write
 // =========================================================================================================
 template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S, int64_t nS, const typename KeyTraits<K>::Slot* __restrict__ slots,
+__global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache,
-                                                         const unsigned long long* __restrict__ tile_offsets,
+                                                         const unsigned long long* __restrict__ chunk_offsets,
                                                          int32_t* __restrict__ outR, int32_t* __restrict__ outS,
                                                          const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
   using T = KeyTraits<K>;
-  using Slot = typename T::Slot;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
-  __shared__ uint32_t stage_r[TILE];
-  __shared__ uint32_t stage_s[TILE];
+  __shared__ uint32_t warp_totals[2][BLOCK_THREADS / 32];
   __shared__ unsigned long long scan_sm[33];
   const bool dups = hdr->has_dups != 0;
-  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
-  const int64_t tile_base = (int64_t)blockIdx.x * TILE;
-  const unsigned long long out_base = tile_offsets[blockIdx.x];
-  const unsigned long long tile_total = tile_offsets[blockIdx.x + 1] - out_base;
-  if (tile_total == 0) return;                                              // uniform across the block
+  const uint64_t pol_s = policy_evict_first();
+  const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
+  unsigned long long out_base = chunk_offsets[blockIdx.x];
+  if (chunk_offsets[blockIdx.x + 1] == out_base) return;                     // nothing to emit for this chunk (uniform)
 
-  uint32_t m[KPT];
-  load_tile_u32<KPV>(mcache, tile_base, pol_s, m);
+  #pragma unroll 1
+  for (int tile = 0; tile < CHUNK_TILES; tile++) {
+    const int64_t tile_base = chunk_base + (int64_t)tile * TILE;
+    if (tile_base >= nS) break;
+    uint32_t m[KPT];
+    #pragma unroll
+    for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
 
-  if (!dups) {
-    // unique build: the cache already holds the build row; compact through shared memory, then one coalesced stream
-    uint32_t c = 0;
-    #pragma unroll
-    for (int k = 0; k < KPT; k++) c += (m[k] != ROW_NONE);
-    uint32_t total32;
-    uint32_t w = block_exclusive_scan<uint32_t>(c, reinterpret_cast<uint32_t*>(scan_sm), &total32);
-    #pragma unroll
-    for (int k = 0; k < KPT; k++) {
-      if (m[k] != ROW_NONE) {
-        const int64_t j = tile_base + ((int64_t)(k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV);
-        stage_r[w] = m[k];
-        stage_s[w] = probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j;
-        w++;
+    if (!dups) {
+      // unique build: the cache already holds the build row. Output order is free (the result is a multiset,
+      // shared.cpp:168-171), so every warp owns one contiguous output range and compacts with ballots: no staging
+      // buffer, one barrier per tile, and each store instruction writes one contiguous run of up to 128 bytes.
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      unsigned mask[KPT];
+      uint32_t wtotal = 0;
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, m[k] != ROW_NONE); wtotal += __popc(mask[k]); }
+      uint32_t* wt = warp_totals[tile & 1];
+      if (lane == 0) wt[warp] = wtotal;
+      __syncthreads();
+      uint32_t wbase = 0, ttotal = 0;
+      #pragma unroll
+      for (int w = 0; w < BLOCK_THREADS / 32; w++) { const uint32_t x = wt[w]; wbase += w < warp ? x : 0u; ttotal += x; }
+      unsigned long long o = out_base + wbase;
+      const unsigned lt = (1u << lane) - 1u;
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        if (m[k] != ROW_NONE) {
+          const int64_t j = elem_index<KPV>(tile_base, k);
+          const unsigned long long dst = o + __popc(mask[k] & lt);
+          st_stream_u32(outR + dst, m[k], pol_s);
+          st_stream_u32(outS + dst, probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j, pol_s);
+        }
+        o += __popc(mask[k]);
       }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < total32; i += BLOCK_THREADS) {
-      st_stream_u32(outR + out_base + i, stage_r[i], pol_s);
-      st_stream_u32(outS + out_base + i, stage_s[i], pol_s);
-    }
-  } else {
-    // duplicates: the cache holds per-row match counts; scan them, then walk the probe sequence once and emit
-    K key[KPT];
-    load_tile_keys<K, VEC>(S, nS, tile_base, pol_s, key);
-    const uint64_t n_slots = hdr->n_slots;
-    unsigned long long c = 0;
-    #pragma unroll
-    for (int k = 0; k < KPT; k++) c += m[k];
-    unsigned long long total64;
-    unsigned long long w = out_base + block_exclusive_scan<unsigned long long>(c, scan_sm, &total64);
-    #pragma unroll
-    for (int k = 0; k < KPT; k++) {
-      uint32_t left = m[k];
-      if (left) {
-        const int64_t j = tile_base + ((int64_t)(k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV);
-        const uint32_t prow = probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j;
-        uint64_t i = T::index(key[k], n_slots);
-        while (left) {
-          Slot cur = ld_table(slots + i, pol_t);
-          if (slot_key_eq(cur, key[k]) && !slot_empty(cur)) {
-            outR[w] = (int32_t)slot_row(cur);
-            outS[w] = (int32_t)prow;
-            w++; left--;
+      out_base += ttotal;
+    } else {
+      // duplicates: the cache holds per-row match counts; scan them, then walk the probe sequence once and emit
+      K key[KPT];
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
+      const uint64_t n_pairs = hdr->n_pairs;
+      unsigned long long c = 0;
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) c += m[k];
+      unsigned long long total64;
+      unsigned long long w = out_base + block_exclusive_scan<unsigned long long>(c, scan_sm, &total64);
+      #pragma unroll 1
+      for (int k = 0; k < KPT; k++) {
+        uint32_t left = m[k];
+        if (left) {
+          const int64_t j = elem_index<KPV>(tile_base, k);
+          const uint32_t prow = probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j;
+          uint64_t pair; uint32_t half;
+          T::home(key[k], n_pairs, pair, half);
+          for (uint32_t t = 0; left; t++) {
+            const Bucket b = ld_bucket(body + probe_bucket(pair, half, t, n_pairs) * 32);
+            #pragma unroll
+            for (int e = 0; e < T::SLOTS; e++) {
+              if (slot_match(b, e, key[k])) { outR[w] = (int32_t)slot_row(b, e, key[k]); outS[w] = (int32_t)prow; w++; left--; }
+            }
           }
-          if (++i == n_slots) i = 0;
         }
       }
+      out_base += total64;
     }
   }
 }
@@ -359,19 +456,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
 cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
                         int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
   ScratchView sv = scratch_view(const_cast<void*>(scratch), nS, key_bytes);
-  if (sv.ntiles == 0) return cudaSuccess;
+  if (sv.nchunks == 0) return cudaSuccess;
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
-  const char* slots = reinterpret_cast<const char*>(table) + HEADER_BYTES;
-  const unsigned grid = (unsigned)sv.ntiles;
+  const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
+  const unsigned grid = (unsigned)sv.nchunks;
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   if (key_bytes == 4) {
-    auto* s = reinterpret_cast<const unsigned long long*>(slots);
-    if (vec) k_write<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets, outR, outS, probe_payload, probe_row_base);
-    else     k_write<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets, outR, outS, probe_payload, probe_row_base);
+    if (vec) k_write<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
+    else     k_write<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
   } else {
-    auto* s = reinterpret_cast<const ulonglong2*>(slots);
-    if (vec) k_write<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets, outR, outS, probe_payload, probe_row_base);
-    else     k_write<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, s, hdr, sv.mcache, sv.tile_offsets, outR, outS, probe_payload, probe_row_base);
+    if (vec) k_write<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
+    else     k_write<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
   }
   return cudaGetLastError();
 }

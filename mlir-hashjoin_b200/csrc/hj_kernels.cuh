@@ -6,31 +6,35 @@
 
 namespace hj {
 
-constexpr int HEADER_BYTES = 256;              // table workspace = header + slots
+constexpr int HEADER_BYTES = 256;              // table workspace = header + body
 
 // tile geometry shared by count/scan/write (must agree between the two probe passes)
 constexpr int BLOCK_THREADS = 256;
 constexpr int VECS_PER_THREAD = 2;
+constexpr int CHUNK_TILES = 8;                 // consecutive tiles one CTA owns; the scan runs over chunks
 __host__ __device__ constexpr int keys_per_vec(int key_bytes) { return 16 / key_bytes; }
 __host__ __device__ constexpr int tile_keys(int key_bytes) { return BLOCK_THREADS * VECS_PER_THREAD * keys_per_vec(key_bytes); }
+__host__ __device__ constexpr int chunk_keys(int key_bytes) { return CHUNK_TILES * tile_keys(key_bytes); }
 
-int64_t preferred_slots(int64_t n_rows);
+int64_t preferred_pairs(int64_t n_rows, int key_bytes);
 int64_t table_bytes(int64_t n_rows, int key_bytes);
 int64_t scratch_bytes(int64_t n_probe, int key_bytes);
-int64_t num_tiles(int64_t n_probe, int key_bytes);
+int64_t num_chunks(int64_t n_probe, int key_bytes);
 
-// Scratch layout (device): [ match cache: u32 x round_up(n_probe, tile) ][ tile offsets: u64 x (ntiles + 1) ]
+// Scratch layout (device): [ match cache: u32 x round_up(n_probe, chunk) ][ chunk offsets: u64 x (nchunks + 1) ]
 struct ScratchView {
   uint32_t* mcache;
-  unsigned long long* tile_offsets;   // after scan: exclusive offsets; [ntiles] = total
-  int64_t ntiles;
+  unsigned long long* chunk_offsets;  // after scan: exclusive offsets; [nchunks] = total
+  int64_t nchunks;
 };
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
+
+void set_allow_dense(int on);   // debug/bench switch: 0 forces the hash layout even for dense key ranges
 
 // K0+K1: clear + build.  payload == nullptr -> row id = row_base + i  (join_v1.mlir:232 stores the thread index).
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
                         void* table, int64_t table_bytes_, cudaStream_t stream);
-// K2+K3: count + scan (async).  Total lands in tile_offsets[ntiles].
+// K2+K3: count + scan (async).  Total lands in chunk_offsets[nchunks].
 cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, cudaStream_t stream);
 // K4: write pairs.
 cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,

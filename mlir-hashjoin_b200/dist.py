@@ -1,0 +1,84 @@
+"""Multi-GPU plans (one process per GPU, torch.distributed over NCCL/NVLink). The reference has none of this
+(projectDescription.md:24 lists partitioned joins as left out); SURVEY.md section 8e defines the two plans.
+
+broadcast build   probe rows range-sharded, build relation replicated: one broadcast of the build columns, then every
+                  rank runs the single-GPU join on its shard with probe_row = shard base + local row. No exchange of S.
+radix partition   both relations partitioned on an independent key hash by K5 (hjPartition), count matrix all-gathered,
+                  (key, global row id) exchanged with a variable-count all-to-all, local join with payload columns.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, join
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row range [lo, hi) of rank ``rank``: sizes differ by at most one row."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_build_join(build_keys: torch.Tensor, probe_shard: torch.Tensor, probe_row_base: int, src: int = 0,
+                         group=None, table: join.HashTable | None = None, replicated: bool = False):
+    """Every rank ends with the pairs of ITS probe rows; the global result is the concatenation (a multiset).
+    ``build_keys`` must be allocated at full size on every rank; its contents matter on ``src`` only unless
+    ``replicated`` says every rank already holds it."""
+    if not replicated and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(build_keys, src=src, group=group)
+    return join.hash_join(build_keys, probe_shard, table=table, probeRowBase=probe_row_base)
+
+
+def partition(keys: torch.Tensor, row_base: int, n_parts: int, rows: torch.Tensor | None = None):
+    """K5 on this rank's shard. Returns (keys_by_part, rows_by_part, offsets[n_parts+1] on the device)."""
+    lib = _lib.load()
+    kb = keys.element_size()
+    n = keys.numel()
+    out_keys = torch.empty_like(keys)
+    out_rows = torch.empty(n, dtype=torch.int32, device=keys.device)
+    offsets = torch.empty(n_parts + 1, dtype=torch.int64, device=keys.device)
+    ws = torch.empty(lib.hjPartitionWorkspaceBytes(n, n_parts), dtype=torch.uint8, device=keys.device)
+    rc = lib.hjPartition(keys.data_ptr(), None if rows is None else rows.data_ptr(), row_base & 0xFFFFFFFF, n, kb, n_parts,
+                         out_keys.data_ptr(), out_rows.data_ptr(), offsets.data_ptr(), ws.data_ptr(), ws.numel(),
+                         torch.cuda.current_stream().cuda_stream)
+    _lib.check_status(rc, "hjPartition")
+    return out_keys, out_rows, offsets
+
+
+@dataclass
+class ExchangePlan:
+    send_counts: list[int]       # rows this rank sends to each peer
+    recv_counts: list[int]       # rows this rank receives from each peer
+
+
+def exchange_plan(offsets: torch.Tensor, group=None) -> ExchangePlan:
+    """All-gather of the N x N count matrix (host-side plan for the variable-count all-to-all)."""
+    world = dist.get_world_size(group)
+    counts = (offsets[1:] - offsets[:-1]).to(torch.int64)
+    gathered = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(gathered, counts, group=group)
+    matrix = torch.stack(gathered).cpu()                       # matrix[src][dst]
+    rank = dist.get_rank(group)
+    return ExchangePlan(matrix[rank].tolist(), matrix[:, rank].tolist())
+
+
+def exchange(parts: torch.Tensor, plan: ExchangePlan, group=None) -> torch.Tensor:
+    """Variable-count all-to-all of a partition-ordered column. Works on any backend (NCCL on GPUs, gloo in CPU tests)."""
+    out = torch.empty(sum(plan.recv_counts), dtype=parts.dtype, device=parts.device)
+    dist.all_to_all_single(out, parts, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts, group=group)
+    return out
+
+
+def radix_join(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int, group=None):
+    """Radix-partitioned join of range-sharded relations. Returns this rank's (build_row, probe_row) pairs, global row ids."""
+    world = dist.get_world_size(group)
+    bk, br, bo = partition(build_shard, build_row_base, world)
+    pk, pr, po = partition(probe_shard, probe_row_base, world)
+    bplan, pplan = exchange_plan(bo, group), exchange_plan(po, group)
+    my_bk, my_br = exchange(bk, bplan, group), exchange(br, bplan, group)
+    my_pk, my_pr = exchange(pk, pplan, group), exchange(pr, pplan, group)
+    return join.hash_join(my_bk, my_pk, buildPayload=my_br, probePayload=my_pr)

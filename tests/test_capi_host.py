@@ -76,8 +76,9 @@ def test_timer_format(lib, capfd):
 
 
 def test_workspace_queries(lib):
-    assert lib.hjTableBytes(0, 4) >= 256 + 64 * 8
-    assert lib.hjTableBytes(1 << 24, 4) == 256 + (1 << 25) * 8
+    assert lib.hjTableBytes(0, 4) >= 256 + 64
+    assert lib.hjTableBytes(1 << 20, 4) == 256 + (1 << 21) * 8            # small table: load factor 0.5
+    assert lib.hjTableBytes(1 << 24, 4) == 256 + (5 << 22) * 8            # big table: load factor 0.8
     assert lib.hjTableBytes(1 << 20, 8) == 256 + (1 << 21) * 16
     assert lib.hjTableBytes(10, 5) < 0 and lib.hjScratchBytes(-1, 4) < 0
     assert lib.hashJoinTableBytes(1000) == lib.hjTableBytes(1000, 4)

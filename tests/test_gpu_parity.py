@@ -10,6 +10,15 @@ from oracle.binding import sorted_pairs
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["auto", "hash"])
+def layout(request, lib):
+    """Every parity case runs twice: with the direct-address layout allowed (dense key ranges take it, and fall back
+    to the hash layout on a duplicate) and with the bucketised hash layout forced."""
+    lib.hjSetAllowDense(1 if request.param == "auto" else 0)
+    yield request.param
+    lib.hjSetAllowDense(1)
+
+
 def _join_np(R, S, cuda):
     import torch
     from mlir_hashjoin_b200 import join
