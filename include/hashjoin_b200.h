@@ -135,7 +135,8 @@ int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64
  * hOutR/hOutS are non-NULL and capacity >= result size. Synchronous. */
 int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes,
                    int32_t* hOutR, int32_t* hOutS, int64_t capacity);
-/* 1 (default): builds whose key range is at most 4x the row count use a direct-address table; 0 forces the hash layout. */
+/* 1 (default): builds whose key range is at most 4x the row count use a direct-address table; 0 forces the hash layout;
+ * 2 additionally lets a unique, gap-free key range count by range test alone (experimental). */
 void hjSetAllowDense(int32_t on);
 const char* hjLastErrorString(void);
 const char* hjVersion(void);

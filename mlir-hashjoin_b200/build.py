@@ -43,7 +43,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         subprocess.run(cmd, check=True)
     drv = CSRC / "host_driver.cpp"
     if drv.exists() and (force or _stale(DRIVER, [drv, LIB])):
-        cmd = [_nvcc(), "-O2", "-std=c++17", "-o", str(DRIVER), str(drv), "-L" + str(LIB.parent), "-lhashjoin_b200",
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-o", str(DRIVER), str(drv), "-L" + str(LIB.parent), "-lhashjoin_b200",
                "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
         if verbose:
             print(" ".join(cmd))

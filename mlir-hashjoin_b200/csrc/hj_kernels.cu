@@ -103,9 +103,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_clear(TableHeader* hdr, int4*
   for (unsigned long long i = blockIdx.x * (unsigned long long)BLOCK_THREADS + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * BLOCK_THREADS) body[i] = ff;
 }
 
-__global__ void k_fallback_prepare(TableHeader* hdr) {
+// count_by_range: experimental (hjSetAllowDense(2)). A unique build whose keys are exactly [kmin, kmax] lets the count pass
+// skip the table (a probe key matches iff it is in range) and moves the single lookup per row into the write pass.
+// Measured on C2 it trades 0.9 ms of count for 1.0 ms of write (profiles/README.md), so it is off by default.
+__global__ void k_fallback_prepare(TableHeader* hdr, int count_by_range) {
   if (hdr->need_fallback) { hdr->mode = MODE_HASH; hdr->dense_range = 0; hdr->has_dups = 0; }
-  else if (hdr->mode == MODE_DENSE && hdr->dense_range == hdr->n_rows) hdr->all_present = 1;   // unique + range == rows
+  else if (count_by_range && hdr->mode == MODE_DENSE && hdr->dense_range == hdr->n_rows) hdr->all_present = 1;
 }
 
 template <typename K, bool VEC>
@@ -199,7 +202,7 @@ static void launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32
   if (nR == 0) return;
   if (vec) k_build_dense<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
   else     k_build_dense<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
-  k_fallback_prepare<<<1, 1, 0, stream>>>(hdr);
+  k_fallback_prepare<<<1, 1, 0, stream>>>(hdr, g_allow_dense == 2);
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
   if (vec) k_build_hash<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
   else     k_build_hash<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   __shared__ unsigned long long red[33];
   const uint32_t mode = hdr->mode;
   const bool dups = hdr->has_dups != 0;
+  const bool all_present = hdr->all_present != 0;
   const uint64_t n_pairs = hdr->n_pairs;
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
@@ -290,6 +294,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
     #pragma unroll
     for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
     uint32_t m[KPT];
+    if (all_present) {
+      // unique build whose keys are exactly [kmin, kmax]: a probe key matches iff it is in range. No table access and
+      // no match cache here; the write pass does the (single) lookup per matching row.
+      #pragma unroll
+      for (int k = 0; k < KPT; k++)
+        cnt += ((unsigned long long)((long long)key[k] - kmin) < drange && elem_index<KPV>(tile_base, k) < nS);
+      continue;
+    }
     if (mode == MODE_DENSE) {
       // direct addressing: one 4-byte load per in-range key, all KPT in flight
       #pragma unroll
@@ -379,7 +391,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   __shared__ uint32_t warp_totals[2][BLOCK_THREADS / 32];
   __shared__ unsigned long long scan_sm[33];
   const bool dups = hdr->has_dups != 0;
-  const uint64_t pol_s = policy_evict_first();
+  const bool all_present = hdr->all_present != 0;
+  const long long kmin = hdr->kmin;
+  const unsigned long long drange = hdr->dense_range;
+  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
   const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
   unsigned long long out_base = chunk_offsets[blockIdx.x];
   if (chunk_offsets[blockIdx.x + 1] == out_base) return;                     // nothing to emit for this chunk (uniform)
@@ -389,8 +404,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
     const int64_t tile_base = chunk_base + (int64_t)tile * TILE;
     if (tile_base >= nS) break;
     uint32_t m[KPT];
-    #pragma unroll
-    for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
+    if (all_present) {
+      K key[KPT];
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
+        m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
+      }
+    } else {
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
+    }
 
     if (!dups) {
       // unique build: the cache already holds the build row. Output order is free (the result is a multiset,
