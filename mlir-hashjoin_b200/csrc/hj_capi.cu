@@ -222,28 +222,67 @@ int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64
   return HJ_OK;
 }
 
+// Host buffers in, host pairs out. The probe relation moves in chunks so that the three PCIe/compute legs overlap:
+//   stream IN : H2D of probe chunk i+1 ...            (all chunk copies are queued up front, one event each)
+//   stream CMP: count(i) -> 8-byte readback -> write(i) at the running output offset
+//   stream OUT: D2H of the pairs of chunk i           (PCIe is full duplex: runs against the H2D of later chunks)
+// Pairs are appended chunk by chunk (probe_row = chunk base + local row), which is a valid order for a multiset result.
 int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes, int32_t* hOutR, int32_t* hOutS, int64_t capacity) {
   if (!key_ok(keyBytes) || nR < 0 || nS < 0 || (nR > 0 && !hR) || (nS > 0 && !hS)) return fail(HJ_ERR_ARG, "hjJoinHost", "bad argument");
   std::lock_guard<std::mutex> lk(g_mu);
-  const int64_t tb = hj::table_bytes(nR, keyBytes), sb = hj::scratch_bytes(nS, keyBytes);
+  const int64_t chunk_rows = (int64_t)1 << 24;                        // multiple of the kernel chunk (16 384 / 8 192 rows)
+  const int64_t nch = (nS + chunk_rows - 1) / chunk_rows;
+  const bool want_out = hOutR && hOutS && capacity > 0;
+  const int64_t tb = hj::table_bytes(nR, keyBytes), sb = hj::scratch_bytes(std::min(nS, chunk_rows), keyBytes);
   HJ_CUDA("hjJoinHost", g_hR.ensure(std::max<int64_t>(nR * keyBytes, 16)));
   HJ_CUDA("hjJoinHost", g_hS.ensure(std::max<int64_t>(nS * keyBytes, 16)));
   HJ_CUDA("hjJoinHost", g_hT.ensure(tb));
   HJ_CUDA("hjJoinHost", g_hSc.ensure(sb));
-  cudaStream_t st = nullptr;
-  if (nR) HJ_CUDA("hjJoinHost", cudaMemcpyAsync(g_hR.p, hR, (size_t)nR * keyBytes, cudaMemcpyHostToDevice, st));   // join_v1.mlir:558-561
-  if (nS) HJ_CUDA("hjJoinHost", cudaMemcpyAsync(g_hS.p, hS, (size_t)nS * keyBytes, cudaMemcpyHostToDevice, st));
-  int32_t rc = hjBuild(g_hR.p, nR, keyBytes, nullptr, 0, g_hT.p, tb, st);
+  if (want_out) { HJ_CUDA("hjJoinHost", g_hOr.ensure(capacity * 4)); HJ_CUDA("hjJoinHost", g_hOs.ensure(capacity * 4)); }
+  static cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  static std::vector<cudaEvent_t> ev_in;
+  static cudaEvent_t ev_w = nullptr;
+  if (!s_in) {
+    HJ_CUDA("hjJoinHost", cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    HJ_CUDA("hjJoinHost", cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+    HJ_CUDA("hjJoinHost", cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    HJ_CUDA("hjJoinHost", cudaEventCreateWithFlags(&ev_w, cudaEventDisableTiming));
+  }
+  while ((int64_t)ev_in.size() < nch) { cudaEvent_t e; HJ_CUDA("hjJoinHost", cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev_in.push_back(e); }
+
+  const char* hSb = reinterpret_cast<const char*>(hS);
+  char* dSb = reinterpret_cast<char*>(g_hS.p);
+  if (nR) HJ_CUDA("hjJoinHost", cudaMemcpyAsync(g_hR.p, hR, (size_t)nR * keyBytes, cudaMemcpyHostToDevice, s_cmp));   // join_v1.mlir:558-561
+  int32_t rc = hjBuild(g_hR.p, nR, keyBytes, nullptr, 0, g_hT.p, tb, s_cmp);
   if (rc != HJ_OK) return rc;
-  int64_t total = hjCount(g_hS.p, nS, keyBytes, g_hT.p, g_hSc.p, sb, st);
-  if (total <= 0 || !hOutR || !hOutS || capacity < total) return total;                                           // :600-601
-  HJ_CUDA("hjJoinHost", g_hOr.ensure(total * 4));
-  HJ_CUDA("hjJoinHost", g_hOs.ensure(total * 4));
-  rc = hjWrite(g_hS.p, nS, keyBytes, g_hT.p, g_hSc.p, (int32_t*)g_hOr.p, (int32_t*)g_hOs.p, nullptr, 0, st);
-  if (rc != HJ_OK) return rc;
-  HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutR, g_hOr.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));          // :614-615
-  HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutS, g_hOs.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-  HJ_CUDA("hjJoinHost", cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < nch; i++) {
+    const int64_t off = i * chunk_rows, n = std::min(chunk_rows, nS - off);
+    HJ_CUDA("hjJoinHost", cudaMemcpyAsync(dSb + off * keyBytes, hSb + off * keyBytes, (size_t)n * keyBytes, cudaMemcpyHostToDevice, s_in));
+    HJ_CUDA("hjJoinHost", cudaEventRecord(ev_in[(size_t)i], s_in));
+  }
+  int64_t total = 0;
+  bool overflow = !want_out;
+  for (int64_t i = 0; i < nch; i++) {
+    const int64_t off = i * chunk_rows, n = std::min(chunk_rows, nS - off);
+    HJ_CUDA("hjJoinHost", cudaStreamWaitEvent(s_cmp, ev_in[(size_t)i], 0));
+    const int64_t c = hjCount(dSb + off * keyBytes, n, keyBytes, g_hT.p, g_hSc.p, sb, s_cmp);                         // :591 (per chunk)
+    if (c < 0) return c;
+    if (!overflow && total + c > capacity) overflow = true;
+    if (!overflow && c > 0) {                                                                                        // :600-615
+      int32_t* dR = reinterpret_cast<int32_t*>(g_hOr.p) + total;
+      int32_t* dS = reinterpret_cast<int32_t*>(g_hOs.p) + total;
+      rc = hjWrite(dSb + off * keyBytes, n, keyBytes, g_hT.p, g_hSc.p, dR, dS, nullptr, (uint32_t)off, s_cmp);
+      if (rc != HJ_OK) return rc;
+      HJ_CUDA("hjJoinHost", cudaEventRecord(ev_w, s_cmp));
+      HJ_CUDA("hjJoinHost", cudaStreamWaitEvent(s_out, ev_w, 0));
+      HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutR + total, dR, (size_t)c * 4, cudaMemcpyDeviceToHost, s_out));
+      HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutS + total, dS, (size_t)c * 4, cudaMemcpyDeviceToHost, s_out));
+    }
+    total += c;
+  }
+  HJ_CUDA("hjJoinHost", cudaStreamSynchronize(s_in));
+  HJ_CUDA("hjJoinHost", cudaStreamSynchronize(s_cmp));
+  HJ_CUDA("hjJoinHost", cudaStreamSynchronize(s_out));
   return total;
 }
 

@@ -234,6 +234,12 @@ def test_join_host_e2e(lib, cuda, oracle):
     _assert_parity(oracle, R, S, a.numpy(), b.numpy())
     hR, hS, ok = join.main(torch.from_numpy(R), torch.from_numpy(S))
     assert ok == 1 and hR.numel() == n
+    # more than one 2^24-row probe chunk: the H2D / join / D2H pipeline appends chunk results at a running offset
+    S2 = rng.integers(0, 60000, (1 << 24) + 100003).astype(np.int32)
+    a, b, n2 = join.join_host(torch.from_numpy(R), torch.from_numpy(S2))
+    oa, ob = oracle.join(R, S2, threads=0)
+    assert n2 == oa.size and oracle.pair_digest(a.numpy(), b.numpy()) == oracle.pair_digest(oa, ob)
+    assert lib.hjJoinHost(R.ctypes.data, R.size, S2.ctypes.data, S2.size, 4, a.data_ptr(), b.data_ptr(), 1000) == n2   # too small: size only
 
 
 def test_generators_bit_identical(lib, cuda, oracle):
@@ -325,7 +331,8 @@ def test_cpp_host_driver_main(lib, cuda):
     for argv in ([], ["12", "12", "5", "4"], ["100000", "400000", "1000", "50000"]):
         r = subprocess.run([str(DRIVER), *argv], capture_output=True, text=True, env=env, timeout=120)
         assert r.returncode == 0, r.stdout + r.stderr
-        assert len(re.findall(r"For \d+, time taken: \d+ microseconds", r.stdout)) == 4
         vals = re.findall(r"^\[(-?\d+)\]$", r.stdout, flags=re.M)
         assert len(vals) == 2 and vals[1] == "1", r.stdout
+        # init, build, count always print; probe only when the result is not empty (join_v1.mlir:600-601)
+        assert len(re.findall(r"For \d+, time taken: \d+ microseconds", r.stdout)) == (4 if int(vals[0]) else 3)
     assert int(vals[0]) > 0
