@@ -156,8 +156,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
   if (!key_ok(keyBytes) || nR < 0 || (nR > 0 && !dR) || !dTable) return fail(HJ_ERR_ARG, "hjBuild", "null pointer or bad key width");
   if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, "hjBuild", "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
   if (reinterpret_cast<uintptr_t>(dTable) & 15) return fail(HJ_ERR_ARG, "hjBuild", "table workspace must be 16-byte aligned");
-  if (tableBytes < hj::HEADER_BYTES + 64 || (tableBytes - hj::HEADER_BYTES) / 64 * (keyBytes == 4 ? 8 : 4) * 9 < nR * 10)
-    return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
+  if (tableBytes < hj::table_bytes(nR, keyBytes)) return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
   HJ_CUDA("hjBuild", hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, S_(stream)));
   return HJ_OK;
 }

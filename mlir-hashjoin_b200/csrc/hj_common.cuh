@@ -18,7 +18,7 @@ namespace hj {
 
 constexpr uint32_t ROW_NONE = 0xFFFFFFFFu;     // never a valid row id: EMPTY marker lives in the row half of a slot
 constexpr uint32_t HJ_MAGIC = 0x424A4833u;
-constexpr uint32_t MODE_HASH = 0, MODE_DENSE = 1;
+constexpr uint32_t MODE_HASH = 0, MODE_DENSE = 1, MODE_GROUP = 2;
 
 // Device-resident table header (first HEADER_BYTES of the table workspace). Written by the build kernels, read
 // (uniformly) by count/write, so no host round trip is needed to pick the layout.
@@ -35,6 +35,9 @@ struct TableHeader {
   unsigned long long dense_range; // kmax - kmin + 1 when dense
   unsigned long long body_bytes;  // capacity behind the header
   unsigned long long pairs_cap;   // pairs the caller's workspace can hold
+  unsigned long long rows_offset; // grouped layout: byte offset of the u32 row-id array inside the body
+  unsigned long long group_cursor;// grouped layout: bump allocator over the row-id array
+  unsigned long long n_groups;    // grouped layout: distinct build keys
 };
 static_assert(sizeof(TableHeader) <= HEADER_BYTES, "header too large");
 
@@ -152,6 +155,24 @@ __device__ __forceinline__ bool slot_claim(void* bp, Bucket& b, int e, int64_t k
                                      make_ulonglong2((unsigned long long)key, (unsigned long long)row));
   b.w[2 * e] = old.x; b.w[2 * e + 1] = old.y;
   return (uint32_t)old.y == ROW_NONE;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grouped layout (duplicate build keys): 16-byte slots { key:64 ; end_or_cursor:32 | count:32 }, two per bucket, plus
+// one u32 row-id array in which the rows of a key are contiguous: rows[end - count, end).  A probe is a unique-key
+// probe (stop at the first match or the first non-full bucket) whatever the multiplicity; i32 keys are sign-extended.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group_home(long long key, uint64_t n_pairs, uint64_t& pair, uint32_t& half) {
+  KeyTraits<int64_t>::home((int64_t)key, n_pairs, pair, half);
+}
+// payload word of the matching slot (low 32 = end offset, high 32 = count), or 0 when the key is absent
+__device__ __forceinline__ unsigned long long group_finish(const char* __restrict__ body, uint64_t n_pairs, long long key, uint64_t pair, uint32_t half, Bucket b) {
+  for (uint32_t t = 0;; ) {
+    if (b.w[0] == (unsigned long long)key && (uint32_t)b.w[1] != ROW_NONE) return b.w[1];
+    if (b.w[2] == (unsigned long long)key && (uint32_t)b.w[3] != ROW_NONE) return b.w[3];
+    if ((uint32_t)b.w[3] == ROW_NONE) return 0ULL;              // bucket not full: the sequence ends here
+    b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------

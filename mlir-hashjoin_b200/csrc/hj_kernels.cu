@@ -31,7 +31,13 @@ int64_t preferred_pairs(int64_t n_rows, int key_bytes) {
   if (pairs > small_cap) pairs = std::max(small_cap, (5 * n_rows / 4 + slots_per_pair - 1) / slots_per_pair);   // 0.8, never below 32 MB
   return pairs < 4 ? 4 : pairs;
 }
-int64_t table_bytes(int64_t n_rows, int key_bytes) { return HEADER_BYTES + preferred_pairs(n_rows, key_bytes) * 64; }
+// The workspace must also hold the grouped layout a build with duplicate keys is rebuilt into: a u32 row-id array plus
+// 16-byte slots at load factor <= 0.8 for up to n_rows distinct keys.
+int64_t table_bytes(int64_t n_rows, int key_bytes) {
+  const int64_t inline_bytes = preferred_pairs(n_rows, key_bytes) * 64;
+  const int64_t group_bytes = round_up(n_rows * 4, 64) + ((5 * n_rows / 4 + 3) / 4 + 4) * 64;
+  return HEADER_BYTES + std::max(inline_bytes, group_bytes);
+}
 int64_t num_chunks(int64_t n_probe, int key_bytes) {
   const int64_t c = chunk_keys(key_bytes);
   return (n_probe + c - 1) / c;
@@ -59,6 +65,7 @@ __global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned lon
   hdr->magic = HJ_MAGIC; hdr->key_bytes = key_bytes; hdr->mode = MODE_HASH; hdr->has_dups = 0; hdr->need_fallback = 0; hdr->all_present = 0;
   hdr->n_pairs = pairs; hdr->n_rows = n_rows; hdr->kmin = 0x7FFFFFFFFFFFFFFFLL; hdr->kmax = -0x7FFFFFFFFFFFFFFFLL - 1;
   hdr->dense_range = 0; hdr->body_bytes = body_bytes; hdr->pairs_cap = body_bytes / 64;
+  hdr->rows_offset = 0; hdr->group_cursor = 0; hdr->n_groups = 0;
 }
 
 template <typename K>
@@ -93,8 +100,10 @@ __global__ void k_decide(TableHeader* hdr, int allow_dense) {
 
 // fallback_pass == 0: clear what the decided layout needs. fallback_pass == 1: only after a dense build hit a duplicate.
 __global__ void __launch_bounds__(BLOCK_THREADS) k_clear(TableHeader* hdr, int4* body, int fallback_pass) {
-  if (fallback_pass) {
+  if (fallback_pass == 1) {
     if (!hdr->need_fallback) return;
+  } else if (fallback_pass == 2) {
+    if (hdr->mode != MODE_GROUP) return;
   }
   const bool dense = !fallback_pass && hdr->mode == MODE_DENSE;
   const unsigned long long bytes = dense ? ((hdr->dense_range * 4 + 15) & ~15ULL) : hdr->n_pairs * 64;
@@ -149,12 +158,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_dense(const K* __restri
 // occupant, which is final, so every earlier slot of the probe sequence has been compared with `key` by the time the
 // insert lands -> duplicate detection is exact (the later of two equal keys always sees the earlier one).
 template <typename K>
-__device__ __forceinline__ bool insert_one(char* body, uint64_t n_pairs, K key, uint32_t row) {
+__device__ __forceinline__ bool insert_one(char* body, uint64_t n_pairs, K key, uint32_t row, const volatile uint32_t* has_dups) {
   using T = KeyTraits<K>;
   uint64_t pair; uint32_t half;
   T::home(key, n_pairs, pair, half);
   bool dup = false;
   for (uint32_t t = 0;; t++) {
+    if (dup || (t >= 4 && *has_dups)) return true;             // duplicates known: this table is abandoned (grouped rebuild follows)
     char* bp = body + probe_bucket(pair, half, t, n_pairs) * 32;
     Bucket b = ld_bucket(bp);
     #pragma unroll
@@ -180,10 +190,98 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restric
   for (int e = 0; e < KPV; e++) {
     if (i0 + e < nR) {
       const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
-      dup |= insert_one<K>(body, n_pairs, key[e], row);
+      dup |= insert_one<K>(body, n_pairs, key[e], row, &hdr->has_dups);
     }
   }
   if (__ballot_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) atomicOr(&hdr->has_dups, 1u);
+}
+
+
+// ---- grouped rebuild (runs only when the inline build found duplicate keys) --------------------------------
+__global__ void k_group_prepare(TableHeader* hdr) {
+  if (!hdr->has_dups || hdr->mode != MODE_HASH) return;
+  const unsigned long long rows_bytes = (hdr->n_rows * 4 + 63) & ~63ULL;
+  if (hdr->body_bytes < rows_bytes + 256) return;                  // cannot happen with hjTableBytes-sized workspaces
+  hdr->mode = MODE_GROUP;
+  hdr->n_pairs = (hdr->body_bytes - rows_bytes) / 64;
+  hdr->rows_offset = hdr->n_pairs * 64;
+  hdr->group_cursor = 0; hdr->n_groups = 0;
+}
+
+// find-or-insert the (sign-extended) key; returns the address of the slot's payload word
+__device__ __forceinline__ unsigned long long* group_slot(char* body, uint64_t n_pairs, long long key, bool insert) {
+  uint64_t pair; uint32_t half;
+  group_home(key, n_pairs, pair, half);
+  for (uint32_t t = 0;; t++) {
+    char* bp = body + probe_bucket(pair, half, t, n_pairs) * 32;
+    Bucket b = ld_bucket(bp);
+    #pragma unroll
+    for (int e = 0; e < 2; e++) {
+      if ((uint32_t)b.w[2 * e + 1] == ROW_NONE) {
+        if (!insert) return nullptr;
+        const ulonglong2 old = atom_cas128(reinterpret_cast<ulonglong2*>(bp) + e, make_ulonglong2(~0ULL, ~0ULL), make_ulonglong2((unsigned long long)key, 0ULL));
+        b.w[2 * e] = old.x; b.w[2 * e + 1] = old.y;
+        if ((uint32_t)old.y == ROW_NONE) return reinterpret_cast<unsigned long long*>(bp) + 2 * e + 1;     // claimed: payload = 0
+      }
+      if (b.w[2 * e] == (unsigned long long)key) return reinterpret_cast<unsigned long long*>(bp) + 2 * e + 1;
+    }
+  }
+}
+
+template <typename K, bool VEC>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_group_count(const K* __restrict__ R, int64_t nR, char* body, TableHeader* hdr) {
+  if (hdr->mode != MODE_GROUP) return;
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  const uint64_t n_pairs = hdr->n_pairs;
+  const uint64_t pol = policy_evict_first();
+  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
+  K key[KPV];
+  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+  #pragma unroll
+  for (int e = 0; e < KPV; e++)
+    if (i0 + e < nR) atomicAdd(group_slot(body, n_pairs, (long long)key[e], true), 1ULL << 32);     // count lives in the high half
+}
+
+// hand every occupied slot a contiguous range of the row-id array: block scan of the counts + one atomic per CTA
+__global__ void __launch_bounds__(BLOCK_THREADS) k_group_offsets(char* body, TableHeader* hdr) {
+  if (hdr->mode != MODE_GROUP) return;
+  __shared__ unsigned long long sm[33];
+  __shared__ unsigned long long base_sm;
+  const unsigned long long n_slots = hdr->n_pairs * 4;
+  for (unsigned long long s0 = (unsigned long long)blockIdx.x * BLOCK_THREADS; s0 < n_slots; s0 += (unsigned long long)gridDim.x * BLOCK_THREADS) {
+    const unsigned long long s = s0 + threadIdx.x;
+    unsigned long long* pay = reinterpret_cast<unsigned long long*>(body + s * 16) + 1;
+    unsigned long long w = s < n_slots ? *pay : ~0ULL;
+    const bool occ = (uint32_t)w != ROW_NONE;
+    const unsigned long long cnt = occ ? (w >> 32) : 0ULL;
+    unsigned long long total, ex = block_exclusive_scan(cnt, sm, &total);
+    const unsigned long long groups = block_reduce_sum((unsigned long long)occ, sm);
+    if (threadIdx.x == 0) { base_sm = total ? atomicAdd(&hdr->group_cursor, total) : 0ULL; if (groups) atomicAdd(&hdr->n_groups, groups); }
+    __syncthreads();
+    if (occ) *pay = (cnt << 32) | (uint32_t)(base_sm + ex);        // low half: start offset, advanced to `end` by the fill pass
+    __syncthreads();
+  }
+}
+
+template <typename K, bool VEC>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ payload, uint32_t row_base,
+                                                              char* body, TableHeader* hdr) {
+  if (hdr->mode != MODE_GROUP) return;
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  const uint64_t n_pairs = hdr->n_pairs;
+  uint32_t* rows = reinterpret_cast<uint32_t*>(body + hdr->rows_offset);
+  const uint64_t pol = policy_evict_first();
+  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
+  K key[KPV];
+  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+  #pragma unroll
+  for (int e = 0; e < KPV; e++) {
+    if (i0 + e < nR) {
+      unsigned long long* pay = group_slot(body, n_pairs, (long long)key[e], false);
+      const unsigned long long old = atomicAdd(pay, 1ULL);        // low half is the write cursor of this key's range
+      rows[(uint32_t)old] = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
+    }
+  }
 }
 
 static int g_allow_dense = 1;
@@ -206,15 +304,20 @@ static void launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
   if (vec) k_build_hash<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
   else     k_build_hash<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  // duplicates found: rebuild in the grouped layout (every kernel below exits at once otherwise)
+  k_group_prepare<<<1, 1, 0, stream>>>(hdr);
+  k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 2);
+  if (vec) k_group_count<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, body, hdr);
+  else     k_group_count<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, body, hdr);
+  k_group_offsets<<<clear_grid, BLOCK_THREADS, 0, stream>>>(body, hdr);
+  if (vec) k_group_fill<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  else     k_group_fill<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
 }
 
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
                         void* table, int64_t table_bytes_, cudaStream_t stream) {
-  const int64_t slots_per_pair = key_bytes == 4 ? 8 : 4;
-  const int64_t cap = (table_bytes_ - HEADER_BYTES) / 64;
-  int64_t pairs = preferred_pairs(nR, key_bytes);
-  if (cap < pairs) pairs = cap;                                  // caller gave less than preferred: accept up to ~90 % load
-  if (pairs < 1 || pairs * slots_per_pair * 9 < nR * 10) return cudaErrorInvalidValue;
+  if (table_bytes_ < table_bytes(nR, key_bytes)) return cudaErrorInvalidValue;      // sized by hjTableBytes, nothing less
+  const int64_t pairs = preferred_pairs(nR, key_bytes);
   if (pairs > (int64_t)1 << 32) return cudaErrorInvalidValue;
   TableHeader* hdr = reinterpret_cast<TableHeader*>(table);
   char* body = reinterpret_cast<char*>(table) + HEADER_BYTES;
@@ -256,29 +359,18 @@ __device__ __forceinline__ uint32_t finish_probe_unique(const char* __restrict__
     b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
   }
 }
-// number of matches of `key` (duplicates): scan to the first non-full bucket
-template <typename K>
-__device__ __forceinline__ uint32_t finish_probe_count(const char* __restrict__ body, uint64_t n_pairs, K key, uint64_t pair, uint32_t half, Bucket b) {
-  using T = KeyTraits<K>;
-  uint32_t c = 0;
-  for (uint32_t t = 0;; ) {
-    #pragma unroll
-    for (int e = 0; e < T::SLOTS; e++) c += slot_match(b, e, key);
-    if (slot_empty(b, T::SLOTS - 1, key)) return c;
-    b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
-  }
-}
-
-template <typename K, bool VEC>
+// One instantiation per table layout (MODE): the count launch queues all three and the two that do not match the header
+// exit at once. Keeping them separate keeps registers per thread (and so occupancy) at what each layout needs.
+template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
                                                          unsigned long long* __restrict__ chunk_totals) {
   using T = KeyTraits<K>;
+  if (hdr->mode != MODE) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
   __shared__ unsigned long long red[33];
-  const uint32_t mode = hdr->mode;
-  const bool dups = hdr->has_dups != 0;
-  const bool all_present = hdr->all_present != 0;
+  constexpr uint32_t mode = MODE;
+  const bool all_present = MODE == MODE_DENSE && hdr->all_present != 0;
   const uint64_t n_pairs = hdr->n_pairs;
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
@@ -302,7 +394,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
         cnt += ((unsigned long long)((long long)key[k] - kmin) < drange && elem_index<KPV>(tile_base, k) < nS);
       continue;
     }
-    if (mode == MODE_DENSE) {
+    if constexpr (mode == MODE_DENSE) {
       // direct addressing: one 4-byte load per in-range key, all KPT in flight
       #pragma unroll
       for (int k = 0; k < KPT; k++) {
@@ -311,7 +403,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
       }
       #pragma unroll
       for (int k = 0; k < KPT; k++) cnt += (m[k] != ROW_NONE);
-    } else {
+    } else if constexpr (mode == MODE_HASH) {
+      // unique build, bucketised table: the first probe of KPV keys is in flight together, then each sequence is finished
       #pragma unroll
       for (int v = 0; v < VECS_PER_THREAD; v++) {
         uint64_t pair[KPV]; uint32_t half[KPV]; Bucket b[KPV]; bool valid[KPV];
@@ -321,12 +414,31 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
           T::home(key[v * KPV + e], n_pairs, pair[e], half[e]);
         }
         #pragma unroll
-        for (int e = 0; e < KPV; e++) if (valid[e]) b[e] = ld_bucket(body + probe_bucket(pair[e], half[e], 0, n_pairs) * 32);   // KPV buckets in flight
+        for (int e = 0; e < KPV; e++) if (valid[e]) b[e] = ld_bucket(body + probe_bucket(pair[e], half[e], 0, n_pairs) * 32);
         #pragma unroll
         for (int e = 0; e < KPV; e++) {
           const int k = v * KPV + e;
-          if (!dups) { m[k] = valid[e] ? finish_probe_unique<K>(body, n_pairs, key[k], pair[e], half[e], b[e]) : ROW_NONE; cnt += (m[k] != ROW_NONE); }
-          else       { m[k] = valid[e] ? finish_probe_count<K>(body, n_pairs, key[k], pair[e], half[e], b[e]) : 0u; cnt += m[k]; }
+          m[k] = valid[e] ? finish_probe_unique<K>(body, n_pairs, key[k], pair[e], half[e], b[e]) : ROW_NONE;
+          cnt += (m[k] != ROW_NONE);
+        }
+      }
+    } else {
+      // grouped layout (duplicate build keys): one unique-style probe per row yields the match count; the cache holds it
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) {
+        uint64_t pair[KPV]; uint32_t half[KPV]; Bucket b[KPV]; bool valid[KPV];
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) {
+          valid[e] = elem_index<KPV>(tile_base, v * KPV + e) < nS;
+          group_home((long long)key[v * KPV + e], n_pairs, pair[e], half[e]);
+        }
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) if (valid[e]) b[e] = ld_bucket(body + probe_bucket(pair[e], half[e], 0, n_pairs) * 32);
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) {
+          const int k = v * KPV + e;
+          m[k] = valid[e] ? (uint32_t)(group_finish(body, n_pairs, (long long)key[k], pair[e], half[e], b[e]) >> 32) : 0u;
+          cnt += m[k];
         }
       }
     }
@@ -365,13 +477,13 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
   if (sv.nchunks > 0) {
     const unsigned grid = (unsigned)sv.nchunks;
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
-    if (key_bytes == 4) {
-      if (vec) k_count<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      else     k_count<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-    } else {
-      if (vec) k_count<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      else     k_count<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-    }
+#define HJ_LAUNCH_COUNT(K, V) \
+    k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets); \
+    k_count<K, V, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);  \
+    k_count<K, V, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+    if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
+    else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
+#undef HJ_LAUNCH_COUNT
   }
   k_scan_chunks<<<1, SCAN_THREADS, 0, stream>>>(sv.chunk_offsets, sv.nchunks);
   return cudaGetLastError();
@@ -390,7 +502,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
   __shared__ uint32_t warp_totals[2][BLOCK_THREADS / 32];
   __shared__ unsigned long long scan_sm[33];
-  const bool dups = hdr->has_dups != 0;
+  const bool dups = hdr->mode == MODE_GROUP;
   const bool all_present = hdr->all_present != 0;
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
@@ -447,32 +559,41 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
       }
       out_base += ttotal;
     } else {
-      // duplicates: the cache holds per-row match counts; scan them, then walk the probe sequence once and emit
+      // grouped layout: the cache holds per-row match counts; scan them, find each key's row range again (one short probe)
+      // and copy it. A row with many matches is copied by the whole warp, the others by their own thread.
       K key[KPT];
       #pragma unroll
       for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
       const uint64_t n_pairs = hdr->n_pairs;
+      const uint32_t* __restrict__ rows = reinterpret_cast<const uint32_t*>(body + hdr->rows_offset);
       unsigned long long c = 0;
       #pragma unroll
       for (int k = 0; k < KPT; k++) c += m[k];
       unsigned long long total64;
       unsigned long long w = out_base + block_exclusive_scan<unsigned long long>(c, scan_sm, &total64);
+      const int lane = threadIdx.x & 31;
       #pragma unroll 1
       for (int k = 0; k < KPT; k++) {
-        uint32_t left = m[k];
-        if (left) {
+        const uint32_t n = m[k];
+        uint32_t start = 0, prow = 0;
+        if (n) {
           const int64_t j = elem_index<KPV>(tile_base, k);
-          const uint32_t prow = probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j;
+          prow = probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j;
           uint64_t pair; uint32_t half;
-          T::home(key[k], n_pairs, pair, half);
-          for (uint32_t t = 0; left; t++) {
-            const Bucket b = ld_bucket(body + probe_bucket(pair, half, t, n_pairs) * 32);
-            #pragma unroll
-            for (int e = 0; e < T::SLOTS; e++) {
-              if (slot_match(b, e, key[k])) { outR[w] = (int32_t)slot_row(b, e, key[k]); outS[w] = (int32_t)prow; w++; left--; }
-            }
-          }
+          group_home((long long)key[k], n_pairs, pair, half);
+          const unsigned long long pay = group_finish(body, n_pairs, (long long)key[k], pair, half, ld_bucket(body + probe_bucket(pair, half, 0, n_pairs) * 32));
+          start = (uint32_t)pay - n;                                          // low half = end of the key's row range
         }
+        // warp-cooperative copy for long runs (output-heavy joins), per-thread copy for short ones
+        unsigned big = __ballot_sync(0xffffffffu, n >= 64);
+        while (big) {
+          const int src = __ffs(big) - 1; big &= big - 1;
+          const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bs = __shfl_sync(0xffffffffu, start, src), bp = __shfl_sync(0xffffffffu, prow, src);
+          const unsigned long long bw = __shfl_sync(0xffffffffu, w, src);
+          for (uint32_t r = lane; r < bn; r += 32) { outR[bw + r] = (int32_t)rows[bs + r]; outS[bw + r] = (int32_t)bp; }
+        }
+        if (n && n < 64) for (uint32_t r = 0; r < n; r++) { outR[w + r] = (int32_t)rows[start + r]; outS[w + r] = (int32_t)prow; }
+        w += n;
       }
       out_base += total64;
     }
