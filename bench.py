@@ -129,7 +129,10 @@ def run_reference_arm(args, cfg) -> None:
 def workload_name(args, cfg) -> str:
     b, p = cfg.build, cfg.probe
     kt = "i32" if b.key_bytes == 4 else "i64"
-    plan = "single GPU" if args.gpus == 1 else ("radix partition + all-to-all" if args.workload == "c5" else "broadcast build, probe sharded")
+    if args.workload == "c5" and args.gpus > 1:
+        how = "partition kernel stores into peer receive buffers over NVLink" if args.exchange == "fused" else "partition + NCCL all-to-all"
+        return f"{cfg.name}: {b.n} build x {p.n} probe rows in total over {args.gpus} GPUs, {kt} keys, radix partition ({how})"
+    plan = "single GPU" if args.gpus == 1 else "broadcast build, probe sharded"
     return f"{cfg.name}: {b.n} build x {p.n} probe rows per GPU, {kt} keys, {plan}"
 
 
@@ -146,6 +149,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5 only: peer-store partition kernel vs partition + NCCL all-to-all")
     ap.add_argument("--layout", default="auto", choices=["auto", "hash"], help="hash = force the bucketised hash table even for dense key ranges")
     ap.add_argument("--no-hash-arm", action="store_true", help="skip the extra forced-hash-layout measurement")
     args = ap.parse_args()
@@ -201,6 +205,9 @@ def main() -> None:
         dS = datagen.generate(pw, dev, plo, p.n)
         dR = datagen.generate(b, dev) if rank == 0 or world == 1 else torch.empty(b.n, dtype=b.dtype, device=dev)
         nR_job, nS_job = b.n, p.n * world
+    peer_x = None
+    if args.workload == "c5" and world > 1 and args.exchange == "fused":
+        peer_x = (hjdist.PeerExchange(int(1.25 * b.n / world) + 65536, b.dtype, dev), hjdist.PeerExchange(int(1.25 * p.n / world) + 65536, p.dtype, dev))
     table = join.allocateHashTable(b.n if not (args.workload == "c5" and world > 1) else int(1.25 * b.n / world) + 1024, None, b.dtype, dev)
     torch.cuda.synchronize()
 
@@ -221,7 +228,7 @@ def main() -> None:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         if args.workload == "c5" and world > 1:
             ev[0].record(stream)
-            a, bb = hjdist.radix_join(dR, blo, dS, plo)
+            a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x) if peer_x else hjdist.radix_join(dR, blo, dS, plo)
             ev[3].record(stream)
             n_out[0] = a.numel()
             launches[0] += 2 * 3 + 5

@@ -203,6 +203,20 @@ int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, 
   return HJ_OK;
 }
 
+int32_t hjPartitionCount(const void* dKeys, int64_t n, int32_t keyBytes, int32_t nParts, uint64_t* dCounts, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dCounts) return fail(HJ_ERR_ARG, "hjPartitionCount", "null pointer or bad key width");
+  HJ_CUDA("hjPartitionCount", hj::partition_count(dKeys, n, keyBytes, nParts, reinterpret_cast<unsigned long long*>(dCounts), S_(stream)));
+  return HJ_OK;
+}
+
+int32_t hjPartitionPush(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
+                        const uint64_t* dPeerKeyPtrs, const uint64_t* dPeerRowPtrs, uint64_t* dCursors, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dPeerKeyPtrs || !dPeerRowPtrs || !dCursors) return fail(HJ_ERR_ARG, "hjPartitionPush", "null pointer or bad key width");
+  HJ_CUDA("hjPartitionPush", hj::partition_push(dKeys, dRows, rowBase, n, keyBytes, nParts, reinterpret_cast<void* const*>(dPeerKeyPtrs),
+                                                reinterpret_cast<uint32_t* const*>(dPeerRowPtrs), reinterpret_cast<unsigned long long*>(dCursors), S_(stream)));
+  return HJ_OK;
+}
+
 int32_t hjPairDigest(const int32_t* dOutR, const int32_t* dOutS, int64_t n, uint64_t* hostOut2, void* stream) {
   if (!hostOut2 || n < 0 || (n > 0 && (!dOutR || !dOutS))) return fail(HJ_ERR_ARG, "hjPairDigest", "bad argument");
   static unsigned long long* d = nullptr;

@@ -619,10 +619,16 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
 }
 
 // =========================================================================================================
-// K5  radix partition on the key hash (feeds the multi-GPU all-to-all)
+// K5  radix partition on the key hash.  Feeds the multi-GPU shuffle two ways:
+//   radix_partition       local: partition p occupies [offsets[p], offsets[p+1]) of out_keys / out_rows (then NCCL all-to-all)
+//   partition_push        fused with the exchange: every (key, row) is stored straight into the receive buffer of the
+//                         rank that owns its partition, through peer-mapped pointers (NVLink), no intermediate copy
+// A CTA takes 4096 tuples, ranks them per partition with shared-memory atomics, sorts them by partition in shared memory and
+// writes each partition's run contiguously (512 tuples = 2-6 KB per run at 8 parts), so HBM / NVLink see full-width stores.
 // =========================================================================================================
 constexpr int PART_MAX = 256;
-constexpr int PART_ITEMS = 8;     // keys per thread per block
+constexpr int PART_ITEMS = 16;                                   // tuples per thread
+constexpr int PART_TILE = BLOCK_THREADS * PART_ITEMS;            // 4096 tuples per CTA
 
 template <typename K>
 __device__ __forceinline__ uint32_t part_of(K key, int n_parts) { return (uint32_t)(((uint64_t)KeyTraits<K>::part_hash(key) * (uint32_t)n_parts) >> 32); }
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_part_hist(const K* __restrict
   __shared__ unsigned int h[PART_MAX];
   for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) h[p] = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * BLOCK_THREADS * PART_ITEMS;
+  const int64_t base = (int64_t)blockIdx.x * PART_TILE;
   #pragma unroll
   for (int e = 0; e < PART_ITEMS; e++) {
     const int64_t i = base + (int64_t)e * BLOCK_THREADS + threadIdx.x;
@@ -651,36 +657,92 @@ __global__ void k_part_offsets(const unsigned long long* __restrict__ counts, in
   }
 }
 
+// dst_keys[p] / dst_rows[p]: base pointer of partition p's destination (all equal for a local partition, peer-mapped
+// receive buffers for the fused push); cursors[p]: next free element of MY region in that destination.
 template <typename K>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_part_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base, int64_t n,
-                                                                int n_parts, K* __restrict__ out_keys, uint32_t* __restrict__ out_rows,
+                                                                int n_parts, K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
                                                                 unsigned long long* __restrict__ cursors) {
-  __shared__ unsigned int h[PART_MAX];
+  __shared__ unsigned int hist[PART_MAX];
+  __shared__ unsigned int lbase[PART_MAX + 1];
   __shared__ unsigned long long gbase[PART_MAX];
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) h[p] = 0;
+  extern __shared__ __align__(16) unsigned char part_smem[];       // dynamic: 4096 x (sizeof(K) + 4 + 1) bytes (53 KB for i64 keys)
+  K* skeys = reinterpret_cast<K*>(part_smem);
+  uint32_t* srows = reinterpret_cast<uint32_t*>(part_smem + PART_TILE * sizeof(K));
+  uint8_t* spart = part_smem + PART_TILE * (sizeof(K) + 4);
+  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) hist[p] = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * BLOCK_THREADS * PART_ITEMS;
-  K key[PART_ITEMS]; uint32_t part[PART_ITEMS], rank[PART_ITEMS];
+  const int64_t base = (int64_t)blockIdx.x * PART_TILE;
+  const int count = (int)(n - base < PART_TILE ? n - base : PART_TILE);
+  K key[PART_ITEMS]; uint32_t pr[PART_ITEMS];                       // part << 16 | rank within (CTA, part)
   #pragma unroll
   for (int e = 0; e < PART_ITEMS; e++) {
-    const int64_t i = base + (int64_t)e * BLOCK_THREADS + threadIdx.x;
-    if (i < n) { key[e] = keys[i]; part[e] = part_of<K>(key[e], n_parts); rank[e] = atomicAdd(&h[part[e]], 1u); }
+    const int li = e * BLOCK_THREADS + threadIdx.x;
+    if (li < count) {
+      key[e] = keys[base + li];
+      const uint32_t p = part_of<K>(key[e], n_parts);
+      pr[e] = (p << 16) | atomicAdd(&hist[p], 1u);
+    }
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) gbase[p] = h[p] ? atomicAdd(&cursors[p], (unsigned long long)h[p]) : 0ULL;
+  if (threadIdx.x < 32) {                                           // exclusive scan of hist -> lbase (n_parts <= 256: 8 per lane)
+    unsigned int v[PART_MAX / 32], sum = 0;
+    #pragma unroll
+    for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; v[q] = p < n_parts ? hist[p] : 0u; sum += v[q]; }
+    unsigned int inc = warp_inclusive_scan(sum), run = inc - sum;
+    #pragma unroll
+    for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; if (p < n_parts) lbase[p] = run; run += v[q]; }
+    if (threadIdx.x == 31) lbase[n_parts] = inc;
+  }
+  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) gbase[p] = hist[p] ? atomicAdd(&cursors[p], (unsigned long long)hist[p]) : 0ULL;
   __syncthreads();
   #pragma unroll
   for (int e = 0; e < PART_ITEMS; e++) {
-    const int64_t i = base + (int64_t)e * BLOCK_THREADS + threadIdx.x;
-    if (i < n) {
-      const unsigned long long dst = gbase[part[e]] + rank[e];
-      out_keys[dst] = key[e];
-      out_rows[dst] = rows ? rows[i] : row_base + (uint32_t)i;
+    const int li = e * BLOCK_THREADS + threadIdx.x;
+    if (li < count) {
+      const uint32_t p = pr[e] >> 16, pos = lbase[p] + (pr[e] & 0xFFFFu);
+      skeys[pos] = key[e];
+      srows[pos] = rows ? rows[base + li] : row_base + (uint32_t)(base + li);
+      spart[pos] = (uint8_t)p;
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < count; i += BLOCK_THREADS) {       // partition-sorted: consecutive i -> consecutive destination addresses
+    const uint32_t p = spart[i];
+    const unsigned long long d = gbase[p] + (unsigned)(i - lbase[p]);
+    dst_keys[p][d] = skeys[i];
+    dst_rows[p][d] = srows[i];
   }
 }
 
-int64_t partition_workspace_bytes(int64_t, int n_parts) { return (int64_t)2 * n_parts * 8 + 64; }
+__global__ void k_part_local_ptrs(void** kp, uint32_t** rp, void* out_keys, uint32_t* out_rows, int n_parts) {
+  for (int p = threadIdx.x; p < n_parts; p += blockDim.x) { kp[p] = out_keys; rp[p] = out_rows; }
+}
+
+// workspace: counts u64[P] | cursors u64[P] | key ptrs [P] | row ptrs [P]
+int64_t partition_workspace_bytes(int64_t, int n_parts) { return (int64_t)4 * n_parts * 8 + 64; }
+
+template <typename K>
+static void launch_scatter(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int n_parts, void* const* kp, uint32_t* const* rp,
+                           unsigned long long* cursors, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((n + PART_TILE - 1) / PART_TILE);
+  constexpr int smem = PART_TILE * (sizeof(K) + 4 + 1);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_part_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  if (grid) k_part_scatter<K><<<grid, BLOCK_THREADS, smem, stream>>>((const K*)keys, rows, row_base, n, n_parts, (K* const*)kp, rp, cursors);
+}
+
+cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, cudaStream_t stream) {
+  if (n_parts < 1 || n_parts > PART_MAX) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n_parts * 8, stream);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((n + PART_TILE - 1) / PART_TILE);
+  if (grid > 0) {
+    if (key_bytes == 4) k_part_hist<int32_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)keys, n, n_parts, counts);
+    else                k_part_hist<int64_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)keys, n, n_parts, counts);
+  }
+  return cudaGetLastError();
+}
 
 cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
                             void* out_keys, uint32_t* out_rows, unsigned long long* offsets, void* workspace, int64_t workspace_bytes,
@@ -688,19 +750,25 @@ cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row
   if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
   unsigned long long* counts = reinterpret_cast<unsigned long long*>(workspace);
   unsigned long long* cursors = counts + n_parts;
-  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n_parts * 8, stream);
+  void** kp = reinterpret_cast<void**>(cursors + n_parts);
+  uint32_t** rp = reinterpret_cast<uint32_t**>(kp + n_parts);
+  cudaError_t e = partition_count(keys, n, key_bytes, n_parts, counts, stream);
   if (e != cudaSuccess) return e;
-  const int64_t per_block = (int64_t)BLOCK_THREADS * PART_ITEMS;
-  const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
-  if (grid > 0) {
-    if (key_bytes == 4) k_part_hist<int32_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)keys, n, n_parts, counts);
-    else                k_part_hist<int64_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)keys, n, n_parts, counts);
-  }
   k_part_offsets<<<1, 32, 0, stream>>>(counts, n_parts, offsets, cursors);
-  if (grid > 0) {
-    if (key_bytes == 4) k_part_scatter<int32_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)keys, rows, row_base, n, n_parts, (int32_t*)out_keys, out_rows, cursors);
-    else                k_part_scatter<int64_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)keys, rows, row_base, n, n_parts, (int64_t*)out_keys, out_rows, cursors);
-  }
+  k_part_local_ptrs<<<1, 256, 0, stream>>>(kp, rp, out_keys, out_rows, n_parts);
+  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, kp, rp, cursors, stream);
+  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, kp, rp, cursors, stream);
+  return cudaGetLastError();
+}
+
+// Fused partition + exchange: peer_keys[p] / peer_rows[p] are DEVICE arrays of peer-mapped receive-buffer pointers,
+// cursors[p] must hold the first element of this rank's region in partition p's receive buffer (from the all-gathered
+// count matrix) and is advanced by the kernel.
+cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
+                           void* const* peer_keys, uint32_t* const* peer_rows, unsigned long long* cursors, cudaStream_t stream) {
+  if (n_parts < 1 || n_parts > PART_MAX) return cudaErrorInvalidValue;
+  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, cursors, stream);
+  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, cursors, stream);
   return cudaGetLastError();
 }
 

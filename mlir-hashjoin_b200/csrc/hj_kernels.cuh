@@ -48,6 +48,9 @@ cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row
                             void* out_keys, uint32_t* out_rows, unsigned long long* offsets, void* workspace, int64_t workspace_bytes,
                             cudaStream_t stream);
 int64_t partition_workspace_bytes(int64_t n, int n_parts);
+cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, cudaStream_t stream);
+cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
+                           void* const* peer_keys, uint32_t* const* peer_rows, unsigned long long* cursors, cudaStream_t stream);
 
 // K6: verification helpers — order-independent digest of a pair stream: out[0] += sum(mix64(pair)), out[1] ^= xor.
 cudaError_t pair_digest(const int32_t* outR, const int32_t* outS, int64_t n, unsigned long long* out2, cudaStream_t stream);

@@ -73,6 +73,60 @@ def exchange(parts: torch.Tensor, plan: ExchangePlan, group=None) -> torch.Tenso
     return out
 
 
+class PeerExchange:
+    """Peer-mapped receive buffers for the fused partition + exchange (K5 ``hjPartitionPush``): every rank allocates the
+    same symmetric buffers (torch symmetric memory = CUDA VMM handles exchanged once at rendezvous; plumbing only) and
+    the partition kernel of each rank stores its tuples straight into the owner's buffer over NVLink. The only
+    collective left on the data path is the all-gather of the N x N count matrix (N^2 int64)."""
+
+    def __init__(self, capacity_rows: int, key_dtype: torch.dtype, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.group = group
+        self.capacity = capacity_rows
+        self.keys = symm_mem.empty(capacity_rows, dtype=key_dtype, device=device)
+        self.rows = symm_mem.empty(capacity_rows, dtype=torch.int32, device=device)
+        self.hk = symm_mem.rendezvous(self.keys, group)
+        self.hr = symm_mem.rendezvous(self.rows, group)
+        self.key_ptrs = torch.tensor(list(self.hk.buffer_ptrs), dtype=torch.int64, device=device)
+        self.row_ptrs = torch.tensor(list(self.hr.buffer_ptrs), dtype=torch.int64, device=device)
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier across the ranks (signal pads in peer memory)."""
+        self.hk.barrier()
+
+    def push(self, keys: torch.Tensor, row_base: int) -> int:
+        """Partition ``keys`` (row ids row_base + i) by owner rank and store them into the owners' buffers. Returns the
+        number of tuples this rank will have received once every rank's push has completed (call barrier())."""
+        lib = _lib.load()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        stream = torch.cuda.current_stream().cuda_stream
+        kb, n = keys.element_size(), keys.numel()
+        counts = torch.empty(world, dtype=torch.int64, device=keys.device)
+        _lib.check_status(lib.hjPartitionCount(keys.data_ptr(), n, kb, world, counts.data_ptr(), stream), "hjPartitionCount")
+        matrix = torch.empty(world * world, dtype=torch.int64, device=keys.device)
+        dist.all_gather_into_tensor(matrix, counts, group=self.group)
+        matrix = matrix.view(world, world)                          # matrix[src][dst]
+        cursors = matrix[:rank].sum(0).contiguous()                 # first element of my region in every destination
+        received = int(matrix[:, rank].sum().item())
+        if int(matrix.sum(0).max().item()) > self.capacity:
+            raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
+        rc = lib.hjPartitionPush(keys.data_ptr(), None, row_base & 0xFFFFFFFF, n, kb, world, self.key_ptrs.data_ptr(), self.row_ptrs.data_ptr(),
+                                 cursors.data_ptr(), stream)
+        _lib.check_status(rc, "hjPartitionPush")
+        return received
+
+
+def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
+                     build_x: PeerExchange, probe_x: PeerExchange):
+    """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink)."""
+    build_x.barrier()                                               # nobody is still reading last step's buffers
+    nb = build_x.push(build_shard, build_row_base)
+    npr = probe_x.push(probe_shard, probe_row_base)
+    build_x.barrier()                                               # every rank's stores have landed
+    return join.hash_join(build_x.keys[:nb], probe_x.keys[:npr], buildPayload=build_x.rows[:nb], probePayload=probe_x.rows[:npr])
+
+
 def radix_join(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int, group=None):
     """Radix-partitioned join of range-sharded relations. Returns this rank's (build_row, probe_row) pairs, global row ids."""
     world = dist.get_world_size(group)

@@ -37,7 +37,13 @@ def main():
         # plan 2: radix partition + all-to-all (both relations range-sharded)
         dRs = datagen.generate(b, dev, blo, bhi - blo)
         a2, b2 = hjdist.radix_join(dRs, blo, dS, plo)
-        for plan, (a, bb) in (("broadcast", (a1, b1)), ("radix", (a2, b2))):
+        # plan 3: same, exchange fused into the partition kernel (peer stores over NVLink into symmetric buffers)
+        bx = hjdist.PeerExchange(int(1.5 * b.n / world) + 4096, b.dtype, dev)
+        px = hjdist.PeerExchange(int(1.5 * p.n / world) + 4096, p.dtype, dev)
+        a3, b3 = hjdist.radix_join_fused(dRs, blo, dS, plo, bx, px)
+        a3, b3 = a3.clone(), b3.clone()
+        a4, b4 = hjdist.radix_join_fused(dRs, blo, dS, plo, bx, px)      # buffers are reusable step after step
+        for plan, (a, bb) in (("broadcast", (a1, b1)), ("radix", (a2, b2)), ("radix-fused", (a3, b3)), ("radix-fused#2", (a4, b4))):
             n = torch.tensor([a.numel()], device=dev)
             sizes = [torch.zeros_like(n) for _ in range(world)]
             dist.all_gather(sizes, n)
