@@ -125,14 +125,14 @@ int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
 int64_t hjPartitionWorkspaceBytes(int64_t n, int32_t nParts);
 int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
                     void* dOutKeys, uint32_t* dOutRows, uint64_t* dOffsets, void* dWorkspace, int64_t workspaceBytes, void* stream);
-/* K5 fused with the exchange (multi-GPU): hjPartitionCount fills dCounts[nParts] (tuples per partition); after the ranks
- * have all-gathered their counts, hjPartitionPush stores every (key, row) straight into the receive buffer of the rank
- * that owns its partition through peer-mapped pointers (NVLink P2P): dPeerKeyPtrs / dPeerRowPtrs are device arrays of
- * nParts buffer addresses, dCursors[p] is the first element of this rank's region in partition p's buffer (advanced by
- * the call). The caller synchronises the ranks afterwards. Asynchronous. */
-int32_t hjPartitionCount(const void* dKeys, int64_t n, int32_t keyBytes, int32_t nParts, uint64_t* dCounts, void* stream);
+/* K5 fused with the exchange (multi-GPU): hjPartitionCount fills dCounts[nParts] (tuples per partition) and keeps its per-CTA
+ * count matrix in dWorkspace (hjPartitionWorkspaceBytes); after the ranks have all-gathered their counts, hjPartitionPush (same
+ * keys, same workspace) stores every (key, row) straight into the receive buffer of the rank that owns its partition through
+ * peer-mapped pointers (NVLink P2P): dPeerKeyPtrs / dPeerRowPtrs are device arrays of nParts buffer addresses, dCursors[p] is
+ * the first element of this rank's region in partition p's buffer. The caller synchronises the ranks afterwards. Asynchronous. */
+int32_t hjPartitionCount(const void* dKeys, int64_t n, int32_t keyBytes, int32_t nParts, uint64_t* dCounts, void* dWorkspace, int64_t workspaceBytes, void* stream);
 int32_t hjPartitionPush(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
-                        const uint64_t* dPeerKeyPtrs, const uint64_t* dPeerRowPtrs, uint64_t* dCursors, void* stream);
+                        const uint64_t* dPeerKeyPtrs, const uint64_t* dPeerRowPtrs, const uint64_t* dCursors, void* dWorkspace, int64_t workspaceBytes, void* stream);
 /* K6. Order-independent digest of a pair stream: hostOut2[0] = sum, hostOut2[1] = xor of mix64(r << 32 | s). Synchronous. */
 int32_t hjPairDigest(const int32_t* dOutR, const int32_t* dOutS, int64_t n, uint64_t* hostOut2, void* stream);
 /* Seeded device generators, bit-identical to the oracle's (kinds: 0 index, 1 unique, 2 uniform, 3 mixed, 4 fk, 5 zipf). */
@@ -146,6 +146,9 @@ int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32
 /* 1 (default): builds whose key range is at most 4x the row count use a direct-address table; 0 forces the hash layout;
  * 2 additionally lets a unique, gap-free key range count by range test alone (experimental). */
 void hjSetAllowDense(int32_t on);
+/* 1 (default): hash tables beyond L2 reach (> 48 MB) are built and probed in table-slice order (the relation is radix-partitioned
+ * on the bucket hash first); 0 probes in input order. Costs one header readback (a stream sync) per build and per count. */
+void hjSetLocality(int32_t on);
 const char* hjLastErrorString(void);
 const char* hjVersion(void);
 

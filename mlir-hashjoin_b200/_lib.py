@@ -65,12 +65,13 @@ _SIGNATURES = {
     "hjWrite": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "hjPartitionWorkspaceBytes": (_i64, [_i64, _i32]),
     "hjPartition": (_i32, [_vp, _vp, _u32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "hjPartitionCount": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
-    "hjPartitionPush": (_i32, [_vp, _vp, _u32, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "hjPartitionCount": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "hjPartitionPush": (_i32, [_vp, _vp, _u32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "hjPairDigest": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "hjGenerate": (_i32, [_vp, _i64, _i32, _i32, _u64, _i64, _u64, _u32, _u64, _i64, _u64, _vp]),
     "hjJoinHost": (_i64, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64]),
     "hjSetAllowDense": (None, [_i32]),
+    "hjSetLocality": (None, [_i32]),
     "hjLastErrorString": (C.c_char_p, []),
     "hjVersion": (C.c_char_p, []),
 }

@@ -43,6 +43,12 @@ struct LegacyTable { void* table = nullptr; int64_t table_bytes = 0; void* scrat
 std::mutex g_mu;
 std::map<const void*, LegacyTable> g_tables;
 
+// ---- host-side notes about device workspaces: which tables may be beyond L2 reach (set by hjBuild, read by hjCount) and
+// which scratches hold a slice-ordered copy of the probe relation (set by hjCount, read by hjWrite)
+std::mutex g_note_mu;
+std::map<const void*, bool> g_table_big;
+std::map<const void*, bool> g_scratch_reordered;
+
 // ---- hjJoinHost cache -------------------------------------------------------------------------------------
 struct DevBuf {
   void* p = nullptr; int64_t bytes = 0;
@@ -83,6 +89,7 @@ extern "C" {
 const char* hjLastErrorString(void) { return g_last_error.c_str(); }
 const char* hjVersion(void) { return "hashjoin_b200 0.2 (sm_100a)"; }
 void hjSetAllowDense(int32_t on) { hj::set_allow_dense(on); }
+void hjSetLocality(int32_t on) { hj::set_locality(on); }
 
 // =========================================================================================================
 // A. legacy helper symbols
@@ -157,6 +164,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
   if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, "hjBuild", "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
   if (reinterpret_cast<uintptr_t>(dTable) & 15) return fail(HJ_ERR_ARG, "hjBuild", "table workspace must be 16-byte aligned");
   if (tableBytes < hj::table_bytes(nR, keyBytes)) return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
+  { std::lock_guard<std::mutex> lk(g_note_mu); g_table_big[dTable] = hj::table_is_big(nR, keyBytes); }
   HJ_CUDA("hjBuild", hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, S_(stream)));
   return HJ_OK;
 }
@@ -165,7 +173,10 @@ int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* d
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjCount", "null pointer or bad key width");
   if (reinterpret_cast<uintptr_t>(dScratch) & 15) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 16-byte aligned");
   if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
-  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, S_(stream)));
+  bool big = true, reordered = false;                      // unknown table (not built through this process): look at its header
+  { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_table_big.find(dTable); if (it != g_table_big.end()) big = it->second; }
+  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, big, &reordered, S_(stream)));
+  { std::lock_guard<std::mutex> lk(g_note_mu); g_scratch_reordered[dScratch] = reordered; }
   return HJ_OK;
 }
 
@@ -188,7 +199,9 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjWrite", "null pointer or bad key width");
-  HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, S_(stream)));
+  bool reordered = false;
+  { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_scratch_reordered.find(dScratch); if (it != g_scratch_reordered.end()) reordered = it->second; }
+  HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, reordered, S_(stream)));
   return HJ_OK;
 }
 
@@ -199,21 +212,22 @@ int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, 
   if (!key_ok(keyBytes) || n < 0 || (n > 0 && (!dKeys || !dOutKeys || !dOutRows)) || !dOffsets || !dWorkspace)
     return fail(HJ_ERR_ARG, "hjPartition", "null pointer or bad key width");
   HJ_CUDA("hjPartition", hj::radix_partition(dKeys, dRows, rowBase, n, keyBytes, nParts, dOutKeys, dOutRows,
-                                             reinterpret_cast<unsigned long long*>(dOffsets), dWorkspace, workspaceBytes, S_(stream)));
+                                             reinterpret_cast<unsigned long long*>(dOffsets), dWorkspace, workspaceBytes, 0, S_(stream)));
   return HJ_OK;
 }
 
-int32_t hjPartitionCount(const void* dKeys, int64_t n, int32_t keyBytes, int32_t nParts, uint64_t* dCounts, void* stream) {
-  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dCounts) return fail(HJ_ERR_ARG, "hjPartitionCount", "null pointer or bad key width");
-  HJ_CUDA("hjPartitionCount", hj::partition_count(dKeys, n, keyBytes, nParts, reinterpret_cast<unsigned long long*>(dCounts), S_(stream)));
+int32_t hjPartitionCount(const void* dKeys, int64_t n, int32_t keyBytes, int32_t nParts, uint64_t* dCounts, void* dWorkspace, int64_t workspaceBytes, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dCounts || !dWorkspace) return fail(HJ_ERR_ARG, "hjPartitionCount", "null pointer or bad key width");
+  HJ_CUDA("hjPartitionCount", hj::partition_count(dKeys, n, keyBytes, nParts, reinterpret_cast<unsigned long long*>(dCounts), dWorkspace, workspaceBytes, 0, S_(stream)));
   return HJ_OK;
 }
 
 int32_t hjPartitionPush(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
-                        const uint64_t* dPeerKeyPtrs, const uint64_t* dPeerRowPtrs, uint64_t* dCursors, void* stream) {
-  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dPeerKeyPtrs || !dPeerRowPtrs || !dCursors) return fail(HJ_ERR_ARG, "hjPartitionPush", "null pointer or bad key width");
+                        const uint64_t* dPeerKeyPtrs, const uint64_t* dPeerRowPtrs, const uint64_t* dCursors, void* dWorkspace, int64_t workspaceBytes, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dPeerKeyPtrs || !dPeerRowPtrs || !dCursors || !dWorkspace) return fail(HJ_ERR_ARG, "hjPartitionPush", "null pointer or bad key width");
   HJ_CUDA("hjPartitionPush", hj::partition_push(dKeys, dRows, rowBase, n, keyBytes, nParts, reinterpret_cast<void* const*>(dPeerKeyPtrs),
-                                                reinterpret_cast<uint32_t* const*>(dPeerRowPtrs), reinterpret_cast<unsigned long long*>(dCursors), S_(stream)));
+                                                reinterpret_cast<uint32_t* const*>(dPeerRowPtrs), reinterpret_cast<const unsigned long long*>(dCursors),
+                                                dWorkspace, workspaceBytes, S_(stream)));
   return HJ_OK;
 }
 

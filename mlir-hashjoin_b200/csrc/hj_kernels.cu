@@ -21,37 +21,64 @@ namespace hj {
 // =========================================================================================================
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// 64-byte bucket pairs for n_rows build rows. Small tables (<= 32 MB at load 0.5) take load factor 0.5: they are
-// L2-resident anyway and short probe sequences matter (misses stop at the first non-full bucket). Big tables take 0.8:
-// every byte of footprint beyond L2 costs a 64-byte DRAM fetch per lookup.
+// 64-byte bucket pairs for n_rows build rows: load factor 0.5 (probe sequences: 1.05 buckets on average, 99th percentile 2;
+// at 0.8 the 99th percentile is 8 and a warp waits for its slowest lane). Footprint beyond L2 is handled by probing in
+// table-slice order (LOCALITY_* below), not by packing the table tighter.
 int64_t preferred_pairs(int64_t n_rows, int key_bytes) {
   const int64_t slots_per_pair = key_bytes == 4 ? 8 : 4;
-  const int64_t small_cap = ((int64_t)32 << 20) / 64;
-  int64_t pairs = (2 * n_rows + slots_per_pair - 1) / slots_per_pair;                        // load factor 0.5
-  if (pairs > small_cap) pairs = std::max(small_cap, (5 * n_rows / 4 + slots_per_pair - 1) / slots_per_pair);   // 0.8, never below 32 MB
+  const int64_t pairs = (2 * n_rows + slots_per_pair - 1) / slots_per_pair;
   return pairs < 4 ? 4 : pairs;
 }
 // The workspace must also hold the grouped layout a build with duplicate keys is rebuilt into: a u32 row-id array plus
 // 16-byte slots at load factor <= 0.8 for up to n_rows distinct keys.
-int64_t table_bytes(int64_t n_rows, int key_bytes) {
+static int64_t table_part_bytes(int64_t n_rows, int key_bytes) {
   const int64_t inline_bytes = preferred_pairs(n_rows, key_bytes) * 64;
   const int64_t group_bytes = round_up(n_rows * 4, 64) + ((5 * n_rows / 4 + 3) / 4 + 4) * 64;
-  return HEADER_BYTES + std::max(inline_bytes, group_bytes);
+  return round_up(std::max(inline_bytes, group_bytes), 256);
+}
+// Tables beyond L2 reach (tools/membench: random lookups stop hitting L2 past ~64 MB) are built and probed in
+// table-slice order: the relation is first radix-partitioned (K5) on the SAME hash bits that pick the bucket pair, so
+// consecutive CTAs touch one slice of the table at a time and the slice stays L2-resident.
+constexpr int64_t LOCALITY_MIN_BYTES = (int64_t)48 << 20;
+constexpr int64_t LOCALITY_SLICE_BYTES = (int64_t)8 << 20;
+bool table_is_big(int64_t n_rows, int key_bytes) { return preferred_pairs(n_rows, key_bytes) * 64 > LOCALITY_MIN_BYTES; }
+int locality_parts(int64_t table_body_bytes) {
+  const int64_t f = (table_body_bytes + LOCALITY_SLICE_BYTES - 1) / LOCALITY_SLICE_BYTES;
+  return (int)std::min<int64_t>(256, std::max<int64_t>(2, f));
+}
+static int64_t reorder_bytes(int64_t n, int key_bytes) { return round_up(n * key_bytes, 256) + round_up(n * 4, 256) + partition_workspace_bytes(n, 256) + 256 * 8 + 256; }
+int64_t table_bytes(int64_t n_rows, int key_bytes) {
+  return HEADER_BYTES + table_part_bytes(n_rows, key_bytes) + (table_is_big(n_rows, key_bytes) ? reorder_bytes(n_rows, key_bytes) : 0);
 }
 int64_t num_chunks(int64_t n_probe, int key_bytes) {
   const int64_t c = chunk_keys(key_bytes);
   return (n_probe + c - 1) / c;
 }
-int64_t scratch_bytes(int64_t n_probe, int key_bytes) {
+static int64_t scratch_core_bytes(int64_t n_probe, int key_bytes) {
   const int64_t nc = num_chunks(n_probe, key_bytes);
-  return round_up(nc * chunk_keys(key_bytes) * 4, 256) + (nc + 1) * 8 + 256;
+  return round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((nc + 1) * 8, 256);
 }
+// match cache + chunk offsets + room to reorder the probe relation (keys and original indices) for big tables
+int64_t scratch_bytes(int64_t n_probe, int key_bytes) { return scratch_core_bytes(n_probe, key_bytes) + reorder_bytes(n_probe, key_bytes) + 256; }
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   ScratchView v;
+  char* base = reinterpret_cast<char*>(scratch);
   v.nchunks = num_chunks(n_probe, key_bytes);
-  v.mcache = reinterpret_cast<uint32_t*>(scratch);
-  v.chunk_offsets = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256));
+  v.mcache = reinterpret_cast<uint32_t*>(base);
+  v.chunk_offsets = reinterpret_cast<unsigned long long*>(base + round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256));
+  v.reorder = base + scratch_core_bytes(n_probe, key_bytes);
   return v;
+}
+// reorder area: [keys][original indices u32][offsets u64 x 257][partition workspace]
+struct ReorderView { void* keys; uint32_t* idx; unsigned long long* offsets; void* ws; int64_t ws_bytes; };
+static ReorderView reorder_view(char* area, int64_t n, int key_bytes) {
+  ReorderView r;
+  r.keys = area;
+  r.idx = reinterpret_cast<uint32_t*>(area + round_up(n * key_bytes, 256));
+  r.offsets = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(r.idx) + round_up(n * 4, 256));
+  r.ws = reinterpret_cast<char*>(r.offsets) + 257 * 8 + 56;
+  r.ws_bytes = partition_workspace_bytes(n, 256);
+  return r;
 }
 
 // =========================================================================================================
@@ -176,8 +203,8 @@ __device__ __forceinline__ bool insert_one(char* body, uint64_t n_pairs, K key, 
 }
 
 template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ payload, uint32_t row_base,
-                                                              char* body, TableHeader* hdr) {
+__global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ perm,
+                                                              const uint32_t* __restrict__ payload, uint32_t row_base, char* body, TableHeader* hdr) {
   if (hdr->mode != MODE_HASH) return;
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const uint64_t n_pairs = hdr->n_pairs;
@@ -189,7 +216,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restric
   #pragma unroll
   for (int e = 0; e < KPV; e++) {
     if (i0 + e < nR) {
-      const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
+      const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);          // R may be a slice-ordered copy: perm = original index
+      const uint32_t row = payload ? payload[idx] : row_base + idx;
       dup |= insert_one<K>(body, n_pairs, key[e], row, &hdr->has_dups);
     }
   }
@@ -264,8 +292,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_offsets(char* body, Tab
 }
 
 template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ payload, uint32_t row_base,
-                                                              char* body, TableHeader* hdr) {
+__global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ perm,
+                                                              const uint32_t* __restrict__ payload, uint32_t row_base, char* body, TableHeader* hdr) {
   if (hdr->mode != MODE_GROUP) return;
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const uint64_t n_pairs = hdr->n_pairs;
@@ -279,39 +307,68 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restric
     if (i0 + e < nR) {
       unsigned long long* pay = group_slot(body, n_pairs, (long long)key[e], false);
       const unsigned long long old = atomicAdd(pay, 1ULL);        // low half is the write cursor of this key's range
-      rows[(uint32_t)old] = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
+      const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);
+      rows[(uint32_t)old] = payload ? payload[idx] : row_base + idx;
     }
   }
 }
 
 static int g_allow_dense = 1;
+static int g_locality = 1;
 void set_allow_dense(int on) { g_allow_dense = on; }
+void set_locality(int on) { g_locality = on; }
+constexpr int PART_SEL_OWNER = 0, PART_SEL_TABLE = 1, PART_SEL_GROUP = 2;
+
+static cudaError_t read_header(const void* table, TableHeader* out, cudaStream_t stream) {
+  static TableHeader* pinned = nullptr;
+  if (!pinned) { cudaError_t e = cudaMallocHost(&pinned, sizeof(TableHeader)); if (e != cudaSuccess) return e; }
+  cudaError_t e = cudaMemcpyAsync(pinned, table, sizeof(TableHeader), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) *out = *pinned;
+  return e;
+}
 
 template <typename K>
-static void launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32_t row_base, char* body, TableHeader* hdr, int64_t pairs, cudaStream_t stream) {
+static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32_t row_base, char* body, TableHeader* hdr, int64_t pairs,
+                                bool big, char* reorder_area, cudaStream_t stream) {
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const int64_t threads = (nR + KPV - 1) / KPV;
   const unsigned grid = (unsigned)((threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
-  const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0;
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
   if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
+  // A table beyond L2 reach that did not get the direct-address layout is built in table-slice order: one host look at the
+  // header (the only sync in the build, and only for big tables), then K5 reorders (key, original index) by slice.
+  const K* Rb = R; const uint32_t* perm = nullptr;
+  if (big && nR > 0 && g_locality) {
+    TableHeader h;
+    cudaError_t e = read_header(hdr, &h, stream);
+    if (e != cudaSuccess) return e;
+    if (h.mode == MODE_HASH) {
+      ReorderView rv = reorder_view(reorder_area, nR, (int)sizeof(K));
+      e = radix_partition(R, nullptr, 0, nR, (int)sizeof(K), locality_parts(pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes, PART_SEL_TABLE, stream);
+      if (e != cudaSuccess) return e;
+      Rb = reinterpret_cast<const K*>(rv.keys); perm = rv.idx;
+    }
+  }
+  const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0, vecb = (reinterpret_cast<uintptr_t>(Rb) & 15) == 0;
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 0);
-  if (nR == 0) return;
+  if (nR == 0) return cudaGetLastError();
   if (vec) k_build_dense<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
   else     k_build_dense<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
   k_fallback_prepare<<<1, 1, 0, stream>>>(hdr, g_allow_dense == 2);
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
-  if (vec) k_build_hash<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
-  else     k_build_hash<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  if (vecb) k_build_hash<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  else      k_build_hash<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
   // duplicates found: rebuild in the grouped layout (every kernel below exits at once otherwise)
   k_group_prepare<<<1, 1, 0, stream>>>(hdr);
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 2);
-  if (vec) k_group_count<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, body, hdr);
-  else     k_group_count<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, body, hdr);
+  if (vecb) k_group_count<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
+  else      k_group_count<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
   k_group_offsets<<<clear_grid, BLOCK_THREADS, 0, stream>>>(body, hdr);
-  if (vec) k_group_fill<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
-  else     k_group_fill<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  if (vecb) k_group_fill<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  else      k_group_fill<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  return cudaGetLastError();
 }
 
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
@@ -321,10 +378,11 @@ cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t
   if (pairs > (int64_t)1 << 32) return cudaErrorInvalidValue;
   TableHeader* hdr = reinterpret_cast<TableHeader*>(table);
   char* body = reinterpret_cast<char*>(table) + HEADER_BYTES;
-  k_init_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)key_bytes, (unsigned long long)nR, (unsigned long long)(table_bytes_ - HEADER_BYTES), (unsigned long long)pairs);
-  if (key_bytes == 4) launch_build<int32_t>((const int32_t*)R, nR, payload, row_base, body, hdr, pairs, stream);
-  else                launch_build<int64_t>((const int64_t*)R, nR, payload, row_base, body, hdr, pairs, stream);
-  return cudaGetLastError();
+  const int64_t part_bytes = table_part_bytes(nR, key_bytes);                       // the reorder area (big tables) sits behind it
+  const bool big = table_is_big(nR, key_bytes);
+  k_init_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)key_bytes, (unsigned long long)nR, (unsigned long long)part_bytes, (unsigned long long)pairs);
+  if (key_bytes == 4) return launch_build<int32_t>((const int32_t*)R, nR, payload, row_base, body, hdr, pairs, big, body + part_bytes, stream);
+  return launch_build<int64_t>((const int64_t*)R, nR, payload, row_base, body, hdr, pairs, big, body + part_bytes, stream);
 }
 
 // =========================================================================================================
@@ -375,6 +433,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
   const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
   unsigned long long cnt = 0;
 
@@ -470,10 +529,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunks(unsigned long long
   if (threadIdx.x == 0) t[n] = running;
 }
 
-cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, cudaStream_t stream) {
+cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool* reordered,
+                             cudaStream_t stream) {
   ScratchView sv = scratch_view(scratch, nS, key_bytes);
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
+  const void* S = S_in;
+  *reordered = false;
+  if (big_hint && nS > 0 && g_locality) {
+    TableHeader h;
+    cudaError_t e = read_header(table, &h, stream);
+    if (e != cudaSuccess) return e;
+    if (h.mode != MODE_DENSE && (int64_t)h.n_pairs * 64 > LOCALITY_MIN_BYTES) {
+      ReorderView rv = reorder_view(sv.reorder, nS, key_bytes);
+      e = radix_partition(S_in, nullptr, 0, nS, key_bytes, locality_parts((int64_t)h.n_pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes,
+                          h.mode == MODE_GROUP ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
+      if (e != cudaSuccess) return e;
+      S = rv.keys; *reordered = true;
+    }
+  }
   if (sv.nchunks > 0) {
     const unsigned grid = (unsigned)sv.nchunks;
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
@@ -497,9 +571,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
                                                          const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache,
                                                          const unsigned long long* __restrict__ chunk_offsets,
                                                          int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                         const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
+                                                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
   using T = KeyTraits<K>;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
+  // probe row id of position j of the relation the kernel reads: S may be a slice-ordered copy (perm = original index)
+  auto probe_row = [&](int64_t j) -> uint32_t {
+    const uint32_t idx = perm ? perm[j] : (uint32_t)j;
+    return probe_payload ? probe_payload[idx] : probe_row_base + idx;
+  };
   __shared__ uint32_t warp_totals[2][BLOCK_THREADS / 32];
   __shared__ unsigned long long scan_sm[33];
   const bool dups = hdr->mode == MODE_GROUP;
@@ -507,6 +586,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
   const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
   unsigned long long out_base = chunk_offsets[blockIdx.x];
   if (chunk_offsets[blockIdx.x + 1] == out_base) return;                     // nothing to emit for this chunk (uniform)
@@ -553,7 +633,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
           const int64_t j = elem_index<KPV>(tile_base, k);
           const unsigned long long dst = o + __popc(mask[k] & lt);
           st_stream_u32(outR + dst, m[k], pol_s);
-          st_stream_u32(outS + dst, probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j, pol_s);
+          st_stream_u32(outS + dst, probe_row(j), pol_s);
         }
         o += __popc(mask[k]);
       }
@@ -578,7 +658,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
         uint32_t start = 0, prow = 0;
         if (n) {
           const int64_t j = elem_index<KPV>(tile_base, k);
-          prow = probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j;
+          prow = probe_row(j);
           uint64_t pair; uint32_t half;
           group_home((long long)key[k], n_pairs, pair, half);
           const unsigned long long pay = group_finish(body, n_pairs, (long long)key[k], pair, half, ld_bucket(body + probe_bucket(pair, half, 0, n_pairs) * 32));
@@ -600,20 +680,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   }
 }
 
-cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void* table, const void* scratch,
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, bool reordered, cudaStream_t stream) {
   ScratchView sv = scratch_view(const_cast<void*>(scratch), nS, key_bytes);
   if (sv.nchunks == 0) return cudaSuccess;
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
   const unsigned grid = (unsigned)sv.nchunks;
+  const void* S = S_in; const uint32_t* perm = nullptr;
+  if (reordered) { ReorderView rv = reorder_view(sv.reorder, nS, key_bytes); S = rv.keys; perm = rv.idx; }
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   if (key_bytes == 4) {
-    if (vec) k_write<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
-    else     k_write<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
+    if (vec) k_write<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, perm, probe_payload, probe_row_base);
+    else     k_write<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, perm, probe_payload, probe_row_base);
   } else {
-    if (vec) k_write<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
-    else     k_write<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, probe_payload, probe_row_base);
+    if (vec) k_write<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, perm, probe_payload, probe_row_base);
+    else     k_write<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, outR, outS, perm, probe_payload, probe_row_base);
   }
   return cudaGetLastError();
 }
@@ -627,91 +709,185 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
 // writes each partition's run contiguously (512 tuples = 2-6 KB per run at 8 parts), so HBM / NVLink see full-width stores.
 // =========================================================================================================
 constexpr int PART_MAX = 256;
-constexpr int PART_ITEMS = 16;                                   // tuples per thread
-constexpr int PART_TILE = BLOCK_THREADS * PART_ITEMS;            // 4096 tuples per CTA
+constexpr int PART_ITEMS = 8;                                    // tuples per thread, blocked (contiguous) per thread
+constexpr int PART_TILE = BLOCK_THREADS * PART_ITEMS;            // 2048 tuples per CTA
+constexpr int PART_WARPS = BLOCK_THREADS / 32;
 
-template <typename K>
-__device__ __forceinline__ uint32_t part_of(K key, int n_parts) { return (uint32_t)(((uint64_t)KeyTraits<K>::part_hash(key) * (uint32_t)n_parts) >> 32); }
-
-template <typename K>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_part_hist(const K* __restrict__ keys, int64_t n, int n_parts, unsigned long long* __restrict__ counts) {
-  __shared__ unsigned int h[PART_MAX];
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) h[p] = 0;
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * PART_TILE;
-  #pragma unroll
-  for (int e = 0; e < PART_ITEMS; e++) {
-    const int64_t i = base + (int64_t)e * BLOCK_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&h[part_of<K>(keys[i], n_parts)], 1u);
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) if (h[p]) atomicAdd(&counts[p], (unsigned long long)h[p]);
+// SEL 0: an independent hash (which rank owns the key).  SEL 1 / 2: the SAME hash bits that pick the bucket pair in the
+// inline (1) or grouped (2) table, so a partition is a contiguous slice of the table.
+template <typename K, int SEL>
+__device__ __forceinline__ uint32_t part_of(K key, int n_parts) {
+  if (SEL == 0) return (uint32_t)(((uint64_t)KeyTraits<K>::part_hash(key) * (uint32_t)n_parts) >> 32);
+  if (SEL == 1 && sizeof(K) == 4) return (uint32_t)(((uint64_t)mix32((uint32_t)key) * (uint32_t)n_parts) >> 32);
+  return (uint32_t)__umul64hi(mix64((uint64_t)(long long)key), (uint64_t)n_parts);
 }
 
-__global__ void k_part_offsets(const unsigned long long* __restrict__ counts, int n_parts, unsigned long long* __restrict__ offsets,
-                               unsigned long long* __restrict__ cursors) {
-  if (threadIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int p = 0; p < n_parts; p++) { offsets[p] = run; cursors[p] = run; run += counts[p]; }
-    offsets[n_parts] = run;
+// lanes of the warp whose `p` equals mine, from `bits` ballots (the classic warp multisplit; cheaper than MATCH.ANY here)
+__device__ __forceinline__ unsigned same_part_mask(uint32_t p, int bits) {
+  unsigned m = 0xffffffffu;
+  for (int b = 0; b < bits; b++) {
+    const unsigned bal = __ballot_sync(0xffffffffu, (p >> b) & 1u);
+    m &= ((p >> b) & 1u) ? bal : ~bal;
+  }
+  return m;
+}
+
+// tile loader: coalesced 16-byte vectors; tile-local index of element e of this thread: ((e / KPV) * 256 + t) * KPV + e % KPV
+template <typename K>
+__device__ __forceinline__ int part_li(int e) {
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  return ((e / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (e % KPV);
+}
+template <typename K>
+__device__ __forceinline__ void part_load(const K* __restrict__ keys, int64_t base, int count, bool aligned, uint64_t pol, K (&key)[PART_ITEMS]) {
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  #pragma unroll
+  for (int v = 0; v < PART_ITEMS / KPV; v++) {
+    const int l0 = (v * BLOCK_THREADS + threadIdx.x) * KPV;
+    if (aligned && l0 + KPV <= count) { int4 x = ld_stream_v4(keys + base + l0, pol); memcpy(&key[v * KPV], &x, 16); }
+    else {
+      #pragma unroll
+      for (int e = 0; e < KPV; e++) key[v * KPV + e] = (l0 + e < count) ? keys[base + l0 + e] : K(0);
+    }
+  }
+}
+
+// Two-pass, atomic-free partition. The tiles are dealt to a fixed grid of G persistent CTAs (contiguous tile ranges);
+//   pass 1 (k_part_hist)    every CTA counts its tuples per part                      -> mat[cta][part]
+//   scan   (k_part_scan)    start[part] + prefix over the CTAs                         -> mat[cta][part] = first destination element
+//   pass 2 (k_part_scatter) the same CTA walks the same tiles with running cursors in shared memory
+// (global atomics on the few per-part cursors serialise at about one per clock: 2.7 M of them cost > 1 ms at 2^28 tuples).
+constexpr int PART_GRID = 148 * 4;
+
+__host__ __device__ inline int64_t part_tiles_per_cta(int64_t n, int grid) { const int64_t nt = (n + PART_TILE - 1) / PART_TILE; return (nt + grid - 1) / grid; }
+
+template <typename K, int SEL>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_part_hist(const K* __restrict__ keys, int64_t n, int n_parts, int bits, unsigned long long* __restrict__ mat) {
+  __shared__ unsigned int wh[PART_WARPS][PART_MAX];               // one private histogram per warp: no atomics, no contention
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = lane; p < n_parts; p += 32) wh[warp][p] = 0;
+  __syncwarp();
+  const int64_t tpc = part_tiles_per_cta(n, gridDim.x);
+  const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+  const uint64_t pol = policy_evict_first();
+  for (int64_t tile = blockIdx.x * tpc; tile < (blockIdx.x + 1) * tpc; tile++) {
+    const int64_t base = tile * PART_TILE;
+    if (base >= n) break;
+    const int count = (int)(n - base < PART_TILE ? n - base : PART_TILE);
+    K key[PART_ITEMS];
+    part_load<K>(keys, base, count, aligned, pol, key);
+    #pragma unroll
+    for (int e = 0; e < PART_ITEMS; e++)
+      if (part_li<K>(e) < count) atomicAdd(&wh[warp][part_of<K, SEL>(key[e], n_parts)], 1u);    // warp-private counters: only same-warp lanes collide
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) {
+    unsigned long long t = 0;
+    #pragma unroll
+    for (int w = 0; w < PART_WARPS; w++) t += wh[w][p];
+    mat[(size_t)blockIdx.x * n_parts + p] = t;
+  }
+}
+
+__global__ void __launch_bounds__(PART_MAX) k_part_totals(const unsigned long long* __restrict__ mat, int grid, int n_parts, unsigned long long* __restrict__ counts) {
+  const int p = threadIdx.x;
+  if (p >= n_parts) return;
+  unsigned long long t = 0;
+  for (int c = 0; c < grid; c++) t += mat[(size_t)c * n_parts + p];
+  counts[p] = t;
+}
+
+// one CTA: totals per part -> counts[] (and offsets[] when asked), then mat[cta][part] := start[part] + prefix over CTAs.
+// start[part] = exclusive offsets of the totals (local partition) or the caller's cursors (push into peers' buffers).
+__global__ void __launch_bounds__(PART_MAX) k_part_scan(unsigned long long* __restrict__ mat, int grid, int n_parts, unsigned long long* __restrict__ counts,
+                                                        unsigned long long* __restrict__ offsets, const unsigned long long* __restrict__ start_in) {
+  __shared__ unsigned long long sm[33];
+  const int p = threadIdx.x;
+  unsigned long long total = 0;
+  if (p < n_parts) for (int c = 0; c < grid; c++) total += mat[(size_t)c * n_parts + p];
+  unsigned long long all, ex = block_exclusive_scan(total, sm, &all);
+  if (p < n_parts) {
+    if (counts) counts[p] = total;
+    if (offsets) { offsets[p] = ex; if (p == n_parts - 1) offsets[n_parts] = all; }
+    unsigned long long run = start_in ? start_in[p] : ex;
+    for (int c = 0; c < grid; c++) { const unsigned long long t = mat[(size_t)c * n_parts + p]; mat[(size_t)c * n_parts + p] = run; run += t; }
   }
 }
 
 // dst_keys[p] / dst_rows[p]: base pointer of partition p's destination (all equal for a local partition, peer-mapped
-// receive buffers for the fused push); cursors[p]: next free element of MY region in that destination.
-template <typename K>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_part_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base, int64_t n,
-                                                                int n_parts, K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
-                                                                unsigned long long* __restrict__ cursors) {
-  __shared__ unsigned int hist[PART_MAX];
-  __shared__ unsigned int lbase[PART_MAX + 1];
-  __shared__ unsigned long long gbase[PART_MAX];
-  extern __shared__ __align__(16) unsigned char part_smem[];       // dynamic: 4096 x (sizeof(K) + 4 + 1) bytes (53 KB for i64 keys)
-  K* skeys = reinterpret_cast<K*>(part_smem);
-  uint32_t* srows = reinterpret_cast<uint32_t*>(part_smem + PART_TILE * sizeof(K));
-  uint8_t* spart = part_smem + PART_TILE * (sizeof(K) + 4);
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) hist[p] = 0;
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * PART_TILE;
-  const int count = (int)(n - base < PART_TILE ? n - base : PART_TILE);
-  K key[PART_ITEMS]; uint32_t pr[PART_ITEMS];                       // part << 16 | rank within (CTA, part)
-  #pragma unroll
-  for (int e = 0; e < PART_ITEMS; e++) {
-    const int li = e * BLOCK_THREADS + threadIdx.x;
-    if (li < count) {
-      key[e] = keys[base + li];
-      const uint32_t p = part_of<K>(key[e], n_parts);
-      pr[e] = (p << 16) | atomicAdd(&hist[p], 1u);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {                                           // exclusive scan of hist -> lbase (n_parts <= 256: 8 per lane)
-    unsigned int v[PART_MAX / 32], sum = 0;
+// receive buffers for the fused push). Ranking is atomic-free: ballots give the rank inside a warp instruction, per-warp
+// histograms the rank inside the warp, a scan over (part, warp) the rank inside the tile; tuples are staged
+// partition-sorted in shared memory and each partition's run leaves as one contiguous stream of full sectors.
+template <typename K, int SEL>
+__global__ void __launch_bounds__(BLOCK_THREADS, 6) k_part_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base, int64_t n,
+                                                                int n_parts, int bits, K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
+                                                                const unsigned long long* __restrict__ mat) {
+  __shared__ unsigned int wh[PART_WARPS][PART_MAX];               // per-warp counts, then per-warp exclusive offsets inside the part
+  __shared__ unsigned int lbase[PART_MAX + 1];                    // first staged position of each part
+  __shared__ unsigned long long gcur[PART_MAX];                   // running destination cursor of each part for this CTA
+  __shared__ K* kptr[PART_MAX];
+  __shared__ uint32_t* rptr[PART_MAX];
+  __shared__ K skeys[PART_TILE];
+  __shared__ unsigned short sidx[PART_TILE];                      // tile-local original position
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) { kptr[p] = dst_keys[p]; rptr[p] = dst_rows[p]; gcur[p] = mat[(size_t)blockIdx.x * n_parts + p]; }
+  const int64_t tpc = part_tiles_per_cta(n, gridDim.x);
+  const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+  const uint64_t pol = policy_evict_first();
+  for (int64_t tile = blockIdx.x * tpc; tile < (blockIdx.x + 1) * tpc; tile++) {
+    const int64_t base = tile * PART_TILE;
+    if (base >= n) break;
+    const int count = (int)(n - base < PART_TILE ? n - base : PART_TILE);
+    for (int p = threadIdx.x; p < PART_WARPS * PART_MAX; p += BLOCK_THREADS) (&wh[0][0])[p] = 0;
+    __syncthreads();                                              // also orders the previous tile's output loop before restaging
+    K key[PART_ITEMS]; uint32_t pr[PART_ITEMS];                   // part << 16 | rank inside (warp, part)
+    part_load<K>(keys, base, count, aligned, pol, key);
     #pragma unroll
-    for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; v[q] = p < n_parts ? hist[p] : 0u; sum += v[q]; }
-    unsigned int inc = warp_inclusive_scan(sum), run = inc - sum;
-    #pragma unroll
-    for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; if (p < n_parts) lbase[p] = run; run += v[q]; }
-    if (threadIdx.x == 31) lbase[n_parts] = inc;
-  }
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) gbase[p] = hist[p] ? atomicAdd(&cursors[p], (unsigned long long)hist[p]) : 0ULL;
-  __syncthreads();
-  #pragma unroll
-  for (int e = 0; e < PART_ITEMS; e++) {
-    const int li = e * BLOCK_THREADS + threadIdx.x;
-    if (li < count) {
-      const uint32_t p = pr[e] >> 16, pos = lbase[p] + (pr[e] & 0xFFFFu);
-      skeys[pos] = key[e];
-      srows[pos] = rows ? rows[base + li] : row_base + (uint32_t)(base + li);
-      spart[pos] = (uint8_t)p;
+    for (int e = 0; e < PART_ITEMS; e++) {
+      if (part_li<K>(e) < count) {
+        const uint32_t p = part_of<K, SEL>(key[e], n_parts);
+        pr[e] = (p << 16) | atomicAdd(&wh[warp][p], 1u);          // rank inside (warp, part); warp-private counters
+      }
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < count; i += BLOCK_THREADS) {       // partition-sorted: consecutive i -> consecutive destination addresses
-    const uint32_t p = spart[i];
-    const unsigned long long d = gbase[p] + (unsigned)(i - lbase[p]);
-    dst_keys[p][d] = skeys[i];
-    dst_rows[p][d] = srows[i];
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) {  // per part: exclusive offsets of the warps, and the part total
+      unsigned int run = 0;
+      #pragma unroll
+      for (int w = 0; w < PART_WARPS; w++) { const unsigned int t = wh[w][p]; wh[w][p] = run; run += t; }
+      lbase[p] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                       // exclusive scan of the part totals (<= 256: 8 per lane)
+      unsigned int v[PART_MAX / 32], sum = 0;
+      #pragma unroll
+      for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; v[q] = p < n_parts ? lbase[p] : 0u; sum += v[q]; }
+      const unsigned int inc = warp_inclusive_scan(sum);
+      unsigned int run = inc - sum;
+      #pragma unroll
+      for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; if (p < n_parts) lbase[p] = run; run += v[q]; }
+      if (threadIdx.x == 31) lbase[n_parts] = inc;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int e = 0; e < PART_ITEMS; e++) {
+      const int li = part_li<K>(e);
+      if (li < count) {
+        const uint32_t p = pr[e] >> 16, pos = lbase[p] + wh[warp][p] + (pr[e] & 0xFFFFu);
+        skeys[pos] = key[e];
+        sidx[pos] = (unsigned short)li;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < count; i += BLOCK_THREADS) {     // partition-sorted: consecutive i -> consecutive destination addresses
+      const K k = skeys[i];
+      const uint32_t p = part_of<K, SEL>(k, n_parts);
+      const unsigned long long d = gcur[p] + (unsigned)(i - lbase[p]);
+      const int64_t src = base + sidx[i];
+      kptr[p][d] = k;
+      rptr[p][d] = rows ? rows[src] : row_base + (uint32_t)src;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) gcur[p] += lbase[p + 1] - lbase[p];
   }
 }
 
@@ -719,56 +895,70 @@ __global__ void k_part_local_ptrs(void** kp, uint32_t** rp, void* out_keys, uint
   for (int p = threadIdx.x; p < n_parts; p += blockDim.x) { kp[p] = out_keys; rp[p] = out_rows; }
 }
 
-// workspace: counts u64[P] | cursors u64[P] | key ptrs [P] | row ptrs [P]
-int64_t partition_workspace_bytes(int64_t, int n_parts) { return (int64_t)4 * n_parts * 8 + 64; }
+// workspace: mat u64[PART_GRID][P] | key ptrs [P] | row ptrs [P]
+int64_t partition_workspace_bytes(int64_t, int n_parts) { return (int64_t)PART_GRID * n_parts * 8 + (int64_t)2 * n_parts * 8 + 64; }
+
+static inline int part_bits(int n_parts) { int b = 0; while ((1 << b) < n_parts) b++; return b; }
+static inline int part_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(PART_GRID, (n + PART_TILE - 1) / PART_TILE)); }
 
 template <typename K>
+static void launch_hist(const void* keys, int64_t n, int n_parts, unsigned long long* mat, int sel, cudaStream_t stream) {
+  const int grid = part_grid(n), bits = part_bits(n_parts);
+  if (sel == PART_SEL_TABLE)      k_part_hist<K, 1><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, n, n_parts, bits, mat);
+  else if (sel == PART_SEL_GROUP) k_part_hist<K, 2><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, n, n_parts, bits, mat);
+  else                            k_part_hist<K, 0><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, n, n_parts, bits, mat);
+}
+template <typename K>
 static void launch_scatter(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int n_parts, void* const* kp, uint32_t* const* rp,
-                           unsigned long long* cursors, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((n + PART_TILE - 1) / PART_TILE);
-  constexpr int smem = PART_TILE * (sizeof(K) + 4 + 1);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_part_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-  if (grid) k_part_scatter<K><<<grid, BLOCK_THREADS, smem, stream>>>((const K*)keys, rows, row_base, n, n_parts, (K* const*)kp, rp, cursors);
+                           const unsigned long long* mat, int sel, cudaStream_t stream) {
+  const int grid = part_grid(n), bits = part_bits(n_parts);
+  if (sel == PART_SEL_TABLE)      k_part_scatter<K, 1><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, rows, row_base, n, n_parts, bits, (K* const*)kp, rp, mat);
+  else if (sel == PART_SEL_GROUP) k_part_scatter<K, 2><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, rows, row_base, n, n_parts, bits, (K* const*)kp, rp, mat);
+  else                            k_part_scatter<K, 0><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, rows, row_base, n, n_parts, bits, (K* const*)kp, rp, mat);
 }
 
-cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, cudaStream_t stream) {
-  if (n_parts < 1 || n_parts > PART_MAX) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n_parts * 8, stream);
-  if (e != cudaSuccess) return e;
-  const unsigned grid = (unsigned)((n + PART_TILE - 1) / PART_TILE);
-  if (grid > 0) {
-    if (key_bytes == 4) k_part_hist<int32_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)keys, n, n_parts, counts);
-    else                k_part_hist<int64_t><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)keys, n, n_parts, counts);
+// pass 1 + totals: counts[p] (device) = tuples of partition p; the per-CTA matrix stays in the workspace for the scatter
+cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, void* workspace, int64_t workspace_bytes,
+                            int sel, cudaStream_t stream) {
+  if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
+  unsigned long long* mat = reinterpret_cast<unsigned long long*>(workspace);
+  if (key_bytes == 4) launch_hist<int32_t>(keys, n, n_parts, mat, sel, stream);
+  else                launch_hist<int64_t>(keys, n, n_parts, mat, sel, stream);
+  if (counts) {                                                    // totals only; the matrix keeps the raw counts for the later scan
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n_parts * 8, stream);
+    if (e != cudaSuccess) return e;
+    k_part_totals<<<1, PART_MAX, 0, stream>>>(mat, part_grid(n), n_parts, counts);
   }
   return cudaGetLastError();
 }
 
 cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
                             void* out_keys, uint32_t* out_rows, unsigned long long* offsets, void* workspace, int64_t workspace_bytes,
-                            cudaStream_t stream) {
+                            int sel, cudaStream_t stream) {
   if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
-  unsigned long long* counts = reinterpret_cast<unsigned long long*>(workspace);
-  unsigned long long* cursors = counts + n_parts;
-  void** kp = reinterpret_cast<void**>(cursors + n_parts);
+  unsigned long long* mat = reinterpret_cast<unsigned long long*>(workspace);
+  void** kp = reinterpret_cast<void**>(mat + (size_t)PART_GRID * n_parts);
   uint32_t** rp = reinterpret_cast<uint32_t**>(kp + n_parts);
-  cudaError_t e = partition_count(keys, n, key_bytes, n_parts, counts, stream);
+  cudaError_t e = partition_count(keys, n, key_bytes, n_parts, nullptr, workspace, workspace_bytes, sel, stream);
   if (e != cudaSuccess) return e;
-  k_part_offsets<<<1, 32, 0, stream>>>(counts, n_parts, offsets, cursors);
+  k_part_scan<<<1, PART_MAX, 0, stream>>>(mat, part_grid(n), n_parts, nullptr, offsets, nullptr);
   k_part_local_ptrs<<<1, 256, 0, stream>>>(kp, rp, out_keys, out_rows, n_parts);
-  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, kp, rp, cursors, stream);
-  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, kp, rp, cursors, stream);
+  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, kp, rp, mat, sel, stream);
+  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, kp, rp, mat, sel, stream);
   return cudaGetLastError();
 }
 
 // Fused partition + exchange: peer_keys[p] / peer_rows[p] are DEVICE arrays of peer-mapped receive-buffer pointers,
-// cursors[p] must hold the first element of this rank's region in partition p's receive buffer (from the all-gathered
-// count matrix) and is advanced by the kernel.
+// cursors[p] holds the first element of this rank's region in partition p's receive buffer (from the all-gathered count
+// matrix). Must follow partition_count() on the same keys and workspace.
 cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
-                           void* const* peer_keys, uint32_t* const* peer_rows, unsigned long long* cursors, cudaStream_t stream) {
-  if (n_parts < 1 || n_parts > PART_MAX) return cudaErrorInvalidValue;
-  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, cursors, stream);
-  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, cursors, stream);
+                           void* const* peer_keys, uint32_t* const* peer_rows, const unsigned long long* cursors, void* workspace, int64_t workspace_bytes,
+                           cudaStream_t stream) {
+  if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
+  unsigned long long* mat = reinterpret_cast<unsigned long long*>(workspace);
+  k_part_scan<<<1, PART_MAX, 0, stream>>>(mat, part_grid(n), n_parts, nullptr, nullptr, cursors);
+  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, mat, PART_SEL_OWNER, stream);
+  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, mat, PART_SEL_OWNER, stream);
   return cudaGetLastError();
 }
 

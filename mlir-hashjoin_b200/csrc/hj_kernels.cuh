@@ -11,10 +11,12 @@ constexpr int HEADER_BYTES = 256;              // table workspace = header + bod
 // tile geometry shared by count/scan/write (must agree between the two probe passes)
 constexpr int BLOCK_THREADS = 256;
 constexpr int VECS_PER_THREAD = 2;
-constexpr int CHUNK_TILES = 8;                 // consecutive tiles one CTA owns; the scan runs over chunks
+// consecutive tiles one CTA owns (the scan runs over chunks). i64 keys: one tile per CTA — a big table is probed in slice
+// order, and the rows in flight (CTAs x chunk) times 32 table bytes per row must stay within L2 reach.
+__host__ __device__ constexpr int chunk_tiles(int key_bytes) { return key_bytes == 4 ? 8 : 1; }
 __host__ __device__ constexpr int keys_per_vec(int key_bytes) { return 16 / key_bytes; }
 __host__ __device__ constexpr int tile_keys(int key_bytes) { return BLOCK_THREADS * VECS_PER_THREAD * keys_per_vec(key_bytes); }
-__host__ __device__ constexpr int chunk_keys(int key_bytes) { return CHUNK_TILES * tile_keys(key_bytes); }
+__host__ __device__ constexpr int chunk_keys(int key_bytes) { return chunk_tiles(key_bytes) * tile_keys(key_bytes); }
 
 int64_t preferred_pairs(int64_t n_rows, int key_bytes);
 int64_t table_bytes(int64_t n_rows, int key_bytes);
@@ -26,19 +28,25 @@ struct ScratchView {
   uint32_t* mcache;
   unsigned long long* chunk_offsets;  // after scan: exclusive offsets; [nchunks] = total
   int64_t nchunks;
+  char* reorder;                      // slice-ordered copy of the probe relation (big tables only)
 };
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
 
-void set_allow_dense(int on);   // debug/bench switch: 0 forces the hash layout even for dense key ranges
+void set_allow_dense(int on);
+void set_locality(int on);      // debug/bench switch: 0 disables the slice-ordered build/probe of big tables
+bool table_is_big(int64_t n_rows, int key_bytes);   // debug/bench switch: 0 forces the hash layout even for dense key ranges
 
 // K0+K1: clear + build.  payload == nullptr -> row id = row_base + i  (join_v1.mlir:232 stores the thread index).
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
                         void* table, int64_t table_bytes_, cudaStream_t stream);
-// K2+K3: count + scan (async).  Total lands in chunk_offsets[nchunks].
-cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, cudaStream_t stream);
+// K2+K3: count + scan (async).  Total lands in chunk_offsets[nchunks].  big_hint: the table may be beyond L2 reach (then the
+// header is read back once and, unless the layout is direct-address, the probe relation is reordered by table slice first);
+// *reordered tells write_pairs which copy of the relation the match cache refers to.
+cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool* reordered,
+                             cudaStream_t stream);
 // K4: write pairs.
 cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base,
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, bool reordered,
                         cudaStream_t stream);
 
 // K5: radix partition by the key hash (multi-GPU shuffle feed).  Two launches: histogram, scatter.
@@ -46,11 +54,13 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
 //   partition p occupies [offsets[p], offsets[p+1]) of out_keys/out_rows.  offsets: u64[n_parts+1] device.
 cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
                             void* out_keys, uint32_t* out_rows, unsigned long long* offsets, void* workspace, int64_t workspace_bytes,
-                            cudaStream_t stream);
+                            int sel, cudaStream_t stream);          // sel 0: owner hash (multi-GPU), 1/2: table-slice hash (inline/grouped)
 int64_t partition_workspace_bytes(int64_t n, int n_parts);
-cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, cudaStream_t stream);
+cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, void* workspace, int64_t workspace_bytes,
+                            int sel, cudaStream_t stream);
 cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
-                           void* const* peer_keys, uint32_t* const* peer_rows, unsigned long long* cursors, cudaStream_t stream);
+                           void* const* peer_keys, uint32_t* const* peer_rows, const unsigned long long* cursors, void* workspace, int64_t workspace_bytes,
+                           cudaStream_t stream);
 
 // K6: verification helpers — order-independent digest of a pair stream: out[0] += sum(mix64(pair)), out[1] ^= xor.
 cudaError_t pair_digest(const int32_t* outR, const int32_t* outS, int64_t n, unsigned long long* out2, cudaStream_t stream);

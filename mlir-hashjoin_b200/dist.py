@@ -103,7 +103,8 @@ class PeerExchange:
         stream = torch.cuda.current_stream().cuda_stream
         kb, n = keys.element_size(), keys.numel()
         counts = torch.empty(world, dtype=torch.int64, device=keys.device)
-        _lib.check_status(lib.hjPartitionCount(keys.data_ptr(), n, kb, world, counts.data_ptr(), stream), "hjPartitionCount")
+        ws = torch.empty(lib.hjPartitionWorkspaceBytes(n, world), dtype=torch.uint8, device=keys.device)
+        _lib.check_status(lib.hjPartitionCount(keys.data_ptr(), n, kb, world, counts.data_ptr(), ws.data_ptr(), ws.numel(), stream), "hjPartitionCount")
         matrix = torch.empty(world * world, dtype=torch.int64, device=keys.device)
         dist.all_gather_into_tensor(matrix, counts, group=self.group)
         matrix = matrix.view(world, world)                          # matrix[src][dst]
@@ -112,7 +113,7 @@ class PeerExchange:
         if int(matrix.sum(0).max().item()) > self.capacity:
             raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
         rc = lib.hjPartitionPush(keys.data_ptr(), None, row_base & 0xFFFFFFFF, n, kb, world, self.key_ptrs.data_ptr(), self.row_ptrs.data_ptr(),
-                                 cursors.data_ptr(), stream)
+                                 cursors.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         _lib.check_status(rc, "hjPartitionPush")
         return received
 

@@ -77,12 +77,12 @@ def test_timer_format(lib, capfd):
 
 def test_workspace_queries(lib):
     assert lib.hjTableBytes(0, 4) >= 256 + 64
-    # room for whichever layout the build picks: inline buckets (load 0.5 / 0.8) or the grouped layout for duplicate keys
-    # (u32 row ids + 16-byte slots at load <= 0.8): 24 bytes per build row bounds both for i32 keys
-    for n in (1 << 10, 1 << 20, 1 << 24):
+    # room for whichever layout the build picks: inline buckets at load 0.5 (16 / 32 bytes per row) or the grouped layout
+    # for duplicate keys (u32 row ids + 16-byte slots at load <= 0.8: 24 bytes per row); tables beyond L2 reach add a reorder area
+    for n in (1 << 10, 1 << 20):
         assert 24 * n <= lib.hjTableBytes(n, 4) - 256 <= 24 * n + 1024
-        assert 32 * n <= lib.hjTableBytes(n, 8) - 256 <= 32 * n + 1024 or n > (1 << 20)
-    assert lib.hjTableBytes(1 << 24, 8) - 256 <= 24 * (1 << 24) + 1024      # big i64 tables: load 0.8 inline, grouped bound wins
+        assert 32 * n <= lib.hjTableBytes(n, 8) - 256 <= 32 * n + 1024
+    assert lib.hjTableBytes(1 << 24, 4) - 256 >= (24 + 8) * (1 << 24)        # + slice-ordered copy of the build relation (key + index)
     assert lib.hjTableBytes(10, 5) < 0 and lib.hjScratchBytes(-1, 4) < 0
     assert lib.hashJoinTableBytes(1000) == lib.hjTableBytes(1000, 4)
     assert lib.hashJoinScratchBytesI64(1000) == lib.hjScratchBytes(1000, 8)

@@ -306,6 +306,32 @@ def test_mid_size_vs_oracle(lib, cuda, oracle):
     assert torch.unique(bb).numel() == bb.numel()
 
 
+@pytest.mark.parametrize("dups", [False, True])
+def test_big_table_slice_ordered_path(lib, cuda, oracle, dups):
+    """Tables beyond L2 reach (> 48 MB) are built and probed in table-slice order (K5 reorders both relations on the
+    bucket hash). 6M sparse build keys, unique (inline layout) and 3x duplicated (grouped layout), with payload columns,
+    against the OpenMP oracle: count + order-independent digest, plus key equality of every pair."""
+    import torch
+    from mlir_hashjoin_b200 import datagen, join
+    nR, nS = 6_000_000, 20_000_003
+    dom = nR // 3 if dups else nR
+    b = datagen.RelationSpec(nR, 4, datagen.KIND_FK if dups else datagen.KIND_UNIQUE, 7, 0, dom, 0, 0x9E3779B1)
+    p = datagen.RelationSpec(nS, 4, datagen.KIND_UNIFORM, 8, 0, 2 * dom, 0, 0x9E3779B1)
+    dR, dS = datagen.generate(b), datagen.generate(p)
+    pr = torch.arange(nR, dtype=torch.int32, device=cuda) * 3 + 1
+    ps = torch.arange(nS, dtype=torch.int32, device=cuda) + 77
+    a, bb = join.hash_join(dR, dS, buildPayload=pr, probePayload=ps)
+    R, S = dR.cpu().numpy(), dS.cpu().numpy()
+    oa, ob = oracle.join(R, S, threads=0)
+    assert a.numel() == oa.size
+    assert join.pair_digest(a, bb) == oracle.pair_digest(oa * 3 + 1, ob + 77)
+    assert bool((dR[((a - 1) // 3).long()] == dS[(bb - 77).long()]).all())
+    lib.hjSetLocality(0)                                           # same join in input order: identical multiset
+    a2, b2 = join.hash_join(dR, dS, buildPayload=pr, probePayload=ps)
+    lib.hjSetLocality(1)
+    assert join.pair_digest(a2, b2) == join.pair_digest(a, bb)
+
+
 @pytest.mark.slow
 def test_c2_full_size_properties(lib, cuda):
     """BASELINE.json config 2 at full size (2^24 x 2^28): analytic count, key equality of every pair, probe rows a permutation."""
