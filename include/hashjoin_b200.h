@@ -149,6 +149,9 @@ void hjSetAllowDense(int32_t on);
 /* 1 (default): hash tables beyond L2 reach (> 48 MB) are built and probed in table-slice order (the relation is radix-partitioned
  * on the bucket hash first); 0 probes in input order. Costs one header readback (a stream sync) per build and per count. */
 void hjSetLocality(int32_t on);
+/* 1: the direct-address count kernel moves its two streams with TMA bulk copies (cp.async.bulk, per-warp mbarriers); 0 (default): LDG/STG.
+ * Experimental: measured 3.7x slower on config 2 (profiles/README.md). */
+void hjSetTmaCount(int32_t on);
 const char* hjLastErrorString(void);
 const char* hjVersion(void);
 

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "hjJoinHost": (_i64, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64]),
     "hjSetAllowDense": (None, [_i32]),
     "hjSetLocality": (None, [_i32]),
+    "hjSetTmaCount": (None, [_i32]),
     "hjLastErrorString": (C.c_char_p, []),
     "hjVersion": (C.c_char_p, []),
 }

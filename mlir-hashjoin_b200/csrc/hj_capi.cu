@@ -90,6 +90,7 @@ const char* hjLastErrorString(void) { return g_last_error.c_str(); }
 const char* hjVersion(void) { return "hashjoin_b200 0.2 (sm_100a)"; }
 void hjSetAllowDense(int32_t on) { hj::set_allow_dense(on); }
 void hjSetLocality(int32_t on) { hj::set_locality(on); }
+void hjSetTmaCount(int32_t on) { hj::set_tma_count(on); }
 
 // =========================================================================================================
 // A. legacy helper symbols

@@ -315,6 +315,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restric
 
 static int g_allow_dense = 1;
 static int g_locality = 1;
+static int g_tma_count = 0;    // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
+void set_tma_count(int on) { g_tma_count = on; }
 void set_allow_dense(int on) { g_allow_dense = on; }
 void set_locality(int on) { g_locality = on; }
 constexpr int PART_SEL_OWNER = 0, PART_SEL_TABLE = 1, PART_SEL_GROUP = 2;
@@ -508,6 +510,88 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   if (threadIdx.x == 0) chunk_totals[blockIdx.x] = cnt;
 }
 
+// Direct-address count with TMA-staged streams (i32 keys, 16-byte aligned probe column). Same result and same match-cache
+// layout as k_count<K, true, MODE_DENSE>; the difference is HOW the two streams move: every warp owns a 256-row block of the
+// tile (its own rows of both vectors), double-buffers it in shared memory with cp.async.bulk + its own mbarrier, and sends the
+// match-cache words back with a bulk store. Only the table lookups go through LDG, so the L1TEX request path — the unit this
+// kernel saturates — carries 2^28 lookups instead of 2^28 + 2 x 2^25 sector requests. No block-wide barrier in the loop.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_count_dense_tma(const int32_t* __restrict__ S, int64_t nS, const char* __restrict__ body,
+                                                                   const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
+                                                                   unsigned long long* __restrict__ chunk_totals) {
+  if (hdr->mode != MODE_DENSE || hdr->all_present) return;
+  constexpr int KPV = 4, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
+  constexpr int CHUNK_TILES = chunk_tiles(4);
+  constexpr uint32_t VEC_BYTES = 32 * KPV * 4;                              // one warp's rows of one vector: 512 bytes
+  __shared__ __align__(128) int32_t keys_sm[2][WARPS][VECS_PER_THREAD][32 * KPV];
+  __shared__ __align__(128) uint32_t m_sm[2][WARPS][VECS_PER_THREAD][32 * KPV];
+  __shared__ __align__(8) unsigned long long bars[2][WARPS];
+  __shared__ unsigned long long red[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long kmin = hdr->kmin;
+  const unsigned long long drange = hdr->dense_range;
+  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
+  if (lane == 0) { mbar_init(&bars[0][warp], 1); mbar_init(&bars[1][warp], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  // rows of this warp in tile `t`: vector v covers [tile_base + (v * 256 + warp * 32) * 4, + 128 rows)
+  auto issue = [&](int t, int buf) {
+    const int64_t tile_base = chunk_base + (int64_t)t * TILE;
+    if (lane == 0) {
+      mbar_expect_tx(&bars[buf][warp], VECS_PER_THREAD * VEC_BYTES);
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++)
+        tma_load_1d(keys_sm[buf][warp][v], S + tile_base + (int64_t)(v * BLOCK_THREADS + warp * 32) * KPV, VEC_BYTES, &bars[buf][warp], pol_s);
+    }
+  };
+  // a tile is "full" when all its rows exist; the (single) ragged tile at the end of the relation takes the LDG path
+  auto full = [&](int t) { return chunk_base + (int64_t)(t + 1) * TILE <= nS; };
+
+  unsigned long long cnt = 0;
+  uint32_t phase[2] = {0, 0};
+  if (full(0)) issue(0, 0);
+  #pragma unroll 1
+  for (int t = 0; t < CHUNK_TILES; t++) {
+    const int64_t tile_base = chunk_base + (int64_t)t * TILE;
+    if (tile_base >= nS) break;
+    const int buf = t & 1;
+    if (t + 1 < CHUNK_TILES && full(t + 1)) issue(t + 1, buf ^ 1);        // prefetch the next tile's keys
+    int32_t key[KPT];
+    if (full(t)) {
+      mbar_wait(&bars[buf][warp], phase[buf]); phase[buf] ^= 1;
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) { const int4 x = *reinterpret_cast<const int4*>(&keys_sm[buf][warp][v][lane * KPV]); memcpy(&key[v * KPV], &x, 16); }
+    } else {
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<int32_t, true>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
+    }
+    uint32_t m[KPT];
+    #pragma unroll
+    for (int k = 0; k < KPT; k++) {
+      const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
+      m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
+    }
+    #pragma unroll
+    for (int k = 0; k < KPT; k++) cnt += (m[k] != ROW_NONE);
+    // match-cache words of this warp leave through shared memory + one bulk store per vector (the cache is padded to whole chunks)
+    tma_store_wait_read<VECS_PER_THREAD>();                               // the stores that last read m_sm[buf] (two tiles ago) are done reading
+    __syncwarp();
+    #pragma unroll
+    for (int v = 0; v < VECS_PER_THREAD; v++) *reinterpret_cast<uint4*>(&m_sm[buf][warp][v][lane * KPV]) = make_uint4(m[v * KPV], m[v * KPV + 1], m[v * KPV + 2], m[v * KPV + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++)
+        tma_store_1d(mcache + tile_base + (int64_t)(v * BLOCK_THREADS + warp * 32) * KPV, m_sm[buf][warp][v], VEC_BYTES, pol_s);
+    }
+  }
+  tma_store_wait_read<0>();
+  cnt = block_reduce_sum(cnt, red);
+  if (threadIdx.x == 0) chunk_totals[blockIdx.x] = cnt;
+}
+
 // =========================================================================================================
 // K3  scan of chunk totals -> exclusive chunk offsets, total at [nchunks]      (replaces join_v1.mlir:371-420)
 // =========================================================================================================
@@ -555,6 +639,12 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets); \
     k_count<K, V, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);  \
     k_count<K, V, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+    if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
+      k_count_dense_tma<<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      k_count<int32_t, true, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      k_count<int32_t, true, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+    } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
 #undef HJ_LAUNCH_COUNT

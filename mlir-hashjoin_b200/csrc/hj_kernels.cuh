@@ -33,7 +33,8 @@ struct ScratchView {
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
 
 void set_allow_dense(int on);
-void set_locality(int on);      // debug/bench switch: 0 disables the slice-ordered build/probe of big tables
+void set_locality(int on);
+void set_tma_count(int on);     // debug/bench switch: 0 = LDG/STG streams in the direct-address count kernel instead of TMA bulk copies      // debug/bench switch: 0 disables the slice-ordered build/probe of big tables
 bool table_is_big(int64_t n_rows, int key_bytes);   // debug/bench switch: 0 forces the hash layout even for dense key ranges
 
 // K0+K1: clear + build.  payload == nullptr -> row id = row_base + i  (join_v1.mlir:232 stores the thread index).
