@@ -195,12 +195,17 @@ __device__ __forceinline__ void group_home(long long key, uint64_t n_pairs, uint
   KeyTraits<int64_t>::home((int64_t)key, n_pairs, pair, half);
 }
 // payload word of the matching slot (low 32 = end offset, high 32 = count), or 0 when the key is absent
-__device__ __forceinline__ unsigned long long group_finish(const char* __restrict__ body, uint64_t n_pairs, long long key, uint64_t pair, uint32_t half, Bucket b) {
-  for (uint32_t t = 0;; ) {
+__device__ __forceinline__ unsigned long long group_finish(const char* __restrict__ body, uint64_t n_pairs, long long key, Bucket b) {
+  if (b.w[0] == (unsigned long long)key && (uint32_t)b.w[1] != ROW_NONE) return b.w[1];
+  if (b.w[2] == (unsigned long long)key && (uint32_t)b.w[3] != ROW_NONE) return b.w[3];
+  if ((uint32_t)b.w[3] == ROW_NONE) return 0ULL;                // home bucket not full: the sequence ends here
+  uint64_t pair; uint32_t half;
+  group_home(key, n_pairs, pair, half);                         // rare: walk on from the recomputed home position
+  for (uint32_t t = 1;; t++) {
+    b = ld_bucket(body + probe_bucket(pair, half, t, n_pairs) * 32);
     if (b.w[0] == (unsigned long long)key && (uint32_t)b.w[1] != ROW_NONE) return b.w[1];
     if (b.w[2] == (unsigned long long)key && (uint32_t)b.w[3] != ROW_NONE) return b.w[3];
-    if ((uint32_t)b.w[3] == ROW_NONE) return 0ULL;              // bucket not full: the sequence ends here
-    b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
+    if ((uint32_t)b.w[3] == ROW_NONE) return 0ULL;
   }
 }
 

@@ -410,15 +410,27 @@ __device__ __forceinline__ void load_vec_u32(const uint32_t* __restrict__ src, i
 
 // first match of `key` (unique build): row id or ROW_NONE
 template <typename K>
-__device__ __forceinline__ uint32_t finish_probe_unique(const char* __restrict__ body, uint64_t n_pairs, K key, uint64_t pair, uint32_t half, Bucket b) {
+__device__ __forceinline__ uint32_t finish_probe_unique(const char* __restrict__ body, uint64_t n_pairs, K key, Bucket b) {
   using T = KeyTraits<K>;
-  for (uint32_t t = 0;; ) {
+  #pragma unroll
+  for (int e = 0; e < T::SLOTS; e++) if (slot_match(b, e, key)) return slot_row(b, e, key);
+  if (slot_empty(b, T::SLOTS - 1, key)) return ROW_NONE;          // home bucket not full: the sequence ends here (the common case)
+  uint64_t pair; uint32_t half;                                    // rare: walk on; the home position is recomputed, not kept live
+  T::home(key, n_pairs, pair, half);
+  for (uint32_t t = 1;; t++) {
+    b = ld_bucket(body + probe_bucket(pair, half, t, n_pairs) * 32);
     #pragma unroll
     for (int e = 0; e < T::SLOTS; e++) if (slot_match(b, e, key)) return slot_row(b, e, key);
-    if (slot_empty(b, T::SLOTS - 1, key)) return ROW_NONE;        // bucket not full: the sequence ends here
-    b = ld_bucket(body + probe_bucket(pair, half, ++t, n_pairs) * 32);
+    if (slot_empty(b, T::SLOTS - 1, key)) return ROW_NONE;
   }
 }
+template <typename K>
+__device__ __forceinline__ const char* home_bucket(const char* __restrict__ body, uint64_t n_pairs, K key) {
+  uint64_t pair; uint32_t half;
+  KeyTraits<K>::home(key, n_pairs, pair, half);
+  return body + probe_bucket(pair, half, 0, n_pairs) * 32;
+}
+
 // One instantiation per table layout (MODE): the count launch queues all three and the two that do not match the header
 // exit at once. Keeping them separate keeps registers per thread (and so occupancy) at what each layout needs.
 template <typename K, bool VEC, uint32_t MODE>
@@ -443,6 +455,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   for (int tile = 0; tile < CHUNK_TILES; tile++) {
     const int64_t tile_base = chunk_base + (int64_t)tile * TILE;
     if (tile_base >= nS) break;
+    if constexpr (mode != MODE_DENSE) {
+      // bucketised layouts: one vector (KPV keys) at a time — its home buckets are in flight together, then each probe sequence
+      // is finished. KPV x 32 bytes of bucket data in registers keeps the kernel at 5-6 CTAs per SM, which hides the serial
+      // finish loops better than more loads per thread would.
+      #pragma unroll 1
+      for (int v = 0; v < VECS_PER_THREAD; v++) {
+        const int64_t i0 = tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV;
+        K kv[KPV]; uint32_t mv[KPV]; Bucket b[KPV];
+        load_vec_keys<K, VEC>(S, nS, i0, pol_s, kv);                        // rows past nS read as key 0: a harmless extra load
+        #pragma unroll
+        for (int e = 0; e < KPV; e++)
+          b[e] = ld_bucket(mode == MODE_HASH ? home_bucket<K>(body, n_pairs, kv[e]) : home_bucket<int64_t>(body, n_pairs, (int64_t)kv[e]));
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) {
+          if constexpr (mode == MODE_HASH) { mv[e] = i0 + e < nS ? finish_probe_unique<K>(body, n_pairs, kv[e], b[e]) : ROW_NONE; cnt += (mv[e] != ROW_NONE); }
+          else { mv[e] = i0 + e < nS ? (uint32_t)(group_finish(body, n_pairs, (long long)kv[e], b[e]) >> 32) : 0u; cnt += mv[e]; }
+        }
+        store_vec_u32<KPV>(mcache, i0, pol_s, mv);
+      }
+      continue;
+    }
     K key[KPT];
     #pragma unroll
     for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
@@ -464,44 +497,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
       }
       #pragma unroll
       for (int k = 0; k < KPT; k++) cnt += (m[k] != ROW_NONE);
-    } else if constexpr (mode == MODE_HASH) {
-      // unique build, bucketised table: the first probe of KPV keys is in flight together, then each sequence is finished
-      #pragma unroll
-      for (int v = 0; v < VECS_PER_THREAD; v++) {
-        uint64_t pair[KPV]; uint32_t half[KPV]; Bucket b[KPV]; bool valid[KPV];
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) {
-          valid[e] = elem_index<KPV>(tile_base, v * KPV + e) < nS;
-          T::home(key[v * KPV + e], n_pairs, pair[e], half[e]);
-        }
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) if (valid[e]) b[e] = ld_bucket(body + probe_bucket(pair[e], half[e], 0, n_pairs) * 32);
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) {
-          const int k = v * KPV + e;
-          m[k] = valid[e] ? finish_probe_unique<K>(body, n_pairs, key[k], pair[e], half[e], b[e]) : ROW_NONE;
-          cnt += (m[k] != ROW_NONE);
-        }
-      }
-    } else {
-      // grouped layout (duplicate build keys): one unique-style probe per row yields the match count; the cache holds it
-      #pragma unroll
-      for (int v = 0; v < VECS_PER_THREAD; v++) {
-        uint64_t pair[KPV]; uint32_t half[KPV]; Bucket b[KPV]; bool valid[KPV];
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) {
-          valid[e] = elem_index<KPV>(tile_base, v * KPV + e) < nS;
-          group_home((long long)key[v * KPV + e], n_pairs, pair[e], half[e]);
-        }
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) if (valid[e]) b[e] = ld_bucket(body + probe_bucket(pair[e], half[e], 0, n_pairs) * 32);
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) {
-          const int k = v * KPV + e;
-          m[k] = valid[e] ? (uint32_t)(group_finish(body, n_pairs, (long long)key[k], pair[e], half[e], b[e]) >> 32) : 0u;
-          cnt += m[k];
-        }
-      }
     }
     #pragma unroll
     for (int v = 0; v < VECS_PER_THREAD; v++) store_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
@@ -749,9 +744,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
         if (n) {
           const int64_t j = elem_index<KPV>(tile_base, k);
           prow = probe_row(j);
-          uint64_t pair; uint32_t half;
-          group_home((long long)key[k], n_pairs, pair, half);
-          const unsigned long long pay = group_finish(body, n_pairs, (long long)key[k], pair, half, ld_bucket(body + probe_bucket(pair, half, 0, n_pairs) * 32));
+          const unsigned long long pay = group_finish(body, n_pairs, (long long)key[k], ld_bucket(home_bucket<int64_t>(body, n_pairs, (int64_t)key[k])));
           start = (uint32_t)pay - n;                                          // low half = end of the key's row range
         }
         // warp-cooperative copy for long runs (output-heavy joins), per-thread copy for short ones
