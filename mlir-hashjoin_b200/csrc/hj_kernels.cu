@@ -166,16 +166,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_dense(const K* __restri
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const long long kmin = hdr->kmin;
   const uint64_t pol = policy_evict_first();
-  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
-  K key[KPV];
-  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
   bool dup = false;
-  #pragma unroll
-  for (int e = 0; e < KPV; e++) {
-    if (i0 + e < nR) {
-      const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
-      const uint32_t old = atomicExch(tab + (unsigned long long)((long long)key[e] - kmin), row);
-      dup |= old != ROW_NONE;
+  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+    K key[KPV];
+    load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+    #pragma unroll
+    for (int e = 0; e < KPV; e++) {
+      if (i0 + e < nR) {
+        const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
+        const uint32_t old = atomicExch(tab + (unsigned long long)((long long)key[e] - kmin), row);
+        dup |= old != ROW_NONE;
+      }
     }
   }
   if (__ballot_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) atomicOr(&hdr->need_fallback, 1u);
@@ -209,16 +210,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restric
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const uint64_t n_pairs = hdr->n_pairs;
   const uint64_t pol = policy_evict_first();
-  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
-  K key[KPV];
-  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
   bool dup = false;
-  #pragma unroll
-  for (int e = 0; e < KPV; e++) {
-    if (i0 + e < nR) {
-      const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);          // R may be a slice-ordered copy: perm = original index
-      const uint32_t row = payload ? payload[idx] : row_base + idx;
-      dup |= insert_one<K>(body, n_pairs, key[e], row, &hdr->has_dups);
+  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+    K key[KPV];
+    load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+    #pragma unroll
+    for (int e = 0; e < KPV; e++) {
+      if (i0 + e < nR) {
+        const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);        // R may be a slice-ordered copy: perm = original index
+        const uint32_t row = payload ? payload[idx] : row_base + idx;
+        dup |= insert_one<K>(body, n_pairs, key[e], row, &hdr->has_dups);
+      }
     }
   }
   if (__ballot_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) atomicOr(&hdr->has_dups, 1u);
@@ -262,12 +264,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_count(const K* __restri
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const uint64_t n_pairs = hdr->n_pairs;
   const uint64_t pol = policy_evict_first();
-  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
-  K key[KPV];
-  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
-  #pragma unroll
-  for (int e = 0; e < KPV; e++)
-    if (i0 + e < nR) atomicAdd(group_slot(body, n_pairs, (long long)key[e], true), 1ULL << 32);     // count lives in the high half
+  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+    K key[KPV];
+    load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+    #pragma unroll
+    for (int e = 0; e < KPV; e++)
+      if (i0 + e < nR) atomicAdd(group_slot(body, n_pairs, (long long)key[e], true), 1ULL << 32);   // count lives in the high half
+  }
 }
 
 // hand every occupied slot a contiguous range of the row-id array: block scan of the counts + one atomic per CTA
@@ -299,19 +302,24 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restric
   const uint64_t n_pairs = hdr->n_pairs;
   uint32_t* rows = reinterpret_cast<uint32_t*>(body + hdr->rows_offset);
   const uint64_t pol = policy_evict_first();
-  const int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV;
-  K key[KPV];
-  load_vec_keys<K, VEC>(R, nR, i0, pol, key);
-  #pragma unroll
-  for (int e = 0; e < KPV; e++) {
-    if (i0 + e < nR) {
-      unsigned long long* pay = group_slot(body, n_pairs, (long long)key[e], false);
-      const unsigned long long old = atomicAdd(pay, 1ULL);        // low half is the write cursor of this key's range
-      const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);
-      rows[(uint32_t)old] = payload ? payload[idx] : row_base + idx;
+  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+    K key[KPV];
+    load_vec_keys<K, VEC>(R, nR, i0, pol, key);
+    #pragma unroll
+    for (int e = 0; e < KPV; e++) {
+      if (i0 + e < nR) {
+        unsigned long long* pay = group_slot(body, n_pairs, (long long)key[e], false);
+        const unsigned long long old = atomicAdd(pay, 1ULL);      // low half is the write cursor of this key's range
+        const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);
+        rows[(uint32_t)old] = payload ? payload[idx] : row_base + idx;
+      }
     }
   }
 }
+
+// kernels that may have nothing to do (their layout was not chosen) run on a bounded grid and loop: an idle launch then
+// costs ~3 us instead of ~12 us for 16 K CTAs that only read the header and exit
+constexpr int PERSIST_GRID = 148 * 8;
 
 static int g_allow_dense = 1;
 static int g_locality = 1;
@@ -335,7 +343,7 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
                                 bool big, char* reorder_area, cudaStream_t stream) {
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const int64_t threads = (nR + KPV - 1) / KPV;
-  const unsigned grid = (unsigned)((threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
+  const unsigned grid = (unsigned)std::min<int64_t>(PERSIST_GRID * 4, (threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
   if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
@@ -436,7 +444,7 @@ __device__ __forceinline__ const char* home_bucket(const char* __restrict__ body
 template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
-                                                         unsigned long long* __restrict__ chunk_totals) {
+                                                         unsigned long long* __restrict__ chunk_totals, int64_t nchunks) {
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
@@ -448,7 +456,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   const unsigned long long drange = hdr->dense_range;
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
   constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
-  const int64_t chunk_base = (int64_t)blockIdx.x * (TILE * CHUNK_TILES);
+  #pragma unroll 1
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {   // bounded grid: consecutive CTAs take consecutive chunks
+  const int64_t chunk_base = chunk * (TILE * CHUNK_TILES);
   unsigned long long cnt = 0;
 
   #pragma unroll 1
@@ -502,7 +512,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
     for (int v = 0; v < VECS_PER_THREAD; v++) store_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
   }
   cnt = block_reduce_sum(cnt, red);
-  if (threadIdx.x == 0) chunk_totals[blockIdx.x] = cnt;
+  if (threadIdx.x == 0) chunk_totals[chunk] = cnt;
+  }
 }
 
 // Direct-address count with TMA-staged streams (i32 keys, 16-byte aligned probe column). Same result and same match-cache
@@ -631,14 +642,14 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     const unsigned grid = (unsigned)sv.nchunks;
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
-    k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets); \
-    k_count<K, V, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);  \
-    k_count<K, V, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+    k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks); \
+    k_count<K, V, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);  \
+    k_count<K, V, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
     if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
-      k_count_dense_tma<<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
+      k_count<int32_t, true, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+      k_count<int32_t, true, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
