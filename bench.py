@@ -140,13 +140,13 @@ def workload_name(args, cfg) -> str:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale-log2", type=int, default=0, help="shrink (<0) the workload by 2^k rows on both sides (debug only)")
     ap.add_argument("--cpu-sample-log2", type=int, default=26, help="probe rows of the CPU baseline sample (2^k)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5 only: peer-store partition kernel vs partition + NCCL all-to-all")
@@ -246,10 +246,11 @@ def main() -> None:
             join.probeRelation(dS, table, outR, outS, probeRowBase=plo)
         ev[3].record(stream)
         n_out[0] = n
-        launches[0] += 12                                  # 9 build-sequence launches, k_count, k_scan_chunks, k_write
+        launches[0] += 19                                  # 13 build-sequence launches, 3 k_count instantiations, k_scan_chunks, 2 k_write instantiations
         return ev, (outR, outS)
 
     def run_timed(steps, warmup, sample_clocks):
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None   # nvidia-smi needs ~100 ms to start: launch it before the warm-up
         for _ in range(warmup):
             step(False)
         torch.cuda.synchronize()
@@ -257,7 +258,6 @@ def main() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
         t0 = time.perf_counter()
         all_ev, last = [], None
         for _ in range(steps):
@@ -349,7 +349,7 @@ def main() -> None:
     if phase_ms["count"]:
         k_ms = {k: sum(v) / len(v) for k, v in phase_ms.items()}
         dom = max(k_ms, key=k_ms.get)
-        kernel = {"build": "k_build (+memset, k_init_header)", "count": "k_count (+k_scan_tiles and the 8-byte readback)", "write": "k_write"}[dom]
+        kernel = {"build": "build sequence (k_minmax, k_clear, k_build_dense | k_build_hash, ...)", "count": "k_count (+ k_scan_chunks and the 8-byte result-size readback)", "write": "k_write"}[dom]
         ach = ab[dom] / (k_ms[dom] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "algorithmic_bytes": ab[dom], "kernel_ms": k_ms[dom], "peak_source": peak_src,
@@ -369,7 +369,7 @@ def main() -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload != "c5" else "weak",
             "vs_baseline": None, "dtype": "int32" if kb == 4 else "int64", "data": "synthetic (seeded device generators, bit-identical to the oracle's)",
             "config": {"workload": workload_name(args, cfg), "build_rows": nR_job, "probe_rows": nS_job, "result_pairs": int(tot_out.item()),
-                       "l2_hygiene": "inputs larger than L2 (probe column >= 1 GiB per GPU, table 256 MiB vs 126 MB L2)",
+                       "l2_hygiene": "inputs larger than L2 (probe column >= 1 GiB per GPU streams through every step)",
                        "timing": "CUDA events on the launching stream per step, summed over steps, max over ranks",
                        "wall_ms_per_step": wall_ms_per_step, "table_layout": args.layout},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches, "clocks": clocks, "parity": parity, "hash_layout": hash_arm}

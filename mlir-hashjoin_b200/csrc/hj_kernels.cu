@@ -639,16 +639,17 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     }
   }
   if (sv.nchunks > 0) {
-    const unsigned grid = (unsigned)sv.nchunks;
+    const unsigned grid = (unsigned)sv.nchunks;                               // direct-address layout: one chunk per CTA
+    const unsigned grid_p = (unsigned)std::min<int64_t>(sv.nchunks, PERSIST_GRID * 2);   // bucketised layouts: bounded grid (idle launch ~3 us), slice-ordered window stays tight
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
     k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks); \
-    k_count<K, V, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);  \
-    k_count<K, V, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+    k_count<K, V, MODE_HASH><<<grid_p, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);  \
+    k_count<K, V, MODE_GROUP><<<grid_p, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
     if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
       k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_HASH><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
-      k_count<int32_t, true, MODE_GROUP><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+      k_count<int32_t, true, MODE_HASH><<<grid_p, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+      k_count<int32_t, true, MODE_GROUP><<<grid_p, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
       if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
