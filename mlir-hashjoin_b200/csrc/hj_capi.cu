@@ -470,6 +470,7 @@ void hashJoinRelease(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_tables) { if (kv.second.table) cudaFree(kv.second.table); if (kv.second.scratch) cudaFree(kv.second.scratch); }
   g_tables.clear();
+  { std::lock_guard<std::mutex> lk2(g_note_mu); g_table_big.clear(); g_scratch_reordered.clear(); }
   g_hR.release(); g_hS.release(); g_hT.release(); g_hSc.release(); g_hOr.release(); g_hOs.release();
 }
 

@@ -38,6 +38,7 @@ struct TableHeader {
   unsigned long long rows_offset; // grouped layout: byte offset of the u32 row-id array inside the body
   unsigned long long group_cursor;// grouped layout: bump allocator over the row-id array
   unsigned long long n_groups;    // grouped layout: distinct build keys
+  unsigned long long work[4];     // ticket counters of the slice-ordered build kernels (hash, group count, group fill)
 };
 static_assert(sizeof(TableHeader) <= HEADER_BYTES, "header too large");
 
@@ -245,6 +246,17 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* smem, T* total) {
   __syncthreads();
   return base + inc - v;
 }
+// Ticket scheduling for bounded grids: CTAs take block indices in order from a global counter, exactly like the hardware
+// block scheduler would, so the blocks in flight stay one contiguous window of the relation (a plain grid-stride loop lets
+// fast CTAs run ahead and the window — and with it the table slice being touched — spreads out).
+__device__ __forceinline__ long long next_ticket(unsigned long long* counter, long long* slot) {
+  if (threadIdx.x == 0) *slot = (long long)atomicAdd(counter, 1ULL);
+  __syncthreads();
+  const long long b = *slot;
+  __syncthreads();
+  return b;
+}
+
 template <typename T>
 __device__ __forceinline__ T block_reduce_sum(T v, T* smem) {            // result valid in every thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;

@@ -11,6 +11,8 @@
 // packed CAS (8-byte slot for i32 keys, 16-byte slot + ATOMG.CAS.128 for i64 keys).  Output contract is the
 // reference's: two i32 columns (build_row, probe_row), any order (join_v1.mlir:498-500, shared.cpp:168-171).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "hj_common.cuh"
 #include "hj_kernels.cuh"
 
@@ -56,7 +58,7 @@ int64_t num_chunks(int64_t n_probe, int key_bytes) {
 }
 static int64_t scratch_core_bytes(int64_t n_probe, int key_bytes) {
   const int64_t nc = num_chunks(n_probe, key_bytes);
-  return round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((nc + 1) * 8, 256);
+  return round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((nc + 1 + 4) * 8, 256);
 }
 // match cache + chunk offsets + room to reorder the probe relation (keys and original indices) for big tables
 int64_t scratch_bytes(int64_t n_probe, int key_bytes) { return scratch_core_bytes(n_probe, key_bytes) + reorder_bytes(n_probe, key_bytes) + 256; }
@@ -66,6 +68,7 @@ ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   v.nchunks = num_chunks(n_probe, key_bytes);
   v.mcache = reinterpret_cast<uint32_t*>(base);
   v.chunk_offsets = reinterpret_cast<unsigned long long*>(base + round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256));
+  v.counters = v.chunk_offsets + v.nchunks + 1;                 // ticket counters: [0] count<inline>, [1] count<grouped>, [2] write<grouped>
   v.reorder = base + scratch_core_bytes(n_probe, key_bytes);
   return v;
 }
@@ -93,6 +96,7 @@ __global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned lon
   hdr->n_pairs = pairs; hdr->n_rows = n_rows; hdr->kmin = 0x7FFFFFFFFFFFFFFFLL; hdr->kmax = -0x7FFFFFFFFFFFFFFFLL - 1;
   hdr->dense_range = 0; hdr->body_bytes = body_bytes; hdr->pairs_cap = body_bytes / 64;
   hdr->rows_offset = 0; hdr->group_cursor = 0; hdr->n_groups = 0;
+  hdr->work[0] = hdr->work[1] = hdr->work[2] = hdr->work[3] = 0;
 }
 
 template <typename K>
@@ -211,7 +215,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restric
   const uint64_t n_pairs = hdr->n_pairs;
   const uint64_t pol = policy_evict_first();
   bool dup = false;
-  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+  __shared__ long long ticket;
+  const long long nblocks = (nR + (long long)BLOCK_THREADS * KPV - 1) / ((long long)BLOCK_THREADS * KPV);
+  for (long long blk = next_ticket(&hdr->work[0], &ticket); blk < nblocks; blk = next_ticket(&hdr->work[0], &ticket)) {
+    const int64_t i0 = (blk * BLOCK_THREADS + threadIdx.x) * KPV;
     K key[KPV];
     load_vec_keys<K, VEC>(R, nR, i0, pol, key);
     #pragma unroll
@@ -264,7 +271,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_count(const K* __restri
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const uint64_t n_pairs = hdr->n_pairs;
   const uint64_t pol = policy_evict_first();
-  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+  __shared__ long long ticket;
+  const long long nblocks = (nR + (long long)BLOCK_THREADS * KPV - 1) / ((long long)BLOCK_THREADS * KPV);
+  for (long long blk = next_ticket(&hdr->work[1], &ticket); blk < nblocks; blk = next_ticket(&hdr->work[1], &ticket)) {
+    const int64_t i0 = (blk * BLOCK_THREADS + threadIdx.x) * KPV;
     K key[KPV];
     load_vec_keys<K, VEC>(R, nR, i0, pol, key);
     #pragma unroll
@@ -302,7 +312,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restric
   const uint64_t n_pairs = hdr->n_pairs;
   uint32_t* rows = reinterpret_cast<uint32_t*>(body + hdr->rows_offset);
   const uint64_t pol = policy_evict_first();
-  for (int64_t i0 = (blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x) * KPV; i0 < nR; i0 += (int64_t)gridDim.x * BLOCK_THREADS * KPV) {
+  __shared__ long long ticket;
+  const long long nblocks = (nR + (long long)BLOCK_THREADS * KPV - 1) / ((long long)BLOCK_THREADS * KPV);
+  for (long long blk = next_ticket(&hdr->work[2], &ticket); blk < nblocks; blk = next_ticket(&hdr->work[2], &ticket)) {
+    const int64_t i0 = (blk * BLOCK_THREADS + threadIdx.x) * KPV;
     K key[KPV];
     load_vec_keys<K, VEC>(R, nR, i0, pol, key);
     #pragma unroll
@@ -320,6 +333,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restric
 // kernels that may have nothing to do (their layout was not chosen) run on a bounded grid and loop: an idle launch then
 // costs ~3 us instead of ~12 us for 16 K CTAs that only read the header and exit
 constexpr int PERSIST_GRID = 148 * 8;
+// Slice-ordered kernels walk the relation grid-stride, so the CTAs in flight cover ONE contiguous window of it (and one slice of
+// the table). That only holds while every CTA of the grid is resident: a grid larger than one wave would sweep the table once per
+// wave. resident_grid() = occupancy x SM count for the given kernel, cached.
+static int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+template <typename Kern>
+static unsigned resident_grid(Kern kern, int64_t needed_blocks) {
+  int per_sm = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS, 0);
+  if (getenv("HJ_DEBUG")) fprintf(stderr, "[hj] resident_grid: err=%d per_sm=%d sms=%d needed=%lld\n", (int)oe, per_sm, num_sms(), (long long)needed_blocks);
+  if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(needed_blocks, (int64_t)per_sm * num_sms()));
+}
 
 static int g_allow_dense = 1;
 static int g_locality = 1;
@@ -343,7 +372,7 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
                                 bool big, char* reorder_area, cudaStream_t stream) {
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const int64_t threads = (nR + KPV - 1) / KPV;
-  const unsigned grid = (unsigned)std::min<int64_t>(PERSIST_GRID * 4, (threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
+  const unsigned grid = (unsigned)std::min<int64_t>(PERSIST_GRID, (threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
   if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
@@ -362,22 +391,23 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
     }
   }
   const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0, vecb = (reinterpret_cast<uintptr_t>(Rb) & 15) == 0;
+  const int64_t need = (threads + BLOCK_THREADS - 1) / BLOCK_THREADS;
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 0);
   if (nR == 0) return cudaGetLastError();
-  if (vec) k_build_dense<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
-  else     k_build_dense<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
+  if (vec) k_build_dense<K, true><<<resident_grid(k_build_dense<K, true>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
+  else     k_build_dense<K, false><<<resident_grid(k_build_dense<K, false>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
   k_fallback_prepare<<<1, 1, 0, stream>>>(hdr, g_allow_dense == 2);
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
-  if (vecb) k_build_hash<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
-  else      k_build_hash<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  if (vecb) k_build_hash<K, true><<<resident_grid(k_build_hash<K, true>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  else      k_build_hash<K, false><<<resident_grid(k_build_hash<K, false>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
   // duplicates found: rebuild in the grouped layout (every kernel below exits at once otherwise)
   k_group_prepare<<<1, 1, 0, stream>>>(hdr);
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 2);
-  if (vecb) k_group_count<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
-  else      k_group_count<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
+  if (vecb) k_group_count<K, true><<<resident_grid(k_group_count<K, true>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
+  else      k_group_count<K, false><<<resident_grid(k_group_count<K, false>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
   k_group_offsets<<<clear_grid, BLOCK_THREADS, 0, stream>>>(body, hdr);
-  if (vecb) k_group_fill<K, true><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
-  else      k_group_fill<K, false><<<grid, BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  if (vecb) k_group_fill<K, true><<<resident_grid(k_group_fill<K, true>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  else      k_group_fill<K, false><<<resident_grid(k_group_fill<K, false>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
   return cudaGetLastError();
 }
 
@@ -444,7 +474,7 @@ __device__ __forceinline__ const char* home_bucket(const char* __restrict__ body
 template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
-                                                         unsigned long long* __restrict__ chunk_totals, int64_t nchunks) {
+                                                         unsigned long long* __restrict__ chunk_totals, int64_t nchunks, unsigned long long* tickets) {
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
@@ -457,7 +487,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
   constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
   #pragma unroll 1
-  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {   // bounded grid: consecutive CTAs take consecutive chunks
+  __shared__ long long ticket;
+  // direct-address layout: one chunk per CTA (full grid). Bucketised layouts: one resident wave taking chunks by ticket.
+  for (long long chunk = MODE == MODE_DENSE ? (long long)blockIdx.x : next_ticket(tickets, &ticket); chunk < nchunks;
+       chunk = MODE == MODE_DENSE ? chunk + gridDim.x : next_ticket(tickets, &ticket)) {
   const int64_t chunk_base = chunk * (TILE * CHUNK_TILES);
   unsigned long long cnt = 0;
 
@@ -638,19 +671,20 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
       S = rv.keys; *reordered = true;
     }
   }
+  { cudaError_t e = cudaMemsetAsync(sv.counters, 0, 4 * sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
   if (sv.nchunks > 0) {
     const unsigned grid = (unsigned)sv.nchunks;                               // direct-address layout: one chunk per CTA
-    const unsigned grid_p = (unsigned)std::min<int64_t>(sv.nchunks, PERSIST_GRID * 2);   // bucketised layouts: bounded grid (idle launch ~3 us), slice-ordered window stays tight
+    // bucketised layouts: one resident wave (idle launch ~3 us; the slice-ordered window stays tight)
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
-    k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks); \
-    k_count<K, V, MODE_HASH><<<grid_p, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);  \
-    k_count<K, V, MODE_GROUP><<<grid_p, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+    k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters); \
+    k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters);  \
+    k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1);
     if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
       k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_HASH><<<grid_p, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
-      k_count<int32_t, true, MODE_GROUP><<<grid_p, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
-      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks);
+      k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters);
+      k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1);
+      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
@@ -668,7 +702,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
 template <typename K, bool VEC, bool GROUPED>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache,
-                                                         const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks,
+                                                         const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks, unsigned long long* tickets,
                                                          int32_t* __restrict__ outR, int32_t* __restrict__ outS,
                                                          const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
   if ((hdr->mode == MODE_GROUP) != GROUPED) return;
@@ -688,7 +722,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
   constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
   #pragma unroll 1
-  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  __shared__ long long ticket;
+  for (long long chunk = GROUPED ? next_ticket(tickets, &ticket) : (long long)blockIdx.x; chunk < nchunks;
+       chunk = GROUPED ? next_ticket(tickets, &ticket) : chunk + gridDim.x) {
   const int64_t chunk_base = chunk * (TILE * CHUNK_TILES);
   unsigned long long out_base = chunk_offsets[chunk];
   if (chunk_offsets[chunk + 1] == out_base) continue;                        // nothing to emit for this chunk (uniform)
@@ -804,13 +840,13 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
   const unsigned grid = (unsigned)sv.nchunks;                                  // unique layouts (the common case): one chunk per CTA measures 10 % faster
-  const unsigned grid_g = (unsigned)std::min<int64_t>(sv.nchunks, PERSIST_GRID * 2);
   const void* S = S_in; const uint32_t* perm = nullptr;
   if (reordered) { ReorderView rv = reorder_view(sv.reorder, nS, key_bytes); S = rv.keys; perm = rv.idx; }
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+  { cudaError_t e = cudaMemsetAsync(sv.counters + 2, 0, sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
 #define HJ_LAUNCH_WRITE(K, V) \
-  k_write<K, V, false><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, outR, outS, perm, probe_payload, probe_row_base); \
-  k_write<K, V, true><<<grid_g, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, outR, outS, perm, probe_payload, probe_row_base);
+  k_write<K, V, false><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base); \
+  k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base);
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
@@ -874,7 +910,7 @@ __device__ __forceinline__ void part_load(const K* __restrict__ keys, int64_t ba
 //   scan   (k_part_scan)    start[part] + prefix over the CTAs                         -> mat[cta][part] = first destination element
 //   pass 2 (k_part_scatter) the same CTA walks the same tiles with running cursors in shared memory
 // (global atomics on the few per-part cursors serialise at about one per clock: 2.7 M of them cost > 1 ms at 2^28 tuples).
-constexpr int PART_GRID = 148 * 4;
+constexpr int PART_GRID = 148 * 6;
 
 __host__ __device__ inline int64_t part_tiles_per_cta(int64_t n, int grid) { const int64_t nt = (n + PART_TILE - 1) / PART_TILE; return (nt + grid - 1) / grid; }
 

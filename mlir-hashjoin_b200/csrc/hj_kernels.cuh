@@ -28,6 +28,7 @@ struct ScratchView {
   uint32_t* mcache;
   unsigned long long* chunk_offsets;  // after scan: exclusive offsets; [nchunks] = total
   int64_t nchunks;
+  unsigned long long* counters;       // ticket counters of the bounded-grid probe kernels
   char* reorder;                      // slice-ordered copy of the probe relation (big tables only)
 };
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
