@@ -149,6 +149,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--c5-total-log2", type=int, default=0, help="c5 only: fix the TOTAL rows per side at 2^k (strong scaling); default 2^28 rows per GPU (weak)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5 only: peer-store partition kernel vs partition + NCCL all-to-all")
     ap.add_argument("--layout", default="auto", choices=["auto", "hash"], help="hash = force the bucketised hash table even for dense key ranges")
     ap.add_argument("--no-hash-arm", action="store_true", help="skip the extra forced-hash-layout measurement")
@@ -162,6 +163,8 @@ def main() -> None:
     if args.workload == "c5":
         per_gpu = 1 << 28                       # rows per GPU per side: 2e9-row C5 at 8 GPUs is 2.5e8 rows per GPU
         n = per_gpu * args.gpus if args.scale_log2 == 0 else max(1, (per_gpu * args.gpus) >> -args.scale_log2)
+        if args.c5_total_log2:
+            n = 1 << args.c5_total_log2
         cfg = datagen.JoinConfig("C5", datagen.replace(cfg.build, n=n, domain=n), datagen.replace(cfg.probe, n=n, domain=n), n, cfg.note)
 
     if args.impl == "reference":
@@ -186,6 +189,8 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps NCCL's banner off stdout: rank 0 prints ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     b, p = cfg.build, cfg.probe
@@ -366,7 +371,7 @@ def main() -> None:
         cpu.pop("seconds", None)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload != "c5" else "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (args.workload == "c5" and args.c5_total_log2) else "weak",
             "vs_baseline": None, "dtype": "int32" if kb == 4 else "int64", "data": "synthetic (seeded device generators, bit-identical to the oracle's)",
             "config": {"workload": workload_name(args, cfg), "build_rows": nR_job, "probe_rows": nS_job, "result_pairs": int(tot_out.item()),
                        "l2_hygiene": "inputs larger than L2 (probe column >= 1 GiB per GPU streams through every step)",

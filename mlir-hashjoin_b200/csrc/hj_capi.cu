@@ -172,6 +172,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
 
 int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjCount", "null pointer or bad key width");
+  if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjCount", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
   if (reinterpret_cast<uintptr_t>(dScratch) & 15) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 16-byte aligned");
   if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
   bool big = true, reordered = false;                      // unknown table (not built through this process): look at its header

@@ -86,6 +86,29 @@ def test_unique_build_partial_hits(lib, cuda, oracle):
     _assert_parity(oracle, R, S, a, b)
 
 
+def test_tma_staged_count_kernel(lib, cuda, oracle):
+    """hjSetTmaCount(1): the experimental direct-address count kernel with cp.async.bulk staged streams (off by default because it
+    is slower) must give the same result, including the ragged last tile that falls back to LDG."""
+    rng = np.random.default_rng(4)
+    lib.hjSetTmaCount(1)
+    try:
+        for nR, nS in ((1024, 4096), (5000, 2048 * 8 * 3 + 777), (70000, 200003)):
+            R = rng.permutation(2 * nR).astype(np.int32)[:nR]
+            S = rng.integers(-5, 2 * nR + 5, nS).astype(np.int32)
+            a, b = _join_np(R, S, cuda)
+            _assert_parity(oracle, R, S, a, b)
+    finally:
+        lib.hjSetTmaCount(0)
+
+
+def test_row_id_limits(lib, cuda):
+    """Row ids are 32-bit patterns (join_v1.mlir:604-605): relations with more rows than that are refused, not wrapped."""
+    import torch
+    t = torch.empty(1 << 12, dtype=torch.uint8, device=cuda)
+    assert lib.hjBuild(t.data_ptr(), (1 << 32), 4, None, 0, t.data_ptr(), t.numel(), None) < 0
+    assert lib.hjCountAsync(t.data_ptr(), (1 << 32) + 5, 4, t.data_ptr(), t.data_ptr(), t.numel(), None) < 0
+
+
 def test_empty_inputs(lib, cuda, oracle):
     e = np.empty(0, np.int32)
     for R, S in ((e, np.arange(10, dtype=np.int32)), (np.arange(10, dtype=np.int32), e), (e, e)):
