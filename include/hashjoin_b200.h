@@ -121,6 +121,13 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
  * probe row id = probeRowBase + j (join_v1.mlir:499-500 stores the thread index). Asynchronous. */
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+/* K2+K3+K4 in ONE pass for callers that can bound the result size before probing (capacity = nS for a unique build): lookup,
+ * decoupled look-back over the tiles' match counts, pairs streamed straight into the result columns; no match cache and no second
+ * pass over the probe relation. The reference's call sequence (count, allocate, probe: join_v1.mlir:591,604-605) cannot use
+ * it. Returns the number of pairs; pairs beyond `capacity` are counted but not written. HJ_ERR_STATE when the build keys were not
+ * unique (use hjCount + hjWrite). Synchronous. */
+int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                    int32_t* dOutR, int32_t* dOutS, int64_t capacity, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
 /* K5. Radix partition on the key hash into nParts (<= 256) contiguous ranges; dOffsets: u64[nParts+1]. Asynchronous. */
 int64_t hjPartitionWorkspaceBytes(int64_t n, int32_t nParts);
 int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,

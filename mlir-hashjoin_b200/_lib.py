@@ -63,6 +63,7 @@ _SIGNATURES = {
     "hjCountResult": (_i64, [_vp, _i64, _i32, _vp]),
     "hjCount": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     "hjWrite": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "hjJoinFused": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _u32, _vp]),
     "hjPartitionWorkspaceBytes": (_i64, [_i64, _i32]),
     "hjPartition": (_i32, [_vp, _vp, _u32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "hjPartitionCount": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),

@@ -207,6 +207,22 @@ int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
   return HJ_OK;
 }
 
+// Single pass (K2+K3+K4 fused, decoupled look-back). Synchronous: returns the number of pairs found; pairs beyond `capacity`
+// are counted, not written (the caller then retries with count + write or a bigger result). Grouped tables (duplicate build
+// keys) are not handled by the fused kernel: HJ_ERR_STATE, use hjCount + hjWrite.
+int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                    int32_t* dOutR, int32_t* dOutS, int64_t capacity, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+  if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch || capacity < 0 || (capacity > 0 && (!dOutR || !dOutS)))
+    return fail(HJ_ERR_ARG, "hjJoinFused", "null pointer or bad key width");
+  if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjJoinFused", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
+  if ((reinterpret_cast<uintptr_t>(dScratch) & 15) || scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjJoinFused", "scratch workspace misaligned or too small (see hjScratchBytes)");
+  HJ_CUDA("hjJoinFused", hj::join_fused_async(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, capacity, dProbePayload, probeRowBase, S_(stream)));
+  uint32_t mode = 0;
+  HJ_CUDA("hjJoinFused", hj::read_table_mode(dTable, &mode, S_(stream)));
+  if (mode == 2) return fail(HJ_ERR_STATE, "hjJoinFused", "build keys are not unique (grouped table): use hjCount + hjWrite");
+  return hjCountResult(dScratch, nS, keyBytes, stream);
+}
+
 int64_t hjPartitionWorkspaceBytes(int64_t n, int32_t nParts) { return hj::partition_workspace_bytes(n, nParts); }
 
 int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,

@@ -367,6 +367,13 @@ static cudaError_t read_header(const void* table, TableHeader* out, cudaStream_t
   return e;
 }
 
+cudaError_t read_table_mode(const void* table, uint32_t* mode, cudaStream_t stream) {
+  TableHeader h;
+  cudaError_t e = read_header(table, &h, stream);
+  if (e == cudaSuccess) *mode = h.mode;
+  return e;
+}
+
 template <typename K>
 static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32_t row_base, char* body, TableHeader* hdr, int64_t pairs,
                                 bool big, char* reorder_area, cudaStream_t stream) {
@@ -850,6 +857,142 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
+  return cudaGetLastError();
+}
+
+// =========================================================================================================
+// K2+K3+K4 fused: single-pass probe for callers that can bound the result size up front (e.g. capacity = |S| for a unique
+// build). One kernel looks up a tile, publishes its match count, obtains its output offset by DECOUPLED LOOK-BACK over the
+// tiles before it (tiles are taken by ticket, so every tile a CTA waits for is already running) and streams its pairs
+// straight into the result columns: no match cache, no second pass over the probe relation. The reference's call sequence
+// (countRows -> allocate -> probeRelation, join_v1.mlir:591,604-605) cannot use it; hjJoinFused can.
+// =========================================================================================================
+constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INCL = 2ULL << 62, LB_MASK = (1ULL << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <typename K, bool VEC, uint32_t MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,
+                                                              unsigned long long* __restrict__ tile_state, unsigned long long* tickets, int64_t ntiles,
+                                                              int32_t* __restrict__ outR, int32_t* __restrict__ outS, unsigned long long capacity,
+                                                              const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
+                                                              unsigned long long* __restrict__ total_out) {
+  using T = KeyTraits<K>;
+  if (hdr->mode != MODE) return;
+  constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
+  __shared__ long long ticket;
+  __shared__ uint32_t wt[WARPS];
+  __shared__ unsigned long long base_sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t n_pairs = hdr->n_pairs;
+  const long long kmin = hdr->kmin;
+  const unsigned long long drange = hdr->dense_range;
+  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+
+  for (long long tile = next_ticket(tickets, &ticket); tile < ntiles; tile = next_ticket(tickets, &ticket)) {
+    const int64_t tile_base = tile * TILE;
+    K key[KPT];
+    #pragma unroll
+    for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
+    uint32_t m[KPT];
+    if constexpr (MODE == MODE_DENSE) {
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
+        m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
+      }
+    } else {
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) {
+        Bucket b[KPV];
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) b[e] = ld_bucket(home_bucket<K>(body, n_pairs, key[v * KPV + e]));
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) {
+          const int k = v * KPV + e;
+          m[k] = elem_index<KPV>(tile_base, k) < nS ? finish_probe_unique<K>(body, n_pairs, key[k], b[e]) : ROW_NONE;
+        }
+      }
+    }
+    unsigned mask[KPT];
+    uint32_t wtot = 0;
+    #pragma unroll
+    for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, m[k] != ROW_NONE); wtot += __popc(mask[k]); }
+    if (lane == 0) wt[warp] = wtot;
+    __syncthreads();
+    uint32_t wbase = 0, ttot = 0;
+    #pragma unroll
+    for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[w]; wbase += w < warp ? x : 0u; ttot += x; }
+
+    // decoupled look-back, one warp: publish this tile's aggregate, then sum the tiles before it until an inclusive prefix shows up
+    if (warp == 0) {
+      if (lane == 0) st_release_u64(tile_state + tile, (tile == 0 ? LB_INCL : LB_AGG) | ttot);
+      unsigned long long prefix = 0;
+      long long j = tile - 1;
+      while (j >= 0) {
+        const long long idx = j - lane;
+        unsigned long long st = idx >= 0 ? ld_acquire_u64(tile_state + idx) : LB_INCL;
+        while (__any_sync(0xffffffffu, (st >> 62) == 0)) { if ((st >> 62) == 0) st = ld_acquire_u64(tile_state + idx); }
+        const unsigned incl = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+        const int first = incl ? __ffs(incl) - 1 : 32;
+        unsigned long long v = lane <= first ? (st & LB_MASK) : 0ULL;
+        v = warp_reduce_sum(v);
+        prefix += v;
+        if (first < 32) break;
+        j -= 32;
+      }
+      if (lane == 0) {
+        if (tile > 0) st_release_u64(tile_state + tile, LB_INCL | (prefix + ttot));
+        base_sm = prefix;
+        if (tile == ntiles - 1) *total_out = prefix + ttot;
+      }
+    }
+    __syncthreads();
+    unsigned long long o = base_sm + wbase;
+    const unsigned lt = (1u << lane) - 1u;
+    #pragma unroll
+    for (int k = 0; k < KPT; k++) {
+      if (m[k] != ROW_NONE) {
+        const unsigned long long dst = o + __popc(mask[k] & lt);
+        if (dst < capacity) {
+          const int64_t j = elem_index<KPV>(tile_base, k);
+          st_stream_u32(outR + dst, m[k], pol_s);
+          st_stream_u32(outS + dst, probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j, pol_s);
+        }
+      }
+      o += __popc(mask[k]);
+    }
+  }
+}
+
+// Returns through total_out (device, u64): pairs found (pairs beyond `capacity` are counted but not written). *unsupported is set
+// when the table is in the grouped layout (duplicate build keys): the caller falls back to count + write.
+cudaError_t join_fused_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, int32_t* outR, int32_t* outS, int64_t capacity,
+                             const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+  ScratchView sv = scratch_view(scratch, nS, key_bytes);
+  const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
+  const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
+  const int64_t ntiles = (nS + tile_keys(key_bytes) - 1) / tile_keys(key_bytes);
+  unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(sv.mcache);      // the match cache is not needed: reuse it (8 B per tile)
+  unsigned long long* total = sv.chunk_offsets + sv.nchunks;                              // same slot the two-phase path reports in
+  cudaError_t e = cudaMemsetAsync(sv.counters, 0, 4 * sizeof(unsigned long long), stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(total, 0, 8, stream);
+  if (e == cudaSuccess && ntiles > 0) e = cudaMemsetAsync(tile_state, 0, (size_t)ntiles * 8, stream);
+  if (e != cudaSuccess || ntiles == 0) return e;
+  const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+#define HJ_LAUNCH_FUSED(K, V) \
+  k_join_fused<K, V, MODE_DENSE><<<resident_grid(k_join_fused<K, V, MODE_DENSE>, ntiles), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, tile_state, sv.counters, ntiles, outR, outS, (unsigned long long)capacity, probe_payload, probe_row_base, total); \
+  k_join_fused<K, V, MODE_HASH><<<resident_grid(k_join_fused<K, V, MODE_HASH>, ntiles), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, tile_state, sv.counters + 1, ntiles, outR, outS, (unsigned long long)capacity, probe_payload, probe_row_base, total);
+  if (key_bytes == 4) { if (vec) { HJ_LAUNCH_FUSED(int32_t, true) } else { HJ_LAUNCH_FUSED(int32_t, false) } }
+  else                { if (vec) { HJ_LAUNCH_FUSED(int64_t, true) } else { HJ_LAUNCH_FUSED(int64_t, false) } }
+#undef HJ_LAUNCH_FUSED
   return cudaGetLastError();
 }
 

@@ -51,6 +51,11 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
                         int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, bool reordered,
                         cudaStream_t stream);
 
+// K2+K3+K4 fused (single pass, decoupled look-back): unique layouts only; the total lands where count_rows_async puts it.
+cudaError_t join_fused_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, int32_t* outR, int32_t* outS, int64_t capacity,
+                             const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
+cudaError_t read_table_mode(const void* table, uint32_t* mode, cudaStream_t stream);
+
 // K5: radix partition by the key hash (multi-GPU shuffle feed).  Two launches: histogram, scatter.
 //   counts: u64[n_parts] (device, zeroed by the call); offsets computed on device; keys/rows scattered so that
 //   partition p occupies [offsets[p], offsets[p+1]) of out_keys/out_rows.  offsets: u64[n_parts+1] device.

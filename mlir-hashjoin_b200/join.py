@@ -116,6 +116,22 @@ def probeRelation(probeRelation_: torch.Tensor, table: HashTable, resultIndicesR
     _lib.check_status(rc, "hjWrite")
 
 
+def join_fused(probeRelation_: torch.Tensor, table: HashTable, resultIndicesR: torch.Tensor, resultIndicesS: torch.Tensor,
+               probePayload: torch.Tensor | None = None, probeRowBase: int = 0) -> int:
+    """Single-pass probe (hjJoinFused) into caller-allocated result columns whose length bounds the result (e.g. |S| for a
+    unique build). Returns the number of pairs found; when it exceeds the columns' length only the first ``len`` were written.
+    Raises for grouped tables (duplicate build keys): use countRows + probeRelation there."""
+    _require_cuda(probeRelation_, "probeRelation")
+    if not table.built:
+        raise _lib.HashJoinError("join_fused on a table that was never built")
+    lib = _lib.load()
+    scratch = _scratch_for(table, probeRelation_)
+    n = lib.hjJoinFused(_ptr(probeRelation_), probeRelation_.numel(), table.key_bytes, _ptr(table.storage), _ptr(scratch), scratch.numel(),
+                        _ptr(resultIndicesR), _ptr(resultIndicesS), min(resultIndicesR.numel(), resultIndicesS.numel()),
+                        _ptr(probePayload), probeRowBase & 0xFFFFFFFF, _stream_ptr())
+    return _lib.check_status(n, "hjJoinFused")
+
+
 def hash_join(buildRelation: torch.Tensor, probeRelation_: torch.Tensor, table: HashTable | None = None,
               buildPayload: torch.Tensor | None = None, probePayload: torch.Tensor | None = None,
               rowBase: int = 0, probeRowBase: int = 0):

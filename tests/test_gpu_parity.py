@@ -109,6 +109,34 @@ def test_row_id_limits(lib, cuda):
     assert lib.hjCountAsync(t.data_ptr(), (1 << 32) + 5, 4, t.data_ptr(), t.data_ptr(), t.numel(), None) < 0
 
 
+def test_fused_single_pass(lib, cuda, oracle):
+    """hjJoinFused: lookup + decoupled look-back + write in one pass gives the same multiset as count + write; a too-small result
+    only truncates (the count is still exact); grouped tables are refused."""
+    import torch
+    from mlir_hashjoin_b200 import _lib, join
+    rng = np.random.default_rng(17)
+    for kd, nR, nS in ((np.int32, 50_000, 300_007), (np.int64, 20_000, 100_003), (np.int32, 1, 5000), (np.int32, 300_000, 2_000_003)):
+        R = rng.permutation(3 * nR)[:nR].astype(kd)                       # unique; sparse enough that the hash layout runs under "hash"
+        if kd == np.int64:
+            R = R * np.int64(0x9E3779B97F4A7C15 - (1 << 64))
+        S = rng.choice(np.concatenate([R, R + 1]), nS).astype(kd)        # about half of the probe rows hit
+        dR, dS = torch.from_numpy(R).to(cuda), torch.from_numpy(S).to(cuda)
+        table = join.allocateHashTable(nR, None, dR.dtype, cuda)
+        join.buildTable(dR, table)
+        outR = torch.empty(nS, dtype=torch.int32, device=cuda); outS = torch.empty(nS, dtype=torch.int32, device=cuda)
+        n = join.join_fused(dS, table, outR, outS, probeRowBase=11)
+        oa, ob = oracle.join(R, S)
+        assert n == oa.size
+        assert np.array_equal(sorted_pairs(outR[:n].cpu().numpy(), outS[:n].cpu().numpy()), sorted_pairs(oa, ob + 11))
+        small = torch.empty(max(1, n // 3), dtype=torch.int32, device=cuda)
+        assert join.join_fused(dS, table, small, small.clone()) == n      # capacity too small: exact count, truncated output
+    Rd = np.repeat(np.arange(1000, dtype=np.int32), 3)
+    table = join.allocateHashTable(Rd.size, None, torch.int32, cuda)
+    join.buildTable(torch.from_numpy(Rd).to(cuda), table)
+    with pytest.raises(_lib.HashJoinError):
+        join.join_fused(torch.from_numpy(Rd).to(cuda), table, outR, outS)
+
+
 def test_empty_inputs(lib, cuda, oracle):
     e = np.empty(0, np.int32)
     for R, S in ((e, np.arange(10, dtype=np.int32)), (np.arange(10, dtype=np.int32), e), (e, e)):
