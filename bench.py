@@ -152,6 +152,8 @@ def main() -> None:
     ap.add_argument("--c5-total-log2", type=int, default=0, help="c5 only: fix the TOTAL rows per side at 2^k (strong scaling); default 2^28 rows per GPU (weak)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5 only: peer-store partition kernel vs partition + NCCL all-to-all")
     ap.add_argument("--layout", default="auto", choices=["auto", "hash"], help="hash = force the bucketised hash table even for dense key ranges")
+    ap.add_argument("--sparse", type=int, default=1, choices=[0, 1, 2], help="hjSetSparse: hit lists for selective joins (0 never, 1 sampled on the device, 2 always)")
+    ap.add_argument("--dense-waves", type=int, default=None, help="hjSetDenseWaves (experiment): grid of the direct-address probe kernels")
     ap.add_argument("--no-hash-arm", action="store_true", help="skip the extra forced-hash-layout measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -218,6 +220,9 @@ def main() -> None:
 
     stream = torch.cuda.current_stream()
     lib.hjSetAllowDense(0 if args.layout == "hash" else 1)
+    lib.hjSetSparse(args.sparse)
+    if args.dense_waves is not None:
+        lib.hjSetDenseWaves(args.dense_waves)
     out_buf = {"R": None, "S": None}             # result columns live outside the timed region (allocation is excluded)
 
     def result_columns(n):
@@ -251,7 +256,12 @@ def main() -> None:
             join.probeRelation(dS, table, outR, outS, probeRowBase=plo)
         ev[3].record(stream)
         n_out[0] = n
-        launches[0] += 19                                  # 13 build-sequence launches, 3 k_count instantiations, k_scan_chunks, 2 k_write instantiations
+        # 13 build-sequence launches, k_sample_hits (>= 2^20 probe rows), 3 k_count + 2 k_count_sparse instantiations, k_scan_blocks
+        # (+ k_scan_add beyond 16384 chunks), 2 k_write instantiations + k_write_sparse (the kernels whose layout / probe path was
+        # not chosen exit at once; they are launches all the same)
+        chunk_rows = 16384 if dS.element_size() == 4 else 1024
+        launches[0] += 13 + (1 if dS.numel() >= (1 << 20) and args.sparse else 0) + 3 + (2 if args.sparse else 0) \
+            + (2 if dS.numel() > 16384 * chunk_rows else 1) + 2 + (1 if args.sparse else 0)
         return ev, (outR, outS)
 
     def run_timed(steps, warmup, sample_clocks):
@@ -379,7 +389,7 @@ def main() -> None:
     if phase_ms["count"]:
         k_ms = {k: sum(v) / len(v) for k, v in phase_ms.items()}
         dom = max(k_ms, key=k_ms.get)
-        kernel = {"build": "build sequence (k_minmax, k_clear, k_build_dense | k_build_hash, ...)", "count": "k_count (+ k_scan_chunks and the 8-byte result-size readback)", "write": "k_write"}[dom]
+        kernel = {"build": "build sequence (k_minmax, k_clear, k_build_dense | k_build_hash, ...)", "count": "k_count | k_count_sparse (+ k_sample_hits, k_scan_blocks and the 8-byte result-size readback)", "write": "k_write | k_write_sparse"}[dom]
         ach = ab[dom] / (k_ms[dom] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "algorithmic_bytes": ab[dom], "kernel_ms": k_ms[dom], "peak_source": peak_src,

@@ -159,6 +159,15 @@ void hjSetLocality(int32_t on);
 /* 1: the direct-address count kernel moves its two streams with TMA bulk copies (cp.async.bulk, per-warp mbarriers); 0 (default): LDG/STG.
  * Experimental: measured 3.7x slower on config 2 (profiles/README.md). */
 void hjSetTmaCount(int32_t on);
+/* Hit lists for selective joins (unique build keys): the count pass appends (build row, probe position) per chunk instead of writing a
+ * match-cache word per probe row, the write pass copies the lists. 1 (default): decided on the device from a sample of 8192 probe
+ * keys (lists when < 35 % hit, relations of >= 2^20 probe rows); 0: never; 2: always. Same result either way. */
+void hjSetSparse(int32_t policy);
+/* Experiment switch: grid of BOTH direct-address probe kernels: 0 = one chunk per CTA, k > 0 = at most k resident waves striding over
+ * the chunks. Default (not reachable through this call): count 2 waves, write one chunk per CTA — see hj_kernels.cu for the numbers. */
+void hjSetDenseWaves(int32_t k);
+/* Which probe path the last hjCount on this scratch took: 0 = match cache, 1 = hit lists (diagnostic; one 8-byte readback). */
+int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream);
 const char* hjLastErrorString(void);
 const char* hjVersion(void);
 

@@ -74,6 +74,9 @@ _SIGNATURES = {
     "hjSetAllowDense": (None, [_i32]),
     "hjSetLocality": (None, [_i32]),
     "hjSetTmaCount": (None, [_i32]),
+    "hjSetSparse": (None, [_i32]),
+    "hjSetDenseWaves": (None, [_i32]),
+    "hjProbePath": (_i32, [_vp, _i64, _i32, _vp]),
     "hjLastErrorString": (C.c_char_p, []),
     "hjVersion": (C.c_char_p, []),
 }

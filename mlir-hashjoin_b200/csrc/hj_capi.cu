@@ -91,6 +91,8 @@ const char* hjVersion(void) { return "hashjoin_b200 0.2 (sm_100a)"; }
 void hjSetAllowDense(int32_t on) { hj::set_allow_dense(on); }
 void hjSetLocality(int32_t on) { hj::set_locality(on); }
 void hjSetTmaCount(int32_t on) { hj::set_tma_count(on); }
+void hjSetSparse(int32_t policy) { hj::set_sparse(policy); }
+void hjSetDenseWaves(int32_t k) { hj::set_dense_waves(k); }
 
 // =========================================================================================================
 // A. legacy helper symbols
@@ -190,6 +192,16 @@ int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* 
   HJ_CUDA("hjCountResult", cudaMemcpyAsync(host, sv.chunk_offsets + sv.nchunks, 8, cudaMemcpyDeviceToHost, S_(stream)));
   HJ_CUDA("hjCountResult", cudaStreamSynchronize(S_(stream)));
   return (int64_t)*host;
+}
+
+int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream) {
+  if (!dScratch || !key_ok(keyBytes) || nS < 0) return fail(HJ_ERR_ARG, "hjProbePath", "bad argument");
+  unsigned long long* host = pinned_total();
+  if (!host) return fail(HJ_ERR_CUDA, "hjProbePath", "cudaMallocHost failed");
+  hj::ScratchView sv = hj::scratch_view(const_cast<void*>(dScratch), nS, keyBytes);
+  HJ_CUDA("hjProbePath", cudaMemcpyAsync(host + 1, sv.counters + 3, 8, cudaMemcpyDeviceToHost, S_(stream)));
+  HJ_CUDA("hjProbePath", cudaStreamSynchronize(S_(stream)));
+  return host[1] ? 1 : 0;
 }
 
 int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {

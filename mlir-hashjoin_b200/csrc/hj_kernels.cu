@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include "hj_common.cuh"
 #include "hj_kernels.cuh"
 
@@ -56,19 +57,23 @@ int64_t num_chunks(int64_t n_probe, int key_bytes) {
   const int64_t c = chunk_keys(key_bytes);
   return (n_probe + c - 1) / c;
 }
+constexpr int SCRATCH_COUNTERS = 8, SCRATCH_SCAN_BLOCKS = 264;     // counters, then one total per 16 384 chunks for the two-level scan
 static int64_t scratch_core_bytes(int64_t n_probe, int key_bytes) {
   const int64_t nc = num_chunks(n_probe, key_bytes);
-  return round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((nc + 1 + 4) * 8, 256);
+  return 2 * round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((nc + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256) + round_up(nc * (BLOCK_THREADS / 32) * 4, 256);
 }
-// match cache + chunk offsets + room to reorder the probe relation (keys and original indices) for big tables
+// match cache + hit positions + chunk offsets + room to reorder the probe relation (keys and original indices) for big tables
 int64_t scratch_bytes(int64_t n_probe, int key_bytes) { return scratch_core_bytes(n_probe, key_bytes) + reorder_bytes(n_probe, key_bytes) + 256; }
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   ScratchView v;
   char* base = reinterpret_cast<char*>(scratch);
   v.nchunks = num_chunks(n_probe, key_bytes);
   v.mcache = reinterpret_cast<uint32_t*>(base);
-  v.chunk_offsets = reinterpret_cast<unsigned long long*>(base + round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256));
-  v.counters = v.chunk_offsets + v.nchunks + 1;                 // ticket counters: [0] count<inline>, [1] count<grouped>, [2] write<grouped>
+  const int64_t cache_bytes = round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256);
+  v.hit_list = reinterpret_cast<uint2*>(base);                  // the same bytes as the match cache plus as much again behind it
+  v.chunk_offsets = reinterpret_cast<unsigned long long*>(base + 2 * cache_bytes);
+  v.counters = v.chunk_offsets + v.nchunks + 1;                 // [0] count<inline>, [1] count<grouped>, [2] write<grouped> tickets, [3] hit-list flag, [4] count_sparse ticket
+  v.warp_counts = reinterpret_cast<uint32_t*>(base + 2 * cache_bytes + round_up((v.nchunks + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256));
   v.reorder = base + scratch_core_bytes(n_probe, key_bytes);
   return v;
 }
@@ -153,6 +158,19 @@ __global__ void k_fallback_prepare(TableHeader* hdr, int count_by_range) {
 
 template <typename K, bool VEC>
 __device__ __forceinline__ void load_vec_keys(const K* __restrict__ src, int64_t n, int64_t i0, uint64_t pol, K* key) {
+  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
+  if (VEC && i0 + KPV <= n) {
+    int4 x = ld_stream_v4(src + i0, pol);
+    memcpy(key, &x, 16);
+  } else {
+    #pragma unroll
+    for (int e = 0; e < KPV; e++) key[e] = (i0 + e < n) ? src[i0 + e] : K(0);
+  }
+}
+
+// same, 32-bit positions relative to a chunk of `n` rows
+template <typename K, bool VEC>
+__device__ __forceinline__ void load_vec_keys32(const K* __restrict__ src, uint32_t n, uint32_t i0, uint64_t pol, K* key) {
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   if (VEC && i0 + KPV <= n) {
     int4 x = ld_stream_v4(src + i0, pol);
@@ -352,6 +370,19 @@ static unsigned resident_grid(Kern kern, int64_t needed_blocks) {
 
 static int g_allow_dense = 1;
 static int g_locality = 1;
+// Grid of the direct-address probe kernels: 0 = one chunk per CTA, k = at most k resident waves striding over the chunks.
+// Measured on config 2 (20 steps): count 1.231 / 1.248 / 1.233 / 1.231 ms and write 0.536 / 0.597 / 0.591 / 0.555 ms for k = 0 / 1 / 2 / 4.
+// The count kernel therefore runs two waves (when it is NOT the chosen kernel — selective joins take k_count_sparse — its launch
+// costs ~3 us instead of ~37 us at 2^30 probe rows) and the write kernel keeps one chunk per CTA.
+static int g_count_waves = 2, g_write_waves = 0;
+void set_dense_waves(int k) { g_count_waves = g_write_waves = k; }
+template <typename Kern>
+static unsigned dense_grid(Kern kern, int64_t nchunks, int waves) {
+  if (waves <= 0) return (unsigned)nchunks;
+  return (unsigned)std::min<int64_t>(nchunks, (int64_t)waves * resident_grid(kern, nchunks));
+}
+static int g_sparse = 1;       // hit lists for selective joins: 0 never, 1 sampled on the device, 2 always (unique layouts)
+void set_sparse(int policy) { g_sparse = policy; }
 static int g_tma_count = 0;    // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
 void set_tma_count(int on) { g_tma_count = on; }
 void set_allow_dense(int on) { g_allow_dense = on; }
@@ -481,9 +512,11 @@ __device__ __forceinline__ const char* home_bucket(const char* __restrict__ body
 template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
-                                                         unsigned long long* __restrict__ chunk_totals, int64_t nchunks, unsigned long long* tickets) {
+                                                         unsigned long long* __restrict__ chunk_totals, int64_t nchunks, unsigned long long* tickets,
+                                                         const unsigned long long* __restrict__ sparse_flag) {
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
+  if (MODE != MODE_GROUP && *sparse_flag) return;                  // selective join: k_count_sparse takes it
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
   __shared__ unsigned long long red[33];
   constexpr uint32_t mode = MODE;
@@ -553,6 +586,219 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   }
   cnt = block_reduce_sum(cnt, red);
   if (threadIdx.x == 0) chunk_totals[chunk] = cnt;
+  }
+}
+
+// =========================================================================================================
+// K2s  selective joins: hit lists instead of a match-cache word per probe row
+// =========================================================================================================
+// A match cache costs 4 bytes written and 4 bytes read per PROBE ROW whatever the selectivity (config 3: 8.6 GB of a 14 GB
+// step for 10 % hits). When a sample of the probe keys says few rows hit, the count pass appends (matched build row, probe
+// position) to a hit list of the chunk instead — the chunk's slice of the same scratch arrays, so capacity is never a
+// question — and the write pass only copies lists to their final offsets. The decision is taken on the device
+// (k_sample_hits -> counters[3]) and read uniformly by the kernels of both passes: no host round trip, and either path
+// is correct for any selectivity (hjSetSparse(2) forces this one in the parity tests).
+constexpr int SAMPLE_THREADS = 1024, SAMPLE_PER_THREAD = 8;
+constexpr int64_t SPARSE_MIN_ROWS = (int64_t)1 << 20;      // below this the sample costs more than it can save
+constexpr unsigned SPARSE_MAX_PERCENT = 35;                // hit lists move 16 B per hit, the match cache 8 B per row
+
+template <typename K>
+__global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_hits(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,
+                                                                unsigned long long* __restrict__ flag, int policy) {
+  __shared__ unsigned long long red[33];
+  const uint32_t mode = hdr->mode;
+  if (mode == MODE_GROUP || hdr->all_present) return;            // flag stays 0 (grouped: the cache holds counts; all_present: no cache at all)
+  if (policy == 2) { if (threadIdx.x == 0) *flag = 1ULL; return; }
+  const uint64_t n_pairs = hdr->n_pairs;
+  const long long kmin = hdr->kmin;
+  const unsigned long long drange = hdr->dense_range;
+  unsigned long long hits = 0;
+  #pragma unroll
+  for (int s = 0; s < SAMPLE_PER_THREAD; s++) {
+    const uint64_t j = __umul64hi(mix64((uint64_t)(threadIdx.x * SAMPLE_PER_THREAD + s) + 0x9E3779B97F4A7C15ULL), (uint64_t)nS);   // spread, not strided
+    const K key = S[j];
+    if (mode == MODE_DENSE) {
+      const unsigned long long off = (unsigned long long)((long long)key - kmin);
+      hits += off < drange && reinterpret_cast<const uint32_t*>(body)[off] != ROW_NONE;
+    } else {
+      hits += finish_probe_unique<K>(body, n_pairs, key, ld_bucket(home_bucket<K>(body, n_pairs, key))) != ROW_NONE;
+    }
+  }
+  hits = block_reduce_sum(hits, red);
+  if (threadIdx.x == 0) *flag = hits * 100 < (unsigned long long)SPARSE_MAX_PERCENT * SAMPLE_THREADS * SAMPLE_PER_THREAD ? 1ULL : 0ULL;
+}
+
+// Append the warp's hits among m[0..N) to the WARP's hit list (8-byte entries: matched build row, position of the probe row
+// inside the chunk). Every warp owns a fixed sub-slice of the chunk's slice — as many entries as it has rows — so there is no
+// cursor to share: no atomics, no block barrier. Inside the warp the order is thread-major (the order of a result is free,
+// shared.cpp:168-171): each thread counts its hits, a shuffle scan ranks the threads, the hits are packed into the warp's
+// shared-memory staging buffer with 32-bit addresses and leave as one coalesced run. The kernel is bound by instruction issue,
+// not by memory (ncu on config 3: 2.9 IPC per SM at 365 warp instructions per tile for the first version, which ranked with one
+// ballot per key slot and stored rows and positions to two arrays with 64-bit address arithmetic per slot), so the helpers
+// below are PTX: nvcc turns the C++ forms into select chains, and wraps its own warp aggregation around a one-lane atomic.
+__device__ __forceinline__ void count_hit(uint32_t& c, uint32_t row) {                  // c += row != ROW_NONE
+  asm("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0xffffffff;\n @p add.u32 %0, %0, 1;\n}" : "+r"(c) : "r"(row));
+}
+__device__ __forceinline__ void stage_hit(uint32_t& saddr, uint32_t row, uint32_t pos) {   // if hit: *saddr++ = (row, pos)   (shared memory)
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0xffffffff;\n @p st.shared.v2.u32 [%0], {%1, %2};\n @p add.u32 %0, %0, 8;\n}"
+               : "+r"(saddr) : "r"(row), "r"(pos) : "memory");
+}
+__device__ __forceinline__ uint32_t warp_inclusive_scan_u32(uint32_t v) {               // shfl.up with its in-range predicate: 2 instructions per step
+  #pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+    asm volatile("{\n .reg .pred p;\n .reg .u32 t;\n shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n @p add.u32 %0, %0, t;\n}" : "+r"(v) : "r"(d));
+  return v;
+}
+// returns the number of entries appended at wlist[0 ..)
+template <int N>
+__device__ __forceinline__ uint32_t append_hits(const uint32_t (&m)[N], const uint32_t (&pos)[N], uint2* __restrict__ wlist, uint2* stage) {
+  const int lane = threadIdx.x & 31;
+  uint32_t c = 0;
+  #pragma unroll
+  for (int k = 0; k < N; k++) count_hit(c, m[k]);
+  const uint32_t inc = warp_inclusive_scan_u32(c);
+  const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+  if (wtot == 0) return 0;                                         // warp-uniform
+  uint32_t saddr = smem_addr(stage) + (inc - c) * 8;
+  #pragma unroll
+  for (int k = 0; k < N; k++) stage_hit(saddr, m[k], pos[k]);
+  __syncwarp();
+  for (uint32_t i = lane; i < wtot; i += 32) wlist[i] = stage[i];
+  __syncwarp();                                                    // the staging buffer is rewritten by the next call
+  return wtot;
+}
+
+constexpr int SPARSE_WARPS = BLOCK_THREADS / 32;
+constexpr int PREFETCH_TILES = 2;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+template <typename K, bool VEC, uint32_t MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_count_sparse(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,
+                                                                uint2* __restrict__ hit_list, uint32_t* __restrict__ warp_counts,
+                                                                unsigned long long* __restrict__ chunk_totals, int64_t nchunks, unsigned long long* tickets,
+                                                                const unsigned long long* __restrict__ sparse_flag) {
+  using T = KeyTraits<K>;
+  using UK = typename std::make_unsigned<K>::type;
+  if (hdr->mode != MODE || !*sparse_flag) return;
+  constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
+  constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K)), CHUNK_ROWS = TILE * CHUNK_TILES, WARP_ROWS = CHUNK_ROWS / SPARSE_WARPS;
+  __shared__ __align__(16) uint2 stage_sm[SPARSE_WARPS][32 * KPT];
+  __shared__ uint32_t wc[2][SPARSE_WARPS];
+  __shared__ long long ticket;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* stage = stage_sm[warp];
+  const uint64_t n_pairs = hdr->n_pairs;
+  // direct addressing in the key's own width: (UK)key - (UK)kmin < range is exact although it wraps (range <= 2^32 - 1, k_decide)
+  const UK kmin = (UK)hdr->kmin, drange = (UK)hdr->dense_range;
+  const uint32_t* __restrict__ tab = reinterpret_cast<const uint32_t*>(body);
+  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  int par = 0;
+  // both layouts on one resident wave: direct-address strides over the chunks, the bucketised layout takes them by ticket (slice order)
+  for (long long chunk = MODE == MODE_DENSE ? (long long)blockIdx.x : next_ticket(tickets, &ticket); chunk < nchunks;
+       chunk = MODE == MODE_DENSE ? chunk + gridDim.x : next_ticket(tickets, &ticket), par ^= 1) {
+    const int64_t chunk_base = chunk * CHUNK_ROWS;
+    const uint32_t lim = (uint32_t)(nS - chunk_base < CHUNK_ROWS ? nS - chunk_base : CHUNK_ROWS);    // rows of this chunk
+    const K* __restrict__ Sc = S + chunk_base;
+    uint2* __restrict__ wlist = hit_list + chunk_base + warp * WARP_ROWS;
+    uint32_t wcur = 0;
+    #pragma unroll 1
+    for (uint32_t tile_off = 0; tile_off < lim; tile_off += TILE) {
+      if constexpr (MODE == MODE_DENSE) {
+        K key[KPT];
+        uint32_t m[KPT], pos[KPT];
+        #pragma unroll
+        for (int k = 0; k < KPT; k++) pos[k] = tile_off + ((k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV);
+        if (VEC && tile_off + TILE <= lim) {                         // full tile (uniform): no per-row bounds tests
+          {                                                          // pull the keys this thread reads two tiles from now into L2 (the kernel is latency-bound:
+            const uint32_t ahead = tile_off + PREFETCH_TILES * TILE;   // ncu long-scoreboard stalls 10 warps per issue slot). A register double buffer measured
+            const int64_t nb = ahead < CHUNK_ROWS ? chunk_base + ahead : (chunk + gridDim.x) * CHUNK_ROWS + (ahead - CHUNK_ROWS);   // slower: 48 registers, 5 CTAs per SM
+            if (nb + TILE <= nS) {
+              #pragma unroll
+              for (int v = 0; v < VECS_PER_THREAD; v++) prefetch_l2(S + nb + (v * BLOCK_THREADS + threadIdx.x) * KPV);
+            }
+          }
+          #pragma unroll
+          for (int v = 0; v < VECS_PER_THREAD; v++) { const int4 x = ld_stream_v4(Sc + pos[v * KPV], pol_s); memcpy(&key[v * KPV], &x, 16); }
+          #pragma unroll
+          for (int k = 0; k < KPT; k++) { const UK off = (UK)key[k] - kmin; m[k] = off < drange ? ld_keep_u32(tab + off, pol_t) : ROW_NONE; }
+        } else {
+          #pragma unroll
+          for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys32<K, VEC>(Sc, lim, pos[v * KPV], pol_s, &key[v * KPV]);
+          #pragma unroll
+          for (int k = 0; k < KPT; k++) { const UK off = (UK)key[k] - kmin; m[k] = (off < drange && pos[k] < lim) ? ld_keep_u32(tab + off, pol_t) : ROW_NONE; }
+        }
+        wcur += append_hits<KPT>(m, pos, wlist + wcur, stage);
+      } else {
+        #pragma unroll 1
+        for (int v = 0; v < VECS_PER_THREAD; v++) {
+          const uint32_t p0 = tile_off + (v * BLOCK_THREADS + threadIdx.x) * KPV;
+          K kv[KPV]; uint32_t mv[KPV], pos[KPV]; Bucket b[KPV];
+          load_vec_keys32<K, VEC>(Sc, lim, p0, pol_s, kv);
+          #pragma unroll
+          for (int e = 0; e < KPV; e++) b[e] = ld_bucket(home_bucket<K>(body, n_pairs, kv[e]));
+          #pragma unroll
+          for (int e = 0; e < KPV; e++) { pos[e] = p0 + e; mv[e] = p0 + e < lim ? finish_probe_unique<K>(body, n_pairs, kv[e], b[e]) : ROW_NONE; }
+          wcur += append_hits<KPV>(mv, pos, wlist + wcur, stage);
+        }
+      }
+    }
+    if (lane == 0) { warp_counts[chunk * SPARSE_WARPS + warp] = wcur; wc[par][warp] = wcur; }
+    __syncthreads();                                                 // wc is double-buffered: one barrier per chunk is enough
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      #pragma unroll
+      for (int w = 0; w < SPARSE_WARPS; w++) t += wc[par][w];
+      chunk_totals[chunk] = t;
+    }
+  }
+}
+
+// Write pass of the hit-list mode: one warp per chunk copies the chunk's eight warp lists to their final offsets (coalesced both
+// ways) and turns probe positions into probe row ids (slice-ordered copy -> original index -> payload / row base, like k_write).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_write_sparse(const TableHeader* __restrict__ hdr, const uint2* __restrict__ hit_list, const uint32_t* __restrict__ warp_counts,
+                                                                const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks, int chunk_rows,
+                                                                int32_t* __restrict__ outR, int32_t* __restrict__ outS,
+                                                                const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
+                                                                const unsigned long long* __restrict__ sparse_flag) {
+  if (!*sparse_flag || hdr->mode == MODE_GROUP) return;
+  const int lane = threadIdx.x & 31;
+  const uint64_t pol_s = policy_evict_first();
+  const int64_t warps = (int64_t)gridDim.x * (BLOCK_THREADS / 32);
+  const int warp_rows = chunk_rows / SPARSE_WARPS;
+  for (int64_t chunk = (int64_t)blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += warps) {
+    const unsigned long long o = chunk_offsets[chunk];
+    if (chunk_offsets[chunk + 1] == o) continue;                     // warp-uniform
+    const uint32_t tot = (uint32_t)(chunk_offsets[chunk + 1] - o);
+    const uint32_t cw = lane < SPARSE_WARPS ? warp_counts[chunk * SPARSE_WARPS + lane] : 0u;
+    const uint32_t incl = warp_inclusive_scan_u32(cw);
+    uint32_t end[SPARSE_WARPS];                                      // inclusive ends of the eight warp lists in the chunk's output range
+    #pragma unroll
+    for (int w = 0; w < SPARSE_WARPS; w++) end[w] = __shfl_sync(0xffffffffu, incl, w);
+    const uint2* __restrict__ src = hit_list + chunk * chunk_rows;
+    const uint32_t base = (uint32_t)(chunk * chunk_rows);
+    // the eight lists are walked as ONE virtual list, four entries per lane in flight (one list at a time left the kernel latency-bound)
+    constexpr int U = 4;
+    for (uint32_t v0 = 0; v0 < tot; v0 += 32 * U) {
+      uint2 e[U];
+      #pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t v = v0 + u * 32 + lane;
+        uint32_t start = 0, w = 0;
+        #pragma unroll
+        for (int x = 0; x < SPARSE_WARPS - 1; x++) if (v >= end[x]) { start = end[x]; w = x + 1; }
+        e[u] = v < tot ? src[w * warp_rows + (v - start)] : make_uint2(0u, 0u);
+      }
+      #pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t v = v0 + u * 32 + lane;
+        if (v < tot) {
+          const uint32_t j = base + e[u].y;                                                // positions are chunk-relative
+          const uint32_t idx = perm ? perm[j] : j;
+          st_stream_u32(outR + o + v, e[u].x, pol_s);
+          st_stream_u32(outS + o + v, probe_payload ? probe_payload[idx] : probe_row_base + idx, pol_s);
+        }
+      }
+    }
   }
 }
 
@@ -641,22 +887,51 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count_dense_tma(const int32_t
 // =========================================================================================================
 // K3  scan of chunk totals -> exclusive chunk offsets, total at [nchunks]      (replaces join_v1.mlir:371-420)
 // =========================================================================================================
-constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 8;
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunks(unsigned long long* __restrict__ t, int64_t n) {
+// Two short launches: every CTA scans 16 384 totals in place (thread-contiguous 128-byte runs, one block scan), publishing its
+// block total; the second launch (only when there is more than one block) adds the preceding blocks' totals. A single CTA
+// looping over the array took 61 us for config 3's 65 536 chunks and would take ~1 ms for 2^30 i64 rows (1 M chunks).
+constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 16, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocks(unsigned long long* __restrict__ t, int64_t n, unsigned long long* __restrict__ block_sums) {
   __shared__ unsigned long long sm[33];
-  unsigned long long running = 0;
-  for (int64_t base = 0; base < n; base += (int64_t)SCAN_THREADS * SCAN_ITEMS) {
-    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_ITEMS;
-    unsigned long long v[SCAN_ITEMS], sum = 0;
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long v[SCAN_ITEMS], sum = 0;
+  if (i0 + SCAN_ITEMS <= n) {
     #pragma unroll
-    for (int e = 0; e < SCAN_ITEMS; e++) { v[e] = (i0 + e < n) ? t[i0 + e] : 0ULL; sum += v[e]; }
-    unsigned long long total, ex = block_exclusive_scan(sum, sm, &total);
-    unsigned long long acc = running + ex;
+    for (int e = 0; e < SCAN_ITEMS; e += 2) { const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(t + i0 + e); v[e] = x.x; v[e + 1] = x.y; }
+  } else {
     #pragma unroll
-    for (int e = 0; e < SCAN_ITEMS; e++) { if (i0 + e < n) t[i0 + e] = acc; acc += v[e]; }
-    running += total;
+    for (int e = 0; e < SCAN_ITEMS; e++) v[e] = (i0 + e < n) ? t[i0 + e] : 0ULL;
   }
-  if (threadIdx.x == 0) t[n] = running;
+  #pragma unroll
+  for (int e = 0; e < SCAN_ITEMS; e++) sum += v[e];
+  unsigned long long total, acc = block_exclusive_scan(sum, sm, &total);
+  #pragma unroll
+  for (int e = 0; e < SCAN_ITEMS; e++) { const unsigned long long x = v[e]; v[e] = acc; acc += x; }
+  if (i0 + SCAN_ITEMS <= n) {
+    #pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; e += 2) *reinterpret_cast<ulonglong2*>(t + i0 + e) = make_ulonglong2(v[e], v[e + 1]);
+  } else {
+    #pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; e++) if (i0 + e < n) t[i0 + e] = v[e];
+  }
+  if (threadIdx.x == 0) { block_sums[blockIdx.x] = total; if (gridDim.x == 1) t[n] = total; }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* __restrict__ t, int64_t n, const unsigned long long* __restrict__ block_sums) {
+  __shared__ unsigned long long sm[33];
+  unsigned long long mine = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) mine += block_sums[b];
+  const unsigned long long base = block_reduce_sum(mine, sm);
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  if (blockIdx.x > 0) {
+    #pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; e++) if (i0 + e < n) t[i0 + e] += base;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) t[n] = base + block_sums[blockIdx.x];
+}
+static void launch_scan(unsigned long long* t, int64_t n, unsigned long long* block_sums, cudaStream_t stream) {
+  const unsigned nb = (unsigned)std::max<int64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+  k_scan_blocks<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums);
+  if (nb > 1) k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums);
 }
 
 cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool* reordered,
@@ -678,26 +953,36 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
       S = rv.keys; *reordered = true;
     }
   }
-  { cudaError_t e = cudaMemsetAsync(sv.counters, 0, 4 * sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
+  { cudaError_t e = cudaMemsetAsync(sv.counters, 0, SCRATCH_COUNTERS * sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
+  const unsigned long long* sparse_flag = sv.counters + 3;
+  const int sparse_policy = g_tma_count ? 0 : g_sparse;
+  if (nS > 0 && (sparse_policy == 2 || (sparse_policy == 1 && nS >= SPARSE_MIN_ROWS))) {
+    if (key_bytes == 4) k_sample_hits<int32_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.counters + 3, sparse_policy);
+    else                k_sample_hits<int64_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.counters + 3, sparse_policy);
+  }
   if (sv.nchunks > 0) {
     const unsigned grid = (unsigned)sv.nchunks;                               // direct-address layout: one chunk per CTA
     // bucketised layouts: one resident wave (idle launch ~3 us; the slice-ordered window stays tight)
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
-    k_count<K, V, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters); \
-    k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters);  \
-    k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1);
+    k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
+    k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);  \
+    k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag); \
+    if (sparse_policy) { \
+      k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
+      k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
+    }
     if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
       k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters);
-      k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1);
-      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters);
+      k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
+      k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag);
+      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
 #undef HJ_LAUNCH_COUNT
   }
-  k_scan_chunks<<<1, SCAN_THREADS, 0, stream>>>(sv.chunk_offsets, sv.nchunks);
+  launch_scan(sv.chunk_offsets, sv.nchunks, sv.counters + SCRATCH_COUNTERS, stream);
   return cudaGetLastError();
 }
 
@@ -711,8 +996,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
                                                          const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache,
                                                          const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks, unsigned long long* tickets,
                                                          int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
+                                                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
+                                                         const unsigned long long* __restrict__ sparse_flag) {
   if ((hdr->mode == MODE_GROUP) != GROUPED) return;
+  if (!GROUPED && *sparse_flag) return;                              // hit-list mode: k_write_sparse takes it
   using T = KeyTraits<K>;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
   // probe row id of position j of the relation the kernel reads: S may be a slice-ordered copy (perm = original index)
@@ -852,11 +1139,14 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   { cudaError_t e = cudaMemsetAsync(sv.counters + 2, 0, sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
 #define HJ_LAUNCH_WRITE(K, V) \
-  k_write<K, V, false><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base); \
-  k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base);
+  k_write<K, V, false><<<dense_grid(k_write<K, V, false>, sv.nchunks, g_write_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3); \
+  k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
+  if (g_sparse && !g_tma_count)
+    k_write_sparse<<<(unsigned)std::min<int64_t>(PERSIST_GRID, (sv.nchunks + BLOCK_THREADS / 32 - 1) / (BLOCK_THREADS / 32)), BLOCK_THREADS, 0, stream>>>(
+        hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, chunk_keys(key_bytes), outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);
   return cudaGetLastError();
 }
 
@@ -982,7 +1272,7 @@ cudaError_t join_fused_async(const void* S, int64_t nS, int key_bytes, const voi
   const int64_t ntiles = (nS + tile_keys(key_bytes) - 1) / tile_keys(key_bytes);
   unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(sv.mcache);      // the match cache is not needed: reuse it (8 B per tile)
   unsigned long long* total = sv.chunk_offsets + sv.nchunks;                              // same slot the two-phase path reports in
-  cudaError_t e = cudaMemsetAsync(sv.counters, 0, 4 * sizeof(unsigned long long), stream);
+  cudaError_t e = cudaMemsetAsync(sv.counters, 0, SCRATCH_COUNTERS * sizeof(unsigned long long), stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(total, 0, 8, stream);
   if (e == cudaSuccess && ntiles > 0) e = cudaMemsetAsync(tile_state, 0, (size_t)ntiles * 8, stream);
   if (e != cudaSuccess || ntiles == 0) return e;

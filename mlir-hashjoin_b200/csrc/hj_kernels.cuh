@@ -23,18 +23,24 @@ int64_t table_bytes(int64_t n_rows, int key_bytes);
 int64_t scratch_bytes(int64_t n_probe, int key_bytes);
 int64_t num_chunks(int64_t n_probe, int key_bytes);
 
-// Scratch layout (device): [ match cache: u32 x round_up(n_probe, chunk) ][ chunk offsets: u64 x (nchunks + 1) ]
+// Scratch layout (device): [ match cache: u32 x round_up(n_probe, chunk) ][ as much again ][ chunk offsets: u64 x (nchunks + 1) ]
+// Selective joins (few probe rows hit) use the first two areas together as per-chunk HIT LISTS instead: chunk c's hits are the
+// first cnt[c] 8-byte entries (matched build row, position of the probe row inside the chunk) of its slice, see k_count_sparse.
 struct ScratchView {
   uint32_t* mcache;
+  uint2* hit_list;
+  uint32_t* warp_counts;              // hit-list mode: entries in each of the 8 warp lists of a chunk
   unsigned long long* chunk_offsets;  // after scan: exclusive offsets; [nchunks] = total
   int64_t nchunks;
-  unsigned long long* counters;       // ticket counters of the bounded-grid probe kernels
+  unsigned long long* counters;       // [0..2] ticket counters of the bounded-grid probe kernels, [3] hit-list mode flag, [4] ticket of k_count_sparse
   char* reorder;                      // slice-ordered copy of the probe relation (big tables only)
 };
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
 
 void set_allow_dense(int on);
 void set_locality(int on);
+void set_sparse(int policy);    // hit lists for selective joins: 0 never, 1 decided on the device from a sample of the probe keys (default), 2 always
+void set_dense_waves(int k);    // grid of the direct-address probe kernels: 0 = one chunk per CTA (default), k = at most k resident waves
 void set_tma_count(int on);     // debug/bench switch: 0 = LDG/STG streams in the direct-address count kernel instead of TMA bulk copies      // debug/bench switch: 0 disables the slice-ordered build/probe of big tables
 bool table_is_big(int64_t n_rows, int key_bytes);   // debug/bench switch: 0 forces the hash layout even for dense key ranges
 

@@ -116,6 +116,12 @@ def probeRelation(probeRelation_: torch.Tensor, table: HashTable, resultIndicesR
     _lib.check_status(rc, "hjWrite")
 
 
+def debug_sparse_flag(table: HashTable, probeRelation_: torch.Tensor) -> int:
+    """Which probe path the last countRows took for this probe relation: 0 = match cache, 1 = hit lists (hjProbePath)."""
+    lib = _lib.load()
+    return _lib.check_status(lib.hjProbePath(_ptr(table.scratch), probeRelation_.numel(), table.key_bytes, _stream_ptr()), "hjProbePath")
+
+
 def join_fused(probeRelation_: torch.Tensor, table: HashTable, resultIndicesR: torch.Tensor, resultIndicesS: torch.Tensor,
                probePayload: torch.Tensor | None = None, probeRowBase: int = 0) -> int:
     """Single-pass probe (hjJoinFused) into caller-allocated result columns whose length bounds the result (e.g. |S| for a

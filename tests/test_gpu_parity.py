@@ -10,13 +10,16 @@ from oracle.binding import sorted_pairs
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "hash", "range"])
+@pytest.fixture(autouse=True, params=["auto", "hash", "range", "lists", "hash-lists"])
 def layout(request, lib):
-    """Every parity case runs twice: with the direct-address layout allowed (dense key ranges take it, and fall back
-    to the hash layout on a duplicate) and with the bucketised hash layout forced."""
-    lib.hjSetAllowDense({"auto": 1, "hash": 0, "range": 2}[request.param])
+    """Every parity case runs under each table / probe policy: the direct-address layout allowed (dense key ranges take it, and
+    fall back to the hash layout on a duplicate), the bucketised hash layout forced, count-by-range, and the first two again with
+    the hit-list probe path (hjSetSparse(2)) forced instead of the match cache."""
+    lib.hjSetAllowDense({"auto": 1, "hash": 0, "range": 2, "lists": 1, "hash-lists": 0}[request.param])
+    lib.hjSetSparse(2 if "lists" in request.param else 1)
     yield request.param
     lib.hjSetAllowDense(1)
+    lib.hjSetSparse(1)
 
 
 def _join_np(R, S, cuda):
@@ -84,6 +87,31 @@ def test_unique_build_partial_hits(lib, cuda, oracle):
     S = rng.integers(0, 400000, 777777).astype(np.int32)
     a, b = _join_np(R, S, cuda)
     _assert_parity(oracle, R, S, a, b)
+
+
+def test_selective_join_takes_hit_lists(lib, cuda, oracle, layout):
+    """Config 3 in small: 2^16 unique build keys, 2^21 + 5 probe rows of which ~10 % hit. Under the default policy the device-side
+    sample must pick the hit-list path (and the match cache when half of the rows hit); both give the oracle's multiset."""
+    import torch
+    from mlir_hashjoin_b200 import join
+    rng = np.random.default_rng(33)
+    nR, nS = 1 << 16, (1 << 21) + 5
+    R = (rng.permutation(4 * nR)[:nR] * 3 + 7).astype(np.int32)
+    for frac, expect_lists in ((0.1, True), (0.6, False)):
+        hit = rng.random(nS) < frac
+        S = np.where(hit, rng.choice(R, nS), rng.integers(1 << 28, 1 << 30, nS)).astype(np.int32)
+        dR, dS = torch.from_numpy(R).to(cuda), torch.from_numpy(S).to(cuda)
+        table = join.allocateHashTable(nR, None, dR.dtype, cuda)
+        join.buildTable(dR, table)
+        n = join.countRows(dS, table)
+        sv_flag = join.debug_sparse_flag(table, dS)
+        if layout in ("auto", "hash"):
+            assert sv_flag == int(expect_lists), (frac, sv_flag)
+        elif "lists" in layout:
+            assert sv_flag == 1
+        a = torch.empty(n, dtype=torch.int32, device=cuda); b = torch.empty(n, dtype=torch.int32, device=cuda)
+        join.probeRelation(dS, table, a, b)
+        _assert_parity(oracle, R, S, a.cpu().numpy(), b.cpu().numpy())
 
 
 def test_tma_staged_count_kernel(lib, cuda, oracle):
