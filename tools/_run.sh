@@ -1,9 +1,7 @@
 timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -3
-for w in 0 1 2 4; do
-timeout 300 python bench.py --steps 20 --no-e2e --no-cpu-baseline --no-hash-arm --dense-waves $w > gpurun_out/bench_x.json 2>gpurun_out/bench_x.err; tail -2 gpurun_out/bench_x.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_x.json')); print('c2 waves $w', d['ms_per_step'], d['roofline']['phases_ms'])"
+for W in c4 c5; do
+timeout 300 python bench.py --workload $W --steps 5 --no-cpu-baseline --no-e2e --no-hash-arm > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; tail -2 gpurun_out/bench_$W.err; python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_$W.json')); print('$W', d['value'], d['ms_per_step'], d['roofline']['phases_ms'], d['parity'])"
 done
-for w in 0 2; do
-timeout 300 python bench.py --workload c3 --steps 5 --no-cpu-baseline --no-e2e --no-hash-arm --dense-waves $w > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -2 gpurun_out/bench_c3.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_c3.json')); print('c3 waves $w', d['value'], d['ms_per_step'], d['roofline']['phases_ms'], d['parity'])"
-done
+timeout 300 python bench.py --steps 10 --no-e2e --no-cpu-baseline > gpurun_out/bench_x.json 2>gpurun_out/bench_x.err; tail -2 gpurun_out/bench_x.err; python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_x.json')); print('c2', d['ms_per_step'], d['roofline']['phases_ms'], d['hash_layout']['ms_per_step'], d['hash_layout']['phases_ms'])"
