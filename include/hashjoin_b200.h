@@ -166,6 +166,9 @@ void hjSetSparse(int32_t policy);
 /* Experiment switch: grid of BOTH direct-address probe kernels: 0 = one chunk per CTA, k > 0 = at most k resident waves striding over
  * the chunks. Default (not reachable through this call): count 2 waves, write one chunk per CTA — see hj_kernels.cu for the numbers. */
 void hjSetDenseWaves(int32_t k);
+/* 1 (default): builds of >= 2^18 rows look at 16 384 sampled rows for duplicate keys first and go straight to the grouped layout
+ * when they find some (the inline, unique-key build is otherwise attempted and aborted); 0: always attempt the inline layout. */
+void hjSetDupSample(int32_t on);
 /* Which probe path the last hjCount on this scratch took: 0 = match cache, 1 = hit lists (diagnostic; one 8-byte readback). */
 int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream);
 const char* hjLastErrorString(void);

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "hjSetTmaCount": (None, [_i32]),
     "hjSetSparse": (None, [_i32]),
     "hjSetDenseWaves": (None, [_i32]),
+    "hjSetDupSample": (None, [_i32]),
     "hjProbePath": (_i32, [_vp, _i64, _i32, _vp]),
     "hjLastErrorString": (C.c_char_p, []),
     "hjVersion": (C.c_char_p, []),

@@ -93,6 +93,7 @@ void hjSetLocality(int32_t on) { hj::set_locality(on); }
 void hjSetTmaCount(int32_t on) { hj::set_tma_count(on); }
 void hjSetSparse(int32_t policy) { hj::set_sparse(policy); }
 void hjSetDenseWaves(int32_t k) { hj::set_dense_waves(k); }
+void hjSetDupSample(int32_t on) { hj::set_dup_sample(on); }
 
 // =========================================================================================================
 // A. legacy helper symbols

@@ -141,11 +141,43 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_clear(TableHeader* hdr, int4*
   } else if (fallback_pass == 2) {
     if (hdr->mode != MODE_GROUP) return;
   }
+  if (!fallback_pass && hdr->mode == MODE_HASH && hdr->has_dups) return;          // the sample already found duplicates: no inline attempt
   const bool dense = !fallback_pass && hdr->mode == MODE_DENSE;
   const unsigned long long bytes = dense ? ((hdr->dense_range * 4 + 15) & ~15ULL) : hdr->n_pairs * 64;
   const unsigned long long n16 = bytes / 16;
   const int4 ff = make_int4(-1, -1, -1, -1);
   for (unsigned long long i = blockIdx.x * (unsigned long long)BLOCK_THREADS + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * BLOCK_THREADS) body[i] = ff;
+}
+
+// Duplicate pre-check. Finding out that the build keys are not unique by building the inline table costs a whole aborted build
+// (config 4: reorder 0.4 ms + clear + k_build_hash 0.67 ms before the grouped rebuild starts). One CTA looks at 16 384 pseudo-random
+// rows first: equal keys at two different rows are proof of duplicates (no false positives), has_dups is set and the inline attempt
+// is skipped; a miss only means the old path runs. With every key present 4 times (config 4) the sample holds ~12 such pairs.
+constexpr int DUPS_THREADS = 1024, DUPS_SAMPLES = 16384, DUPS_SLOTS = 32768;
+constexpr int64_t DUPS_MIN_ROWS = (int64_t)1 << 18;
+__device__ __forceinline__ uint64_t sample_pos(uint32_t i, uint64_t n) { return __umul64hi(mix64((uint64_t)i + 0x9E3779B97F4A7C15ULL), n); }
+template <typename K>
+__global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restrict__ R, int64_t nR, TableHeader* hdr) {
+  extern __shared__ __align__(16) unsigned char dups_raw[];
+  if (hdr->mode != MODE_HASH) return;
+  long long* keys_sm = reinterpret_cast<long long*>(dups_raw);                       // [DUPS_SAMPLES]
+  unsigned short* slots = reinterpret_cast<unsigned short*>(keys_sm + DUPS_SAMPLES);  // [DUPS_SLOTS], sample id + 1, 0 = empty (ids < 2^14)
+  for (int s = threadIdx.x; s < DUPS_SLOTS; s += DUPS_THREADS) slots[s] = 0;
+  for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) keys_sm[i] = (long long)R[sample_pos(i, (uint64_t)nR)];
+  __syncthreads();
+  bool dup = false;
+  for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) {
+    const long long key = keys_sm[i];
+    uint32_t h = (uint32_t)(mix64((uint64_t)key) >> 40) & (DUPS_SLOTS - 1);
+    for (;;) {
+      const unsigned short old = atomicCAS(&slots[h], (unsigned short)0, (unsigned short)(i + 1));
+      if (old == 0) break;
+      const int j = old - 1;
+      if (keys_sm[j] == key) { dup |= sample_pos(j, (uint64_t)nR) != sample_pos(i, (uint64_t)nR); break; }   // the same row drawn twice proves nothing
+      h = (h + 1) & (DUPS_SLOTS - 1);
+    }
+  }
+  if (__syncthreads_or(dup) && threadIdx.x == 0) hdr->has_dups = 1;
 }
 
 // count_by_range: experimental (hjSetAllowDense(2)). A unique build whose keys are exactly [kmin, kmax] lets the count pass
@@ -235,7 +267,7 @@ __device__ __forceinline__ bool insert_one(char* body, uint64_t n_pairs, K key, 
 template <typename K, bool VEC>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ perm,
                                                               const uint32_t* __restrict__ payload, uint32_t row_base, char* body, TableHeader* hdr) {
-  if (hdr->mode != MODE_HASH) return;
+  if (hdr->mode != MODE_HASH || hdr->has_dups) return;             // has_dups before the first insert: k_sample_dups found duplicates
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const uint64_t n_pairs = hdr->n_pairs;
   const uint64_t pol = policy_evict_first();
@@ -308,23 +340,38 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_count(const K* __restri
   }
 }
 
-// hand every occupied slot a contiguous range of the row-id array: block scan of the counts + one atomic per CTA
+// hand every occupied slot a contiguous range of the row-id array: four slots per thread, ONE block scan per 1024 slots (the key
+// counts and the number of occupied slots travel packed in one 64-bit word: both stay below 2^32 <= 2^40) + one atomic per CTA
+constexpr int GROUP_OFF_ITEMS = 4;
 __global__ void __launch_bounds__(BLOCK_THREADS) k_group_offsets(char* body, TableHeader* hdr) {
   if (hdr->mode != MODE_GROUP) return;
   __shared__ unsigned long long sm[33];
   __shared__ unsigned long long base_sm;
+  constexpr unsigned long long LOW40 = (1ULL << 40) - 1;
   const unsigned long long n_slots = hdr->n_pairs * 4;
-  for (unsigned long long s0 = (unsigned long long)blockIdx.x * BLOCK_THREADS; s0 < n_slots; s0 += (unsigned long long)gridDim.x * BLOCK_THREADS) {
-    const unsigned long long s = s0 + threadIdx.x;
-    unsigned long long* pay = reinterpret_cast<unsigned long long*>(body + s * 16) + 1;
-    unsigned long long w = s < n_slots ? *pay : ~0ULL;
-    const bool occ = (uint32_t)w != ROW_NONE;
-    const unsigned long long cnt = occ ? (w >> 32) : 0ULL;
-    unsigned long long total, ex = block_exclusive_scan(cnt, sm, &total);
-    const unsigned long long groups = block_reduce_sum((unsigned long long)occ, sm);
-    if (threadIdx.x == 0) { base_sm = total ? atomicAdd(&hdr->group_cursor, total) : 0ULL; if (groups) atomicAdd(&hdr->n_groups, groups); }
+  for (unsigned long long s0 = (unsigned long long)blockIdx.x * BLOCK_THREADS * GROUP_OFF_ITEMS; s0 < n_slots;
+       s0 += (unsigned long long)gridDim.x * BLOCK_THREADS * GROUP_OFF_ITEMS) {
+    const unsigned long long s = s0 + (unsigned long long)threadIdx.x * GROUP_OFF_ITEMS;
+    unsigned long long w[GROUP_OFF_ITEMS], packed = 0;
+    #pragma unroll
+    for (int i = 0; i < GROUP_OFF_ITEMS; i++) {
+      w[i] = s + i < n_slots ? *(reinterpret_cast<const unsigned long long*>(body + (s + i) * 16) + 1) : ~0ULL;
+      if ((uint32_t)w[i] != ROW_NONE) packed += (w[i] >> 32) + (1ULL << 40);
+    }
+    unsigned long long total, ex = block_exclusive_scan(packed, sm, &total);
+    if (threadIdx.x == 0) {
+      base_sm = (total & LOW40) ? atomicAdd(&hdr->group_cursor, total & LOW40) : 0ULL;
+      if (total >> 40) atomicAdd(&hdr->n_groups, total >> 40);
+    }
     __syncthreads();
-    if (occ) *pay = (cnt << 32) | (uint32_t)(base_sm + ex);        // low half: start offset, advanced to `end` by the fill pass
+    unsigned long long run = base_sm + (ex & LOW40);
+    #pragma unroll
+    for (int i = 0; i < GROUP_OFF_ITEMS; i++) {
+      if ((uint32_t)w[i] != ROW_NONE) {                                // low half: start offset, advanced to `end` by the fill pass
+        *(reinterpret_cast<unsigned long long*>(body + (s + i) * 16) + 1) = (w[i] & 0xFFFFFFFF00000000ULL) | (uint32_t)run;
+        run += w[i] >> 32;
+      }
+    }
     __syncthreads();
   }
 }
@@ -388,6 +435,8 @@ static unsigned dense_grid(Kern kern, int64_t nchunks, int waves) {
   if (waves <= 0) return (unsigned)nchunks;
   return (unsigned)std::min<int64_t>(nchunks, (int64_t)waves * resident_grid(kern, nchunks));
 }
+static int g_dup_sample = 1;   // look at a sample of the build keys for duplicates before trying the inline (unique-key) layout
+void set_dup_sample(int on) { g_dup_sample = on; }
 static int g_sparse = 1;       // hit lists for selective joins: 0 never, 1 sampled on the device, 2 always (unique layouts)
 void set_sparse(int policy) { g_sparse = policy; }
 static int g_tma_count = 0;    // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
@@ -421,6 +470,12 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
   if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
+  if (nR >= DUPS_MIN_ROWS && g_dup_sample) {
+    static bool attr_set = false;
+    constexpr int smem = DUPS_SAMPLES * 8 + DUPS_SLOTS * 2;
+    if (!attr_set) { cudaFuncSetAttribute(k_sample_dups<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    k_sample_dups<K><<<1, DUPS_THREADS, smem, stream>>>(R, nR, hdr);
+  }
   // A table beyond L2 reach that did not get the direct-address layout is built in table-slice order: one host look at the
   // header (the only sync in the build, and only for big tables), then K5 reorders (key, original index) by slice.
   const K* Rb = R; const uint32_t* perm = nullptr;
@@ -430,7 +485,9 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
     if (e != cudaSuccess) return e;
     if (h.mode == MODE_HASH) {
       ReorderView rv = reorder_view(reorder_area, nR, (int)sizeof(K));
-      e = radix_partition(R, nullptr, 0, nR, (int)sizeof(K), locality_parts(pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes, PART_SEL_TABLE, stream);
+      // duplicates already known: order by the slices of the grouped table the build goes to (for i64 keys both hashes are the same)
+      e = radix_partition(R, nullptr, 0, nR, (int)sizeof(K), locality_parts(pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes,
+                          h.has_dups ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
       if (e != cudaSuccess) return e;
       Rb = reinterpret_cast<const K*>(rv.keys); perm = rv.idx;
     }

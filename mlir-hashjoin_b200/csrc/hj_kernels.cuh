@@ -40,6 +40,7 @@ ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes);
 void set_allow_dense(int on);
 void set_locality(int on);
 void set_sparse(int policy);    // hit lists for selective joins: 0 never, 1 decided on the device from a sample of the probe keys (default), 2 always
+void set_dup_sample(int on);    // 1 (default): sample the build keys for duplicates before attempting the inline layout
 void set_dense_waves(int k);    // grid of the direct-address probe kernels: 0 = one chunk per CTA (default), k = at most k resident waves
 void set_tma_count(int on);     // debug/bench switch: 0 = LDG/STG streams in the direct-address count kernel instead of TMA bulk copies      // debug/bench switch: 0 disables the slice-ordered build/probe of big tables
 bool table_is_big(int64_t n_rows, int key_bytes);   // debug/bench switch: 0 forces the hash layout even for dense key ranges

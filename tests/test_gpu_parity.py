@@ -17,9 +17,11 @@ def layout(request, lib):
     the hit-list probe path (hjSetSparse(2)) forced instead of the match cache."""
     lib.hjSetAllowDense({"auto": 1, "hash": 0, "range": 2, "lists": 1, "hash-lists": 0}[request.param])
     lib.hjSetSparse(2 if "lists" in request.param else 1)
+    lib.hjSetDupSample(0 if request.param == "hash" else 1)       # "hash" keeps the attempt-inline-then-abort path under test
     yield request.param
     lib.hjSetAllowDense(1)
     lib.hjSetSparse(1)
+    lib.hjSetDupSample(1)
 
 
 def _join_np(R, S, cuda):

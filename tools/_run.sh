@@ -1,7 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -3
-for W in c4 c5; do
-timeout 300 python bench.py --workload $W --steps 5 --no-cpu-baseline --no-e2e --no-hash-arm > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; tail -2 gpurun_out/bench_$W.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_$W.json')); print('$W', d['value'], d['ms_per_step'], d['roofline']['phases_ms'], d['parity'])"
-done
-timeout 300 python bench.py --steps 10 --no-e2e --no-cpu-baseline > gpurun_out/bench_x.json 2>gpurun_out/bench_x.err; tail -2 gpurun_out/bench_x.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_x.json')); print('c2', d['ms_per_step'], d['roofline']['phases_ms'], d['hash_layout']['ms_per_step'], d['hash_layout']['phases_ms'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python bench.py --workload c4 --steps 5 --no-cpu-baseline --no-e2e --no-hash-arm > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -2 gpurun_out/bench_c4.err; python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_c4.json')); print('c4', d['value'], d['ms_per_step'], d['roofline']['phases_ms'], d['parity'])"
+( time timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2>&1 | grep real; tail -2 gpurun_out/bench_default.err
+( time timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ) 2>&1 | grep real; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json | cut -c1-600
