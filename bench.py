@@ -96,12 +96,14 @@ def cpu_baseline(cfg, sample_probe_log2: int, reps: int = 1, threads: int = 0) -
     R = o.generate(b.n, b.key_bytes, b.kind, b.seed, b.lo, b.domain, b.p16, b.key_mul)
     S = o.generate(nS, p.key_bytes, p.kind, p.seed, p.lo, p.domain, p.p16, p.key_mul)
     H = max(1, min(b.n, 2**31 - 1))          # one bucket per build row: the strongest setting of the reference's H
+    if threads == 0:                          # every host core this process may run on (torchrun exports OMP_NUM_THREADS=1: ask explicitly)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     secs, n_out = [], 0
     for _ in range(reps):
         n_out, sec = o.join_timed(R, S, H=H, threads=threads)
         secs.append(sec)
     best = min(secs)
-    cores = o.max_threads() if threads == 0 else threads
+    cores = threads
     return {"value": (b.n + nS) / best, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"full build side ({b.n} rows) x first {nS} probe rows of {cfg.name}, H={H} buckets, {n_out} pairs, {best:.3f} s",
             "seconds": secs}
@@ -123,7 +125,7 @@ def run_reference_arm(args, cfg) -> None:
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_name(args, cfg) -> str:
@@ -137,6 +139,17 @@ def workload_name(args, cfg) -> str:
 
 
 # ----------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +170,12 @@ def main() -> None:
     ap.add_argument("--no-hash-arm", action="store_true", help="skip the extra forced-hash-layout measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # Rank 0 prints ONE JSON line on stdout and nothing else does: libraries that write to fd 1 (NCCL prints its version banner there
+    # when a site-wide nccl.conf sets NCCL_DEBUG=VERSION) are sent to stderr for the whole run; _emit() writes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     sys.path.insert(0, str(ROOT))
     import __graft_entry__ as g
@@ -413,7 +432,7 @@ def main() -> None:
                        "timing": "CUDA events on the launching stream per step, summed over steps, max over ranks",
                        "wall_ms_per_step": wall_ms_per_step, "table_layout": args.layout},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches, "clocks": clocks, "parity": parity, "hash_layout": hash_arm, "fused_single_pass": fused_arm}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -257,6 +257,25 @@ __device__ __forceinline__ long long next_ticket(unsigned long long* counter, lo
   return b;
 }
 
+// The same with the next ticket fetched AHEAD: thread 0 issues the atomic at the top of an iteration and only needs its result at
+// the bottom, so the round trip (~1 us under load) is off the critical path and one barrier per iteration is enough (ncu on the
+// i64 build, two barriers and a blocking atomic per 512 keys: barrier stalls 24 warps per issue slot).
+//   TicketQueue q (shared);  blk = ticket_first(ctr, &q);  for (it = 0; blk < n; it++) { p = ticket_prefetch(ctr); ...; blk = ticket_advance(&q, it, p); }
+struct TicketQueue { long long slot[2]; };
+__device__ __forceinline__ long long ticket_first(unsigned long long* counter, TicketQueue* q) {
+  if (threadIdx.x == 0) q->slot[0] = (long long)atomicAdd(counter, 1ULL);
+  __syncthreads();
+  return q->slot[0];
+}
+__device__ __forceinline__ long long ticket_prefetch(unsigned long long* counter) {
+  return threadIdx.x == 0 ? (long long)atomicAdd(counter, 1ULL) : 0LL;
+}
+__device__ __forceinline__ long long ticket_advance(TicketQueue* q, uint32_t it, long long pending) {
+  if (threadIdx.x == 0) q->slot[(it + 1) & 1] = pending;
+  __syncthreads();                 // slot[it & 1] was read by everyone before this barrier of the PREVIOUS iteration: safe to reuse next time
+  return q->slot[(it + 1) & 1];
+}
+
 template <typename T>
 __device__ __forceinline__ T block_reduce_sum(T v, T* smem) {            // result valid in every thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
