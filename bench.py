@@ -257,7 +257,8 @@ def main() -> None:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         if args.workload == "c5" and world > 1:
             ev[0].record(stream)
-            a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x) if peer_x else hjdist.radix_join(dR, blo, dS, plo)
+            ev[1].record(stream)                                    # overwritten below on the fused path: partition + exchange | local join
+            a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x, exchanged=lambda: ev[1].record(stream)) if peer_x else hjdist.radix_join(dR, blo, dS, plo)
             ev[3].record(stream)
             n_out[0] = a.numel()
             launches[0] += 2 * 3 + 5
@@ -305,7 +306,9 @@ def main() -> None:
         clocks = sampler.stop() if sampler else None
         dev_ms = sum(e[0].elapsed_time(e[3]) for e in all_ev)
         phases = {"build": [], "count": [], "write": []}
-        if not (args.workload == "c5" and world > 1):
+        if args.workload == "c5" and world > 1:
+            phases = {"partition_exchange": [e[0].elapsed_time(e[1]) for e in all_ev], "local_join": [e[1].elapsed_time(e[3]) for e in all_ev]}
+        else:
             for e in all_ev:
                 phases["build"].append(e[0].elapsed_time(e[1])); phases["count"].append(e[1].elapsed_time(e[2])); phases["write"].append(e[2].elapsed_time(e[3]))
         t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
@@ -405,7 +408,16 @@ def main() -> None:
     ab = algorithmic_bytes(b.n, p.n if args.workload != "c5" else p.n // world, out_per_gpu, kb,
                            table_in_hbm=lib.hjTableBytes(b.n, kb) > 96 * 2**20)
     roofline = None
-    if phase_ms["count"]:
+    c5_phases = None
+    if "partition_exchange" in phase_ms and phase_ms["partition_exchange"]:
+        # multi-GPU radix plan: the exchange is bound by NVLink, the rest by HBM. Rank 0's phases (the step time above is the max over ranks).
+        px = sum(phase_ms["partition_exchange"]) / len(phase_ms["partition_exchange"]); lj = sum(phase_ms["local_join"]) / len(phase_ms["local_join"])
+        sent = (world - 1) / world * (dR.numel() + dS.numel()) * (kb + 4)            # (key, global row id) tuples leaving this GPU
+        c5_phases = {"partition_exchange_ms": px, "local_join_ms": lj, "nvlink_bytes_sent_per_gpu": int(sent),
+                     "nvlink_achieved_gbs": sent / (px / 1e3) / 1e9, "nvlink_peak_gbs": 770.0,
+                     "nvlink_frac": sent / (px / 1e3) / 1e9 / 770.0,
+                     "note": "peak = measured peer copy per direction per GPU (B200_PROFILING.md); the phase also holds two histogram passes and the count-matrix all-gather"}
+    if phase_ms.get("count"):
         k_ms = {k: sum(v) / len(v) for k, v in phase_ms.items()}
         dom = max(k_ms, key=k_ms.get)
         kernel = {"build": "build sequence (k_minmax, k_clear, k_build_dense | k_build_hash, ...)", "count": "k_count | k_count_sparse (+ k_sample_hits, k_scan_blocks and the 8-byte result-size readback)", "write": "k_write | k_write_sparse"}[dom]
@@ -432,6 +444,9 @@ def main() -> None:
                        "timing": "CUDA events on the launching stream per step, summed over steps, max over ranks",
                        "wall_ms_per_step": wall_ms_per_step, "table_layout": args.layout},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches, "clocks": clocks, "parity": parity, "hash_layout": hash_arm, "fused_single_pass": fused_arm}
+    if c5_phases is not None:
+        line["c5_phases"] = c5_phases
+        line["parity"] = {"count_matches_analytic": int(tot_out.item()) == cfg.expected_out} if cfg.expected_out is not None else None
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

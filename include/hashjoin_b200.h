@@ -121,6 +121,14 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
  * probe row id = probeRowBase + j (join_v1.mlir:499-500 stores the thread index). Asynchronous. */
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+/* hjCount / hjCountAsync for callers that already know the probe row ids at count time: the ids hjWrite would be given (payload
+ * column, else probeRowBase + j). When the probe relation is reordered by table slice (tables beyond L2 reach) the copy then carries
+ * these ids instead of the original index, and hjWrite needs no random gather through it (2^28 rows: ~4 ms). hjWrite must be called
+ * with the same dProbePayload / probeRowBase afterwards. */
+int32_t hjCountAsyncRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                         const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+int64_t hjCountRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                    const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
 /* K2+K3+K4 in ONE pass for callers that can bound the result size before probing (capacity = nS for a unique build): lookup,
  * decoupled look-back over the tiles' match counts, pairs streamed straight into the result columns; no match cache and no second
  * pass over the probe relation. The reference's call sequence (count, allocate, probe: join_v1.mlir:591,604-605) cannot use
@@ -160,13 +168,13 @@ void hjSetLocality(int32_t on);
  * Experimental: measured 3.7x slower on config 2 (profiles/README.md). */
 void hjSetTmaCount(int32_t on);
 /* Hit lists for selective joins (unique build keys): the count pass appends (build row, probe position) per chunk instead of writing a
- * match-cache word per probe row, the write pass copies the lists. 1 (default): decided on the device from a sample of 8192 probe
+ * match-cache word per probe row, the write pass copies the lists. 1 (default): decided on the device from a sample of 2048 probe
  * keys (lists when < 35 % hit, relations of >= 2^20 probe rows); 0: never; 2: always. Same result either way. */
 void hjSetSparse(int32_t policy);
 /* Experiment switch: grid of BOTH direct-address probe kernels: 0 = one chunk per CTA, k > 0 = at most k resident waves striding over
  * the chunks. Default (not reachable through this call): count 2 waves, write one chunk per CTA — see hj_kernels.cu for the numbers. */
 void hjSetDenseWaves(int32_t k);
-/* 1 (default): builds of >= 2^18 rows look at 16 384 sampled rows for duplicate keys first and go straight to the grouped layout
+/* 1 (default): builds of >= 2^18 rows look at 16 x 4 096 sampled rows for duplicate keys first and go straight to the grouped layout
  * when they find some (the inline, unique-key build is otherwise attempted and aborted); 0: always attempt the inline layout. */
 void hjSetDupSample(int32_t on);
 /* Which probe path the last hjCount on this scratch took: 0 = match cache, 1 = hit lists (diagnostic; one 8-byte readback). */

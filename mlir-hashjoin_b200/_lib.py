@@ -62,6 +62,8 @@ _SIGNATURES = {
     "hjCountAsync": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     "hjCountResult": (_i64, [_vp, _i64, _i32, _vp]),
     "hjCount": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "hjCountAsyncRows": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _u32, _vp]),
+    "hjCountRows": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _u32, _vp]),
     "hjWrite": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "hjJoinFused": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _u32, _vp]),
     "hjPartitionWorkspaceBytes": (_i64, [_i64, _i32]),

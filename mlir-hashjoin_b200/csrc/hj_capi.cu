@@ -47,7 +47,7 @@ std::map<const void*, LegacyTable> g_tables;
 // which scratches hold a slice-ordered copy of the probe relation (set by hjCount, read by hjWrite)
 std::mutex g_note_mu;
 std::map<const void*, bool> g_table_big;
-std::map<const void*, bool> g_scratch_reordered;
+std::map<const void*, int> g_scratch_reordered;
 
 // ---- hjJoinHost cache -------------------------------------------------------------------------------------
 struct DevBuf {
@@ -173,16 +173,31 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
   return HJ_OK;
 }
 
-int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {
+static int32_t count_async(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                           bool carryRows, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjCount", "null pointer or bad key width");
   if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjCount", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
   if (reinterpret_cast<uintptr_t>(dScratch) & 15) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 16-byte aligned");
   if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
-  bool big = true, reordered = false;                      // unknown table (not built through this process): look at its header
+  bool big = true; int reordered = 0;                      // unknown table (not built through this process): look at its header
   { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_table_big.find(dTable); if (it != g_table_big.end()) big = it->second; }
-  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, big, &reordered, S_(stream)));
+  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, big, &reordered, carryRows, dProbePayload, probeRowBase, S_(stream)));
   { std::lock_guard<std::mutex> lk(g_note_mu); g_scratch_reordered[dScratch] = reordered; }
   return HJ_OK;
+}
+
+int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {
+  return count_async(dS, nS, keyBytes, dTable, dScratch, scratchBytes, false, nullptr, 0, stream);
+}
+int32_t hjCountAsyncRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                         const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+  return count_async(dS, nS, keyBytes, dTable, dScratch, scratchBytes, true, dProbePayload, probeRowBase, stream);
+}
+int64_t hjCountRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                    const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+  int32_t rc = hjCountAsyncRows(dS, nS, keyBytes, dTable, dScratch, scratchBytes, dProbePayload, probeRowBase, stream);
+  if (rc != HJ_OK) return rc;
+  return hjCountResult(dScratch, nS, keyBytes, stream);
 }
 
 int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream) {
@@ -214,7 +229,7 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjWrite", "null pointer or bad key width");
-  bool reordered = false;
+  int reordered = 0;
   { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_scratch_reordered.find(dScratch); if (it != g_scratch_reordered.end()) reordered = it->second; }
   HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, reordered, S_(stream)));
   return HJ_OK;

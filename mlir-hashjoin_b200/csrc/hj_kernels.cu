@@ -150,20 +150,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_clear(TableHeader* hdr, int4*
 }
 
 // Duplicate pre-check. Finding out that the build keys are not unique by building the inline table costs a whole aborted build
-// (config 4: reorder 0.4 ms + clear + k_build_hash 0.67 ms before the grouped rebuild starts). One CTA looks at 16 384 pseudo-random
-// rows first: equal keys at two different rows are proof of duplicates (no false positives), has_dups is set and the inline attempt
-// is skipped; a miss only means the old path runs. With every key present 4 times (config 4) the sample holds ~12 such pairs.
-constexpr int DUPS_THREADS = 1024, DUPS_SAMPLES = 16384, DUPS_SLOTS = 32768;
+// (config 4: reorder 0.4 ms + clear + k_build_hash 0.67 ms before the grouped rebuild starts). Sixteen CTAs look at 4 096
+// pseudo-random rows each first: equal keys at two different rows are proof of duplicates (no false positives), has_dups is set
+// and the inline attempt is skipped; a miss only means the old path runs. With every key present 4 times (config 4) the samples
+// hold ~12 such pairs. (One CTA with all 16 384 samples needs 192 KB of shared memory, and a launch with that carve-out costs
+// 27 us even when the kernel exits at once; 48 KB per CTA costs 3 us.)
+constexpr int DUPS_THREADS = 1024, DUPS_CTAS = 16, DUPS_SAMPLES = 4096, DUPS_SLOTS = 8192;
 constexpr int64_t DUPS_MIN_ROWS = (int64_t)1 << 18;
 __device__ __forceinline__ uint64_t sample_pos(uint32_t i, uint64_t n) { return __umul64hi(mix64((uint64_t)i + 0x9E3779B97F4A7C15ULL), n); }
 template <typename K>
 __global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restrict__ R, int64_t nR, TableHeader* hdr) {
-  extern __shared__ __align__(16) unsigned char dups_raw[];
+  __shared__ long long keys_sm[DUPS_SAMPLES];
+  __shared__ unsigned short slots[DUPS_SLOTS];                   // sample id + 1, 0 = empty
   if (hdr->mode != MODE_HASH) return;
-  long long* keys_sm = reinterpret_cast<long long*>(dups_raw);                       // [DUPS_SAMPLES]
-  unsigned short* slots = reinterpret_cast<unsigned short*>(keys_sm + DUPS_SAMPLES);  // [DUPS_SLOTS], sample id + 1, 0 = empty (ids < 2^14)
+  const uint32_t first = blockIdx.x * DUPS_SAMPLES;               // this CTA's samples: global ids [first, first + DUPS_SAMPLES)
   for (int s = threadIdx.x; s < DUPS_SLOTS; s += DUPS_THREADS) slots[s] = 0;
-  for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) keys_sm[i] = (long long)R[sample_pos(i, (uint64_t)nR)];
+  for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) keys_sm[i] = (long long)R[sample_pos(first + i, (uint64_t)nR)];
   __syncthreads();
   bool dup = false;
   for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) {
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restric
       const unsigned short old = atomicCAS(&slots[h], (unsigned short)0, (unsigned short)(i + 1));
       if (old == 0) break;
       const int j = old - 1;
-      if (keys_sm[j] == key) { dup |= sample_pos(j, (uint64_t)nR) != sample_pos(i, (uint64_t)nR); break; }   // the same row drawn twice proves nothing
+      if (keys_sm[j] == key) { dup |= sample_pos(first + j, (uint64_t)nR) != sample_pos(first + i, (uint64_t)nR); break; }   // the same row drawn twice proves nothing
       h = (h + 1) & (DUPS_SLOTS - 1);
     }
   }
@@ -479,12 +481,7 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
   if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
-  if (nR >= DUPS_MIN_ROWS && g_dup_sample) {
-    static bool attr_set = false;
-    constexpr int smem = DUPS_SAMPLES * 8 + DUPS_SLOTS * 2;
-    if (!attr_set) { cudaFuncSetAttribute(k_sample_dups<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    k_sample_dups<K><<<1, DUPS_THREADS, smem, stream>>>(R, nR, hdr);
-  }
+  if (nR >= DUPS_MIN_ROWS && g_dup_sample) k_sample_dups<K><<<DUPS_CTAS, DUPS_THREADS, 0, stream>>>(R, nR, hdr);
   // A table beyond L2 reach that did not get the direct-address layout is built in table-slice order: one host look at the
   // header (the only sync in the build, and only for big tables), then K5 reorders (key, original index) by slice.
   const K* Rb = R; const uint32_t* perm = nullptr;
@@ -495,10 +492,12 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
     if (h.mode == MODE_HASH) {
       ReorderView rv = reorder_view(reorder_area, nR, (int)sizeof(K));
       // duplicates already known: order by the slices of the grouped table the build goes to (for i64 keys both hashes are the same)
-      e = radix_partition(R, nullptr, 0, nR, (int)sizeof(K), locality_parts(pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes,
+      // the reorder carries the FINAL row ids (payload value or row_base + index), read tile by tile next to the keys: looking the
+      // payload up through the carried index afterwards is a random 4-byte gather per row (2^28 rows: +4 ms of DRAM sector traffic)
+      e = radix_partition(R, payload, row_base, nR, (int)sizeof(K), locality_parts(pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes,
                           h.has_dups ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
       if (e != cudaSuccess) return e;
-      Rb = reinterpret_cast<const K*>(rv.keys); perm = rv.idx;
+      Rb = reinterpret_cast<const K*>(rv.keys); perm = rv.idx; payload = nullptr; row_base = 0;
     }
   }
   const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0, vecb = (reinterpret_cast<uintptr_t>(Rb) & 15) == 0;
@@ -674,7 +673,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
 // question — and the write pass only copies lists to their final offsets. The decision is taken on the device
 // (k_sample_hits -> counters[3]) and read uniformly by the kernels of both passes: no host round trip, and either path
 // is correct for any selectivity (hjSetSparse(2) forces this one in the parity tests).
-constexpr int SAMPLE_THREADS = 1024, SAMPLE_PER_THREAD = 8;
+constexpr int SAMPLE_THREADS = 1024, SAMPLE_PER_THREAD = 2;   // 2048 samples: +-1 % on the hit fraction, one round of loads
 constexpr int64_t SPARSE_MIN_ROWS = (int64_t)1 << 20;      // below this the sample costs more than it can save
 constexpr unsigned SPARSE_MAX_PERCENT = 35;                // hit lists move 16 B per hit, the match cache 8 B per row
 
@@ -1010,23 +1009,25 @@ static void launch_scan(unsigned long long* t, int64_t n, unsigned long long* bl
   if (nb > 1) k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums);
 }
 
-cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool* reordered,
-                             cudaStream_t stream) {
+cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, int* reordered,
+                             bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
   ScratchView sv = scratch_view(scratch, nS, key_bytes);
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
   const void* S = S_in;
-  *reordered = false;
+  *reordered = REORDER_NONE;
   if (big_hint && nS > 0 && g_locality) {
     TableHeader h;
     cudaError_t e = read_header(table, &h, stream);
     if (e != cudaSuccess) return e;
     if (h.mode != MODE_DENSE && (int64_t)h.n_pairs * 64 > LOCALITY_MIN_BYTES) {
       ReorderView rv = reorder_view(sv.reorder, nS, key_bytes);
-      e = radix_partition(S_in, nullptr, 0, nS, key_bytes, locality_parts((int64_t)h.n_pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes,
-                          h.mode == MODE_GROUP ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
+      // carry_rows: the caller already knows the probe row ids (payload column / row base), so the reorder carries them instead of
+      // the original index and the write pass needs no gather through it
+      e = radix_partition(S_in, carry_rows ? probe_payload : nullptr, carry_rows ? probe_row_base : 0u, nS, key_bytes, locality_parts((int64_t)h.n_pairs * 64),
+                          rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes, h.mode == MODE_GROUP ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
       if (e != cudaSuccess) return e;
-      S = rv.keys; *reordered = true;
+      S = rv.keys; *reordered = carry_rows ? REORDER_ROWS : REORDER_INDEX;
     }
   }
   { cudaError_t e = cudaMemsetAsync(sv.counters, 0, SCRATCH_COUNTERS * sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
@@ -1204,14 +1205,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
 }
 
 cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, bool reordered, cudaStream_t stream) {
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered, cudaStream_t stream) {
   ScratchView sv = scratch_view(const_cast<void*>(scratch), nS, key_bytes);
   if (sv.nchunks == 0) return cudaSuccess;
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
   const unsigned grid = (unsigned)sv.nchunks;                                  // unique layouts (the common case): one chunk per CTA measures 10 % faster
   const void* S = S_in; const uint32_t* perm = nullptr;
-  if (reordered) { ReorderView rv = reorder_view(sv.reorder, nS, key_bytes); S = rv.keys; perm = rv.idx; }
+  if (reordered != REORDER_NONE) { ReorderView rv = reorder_view(sv.reorder, nS, key_bytes); S = rv.keys; perm = rv.idx; }
+  if (reordered == REORDER_ROWS) { probe_payload = nullptr; probe_row_base = 0; }      // perm already holds the probe row ids
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   { cudaError_t e = cudaMemsetAsync(sv.counters + 2, 0, sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
 #define HJ_LAUNCH_WRITE(K, V) \

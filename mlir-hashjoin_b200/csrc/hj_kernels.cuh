@@ -51,11 +51,14 @@ cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t
 // K2+K3: count + scan (async).  Total lands in chunk_offsets[nchunks].  big_hint: the table may be beyond L2 reach (then the
 // header is read back once and, unless the layout is direct-address, the probe relation is reordered by table slice first);
 // *reordered tells write_pairs which copy of the relation the match cache refers to.
-cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool* reordered,
-                             cudaStream_t stream);
+// carry_rows: the probe row ids (payload column or row base) are known now, so a slice-ordered copy carries THEM (REORDER_ROWS)
+// instead of the original index (REORDER_INDEX); write_pairs must then be given the same ids or none.
+constexpr int REORDER_NONE = 0, REORDER_INDEX = 1, REORDER_ROWS = 2;
+cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, int* reordered,
+                             bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
 // K4: write pairs.
 cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, bool reordered,
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered,
                         cudaStream_t stream);
 
 // K2+K3+K4 fused (single pass, decoupled look-back): unique layouts only; the total lands where count_rows_async puts it.

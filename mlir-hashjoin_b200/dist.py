@@ -119,12 +119,15 @@ class PeerExchange:
 
 
 def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
-                     build_x: PeerExchange, probe_x: PeerExchange):
-    """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink)."""
+                     build_x: PeerExchange, probe_x: PeerExchange, exchanged=None):
+    """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink).
+    ``exchanged`` (optional callable) runs once every rank's tuples have landed, before the local join (bench.py marks a phase there)."""
     build_x.barrier()                                               # nobody is still reading last step's buffers
     nb = build_x.push(build_shard, build_row_base)
     npr = probe_x.push(probe_shard, probe_row_base)
     build_x.barrier()                                               # every rank's stores have landed
+    if exchanged is not None:
+        exchanged()
     return join.hash_join(build_x.keys[:nb], probe_x.keys[:npr], buildPayload=build_x.rows[:nb], probePayload=probe_x.rows[:npr])
 
 

@@ -86,8 +86,10 @@ def _scratch_for(table: HashTable, probeRelation: torch.Tensor) -> torch.Tensor:
     return table.scratch
 
 
-def countRows(probeRelation: torch.Tensor, table: HashTable) -> int:
-    """join_v1.mlir:110-147 -> result size. Runs K2 (count) + K3 (scan) and reads the total back (one host sync)."""
+def countRows(probeRelation: torch.Tensor, table: HashTable, probePayload: torch.Tensor | None = None, probeRowBase: int | None = None) -> int:
+    """join_v1.mlir:110-147 -> result size. Runs K2 (count) + K3 (scan) and reads the total back (one host sync).
+    ``probePayload`` / ``probeRowBase``: the probe row ids, when already known (hjCountRows): a slice-ordered copy of the probe
+    relation then carries them; probeRelation() must be given the same ones."""
     _require_cuda(probeRelation, "probeRelation")
     if not table.built:
         raise _lib.HashJoinError("countRows on a table that was never built")
@@ -95,6 +97,10 @@ def countRows(probeRelation: torch.Tensor, table: HashTable) -> int:
         raise _lib.HashJoinError("probe key dtype does not match the table")
     lib = _lib.load()
     scratch = _scratch_for(table, probeRelation)
+    if probePayload is not None or probeRowBase is not None:
+        total = lib.hjCountRows(_ptr(probeRelation), probeRelation.numel(), table.key_bytes, _ptr(table.storage), _ptr(scratch), scratch.numel(),
+                                _ptr(probePayload), (probeRowBase or 0) & 0xFFFFFFFF, _stream_ptr())
+        return _lib.check_status(total, "hjCountRows")
     total = lib.hjCount(_ptr(probeRelation), probeRelation.numel(), table.key_bytes, _ptr(table.storage),
                         _ptr(scratch), scratch.numel(), _stream_ptr())
     return _lib.check_status(total, "hjCount")
@@ -146,7 +152,7 @@ def hash_join(buildRelation: torch.Tensor, probeRelation_: torch.Tensor, table: 
         table = allocateHashTable(buildRelation.numel(), None, buildRelation.dtype, buildRelation.device)
     initializeHashTable(table)
     buildTable(buildRelation, table, buildPayload, rowBase)
-    n = countRows(probeRelation_, table)
+    n = countRows(probeRelation_, table, probePayload, probeRowBase)                # the probe row ids are known here: hjCountRows
     outR = torch.empty(n, dtype=torch.int32, device=probeRelation_.device)          # join_v1.mlir:604-605
     outS = torch.empty(n, dtype=torch.int32, device=probeRelation_.device)
     if n != 0:                                                                       # :600-601

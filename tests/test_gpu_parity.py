@@ -411,6 +411,14 @@ def test_big_table_slice_ordered_path(lib, cuda, oracle, dups):
     a2, b2 = join.hash_join(dR, dS, buildPayload=pr, probePayload=ps)
     lib.hjSetLocality(1)
     assert join.pair_digest(a2, b2) == join.pair_digest(a, bb)
+    # hash_join knows the probe row ids at count time (hjCountRows: the slice-ordered copy carries them). The reference's call
+    # sequence does not (countRows has no such argument): the copy then carries the original index and the write pass gathers.
+    table = join.allocateHashTable(nR, None, dR.dtype, cuda)
+    join.buildTable(dR, table, pr)
+    n = join.countRows(dS, table)
+    a3 = torch.empty(n, dtype=torch.int32, device=cuda); b3 = torch.empty(n, dtype=torch.int32, device=cuda)
+    join.probeRelation(dS, table, a3, b3, ps)
+    assert n == a.numel() and join.pair_digest(a3, b3) == join.pair_digest(a, bb)
 
 
 @pytest.mark.slow
