@@ -1,3 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -2
-timeout 300 python bench.py --steps 20 --no-e2e --no-cpu-baseline --no-hash-arm > gpurun_out/bench_x.json 2>gpurun_out/bench_x.err; tail -2 gpurun_out/bench_x.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_x.json')); print('c2', d['ms_per_step'], d['roofline']['phases_ms'])"
+C2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-hash-arm"
+timeout 300 $C2 > gpurun_out/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_count$|^k_write$|^k_build_dense$' -s 18 -c 6 -f -o gpurun_out/r1b_ncu_c2 $C2 > gpurun_out/ncu.log 2>&1; tail -1 gpurun_out/ncu.log | cut -c1-80
+C3="python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-hash-arm"
+timeout 300 $C3 > gpurun_out/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_count_sparse$|^k_write_sparse$' -s 9 -c 3 -f -o gpurun_out/r1b_ncu_c3 $C3 > gpurun_out/ncu.log 2>&1; tail -1 gpurun_out/ncu.log | cut -c1-80
