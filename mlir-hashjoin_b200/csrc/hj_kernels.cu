@@ -47,9 +47,9 @@ constexpr int64_t LOCALITY_SLICE_BYTES = (int64_t)8 << 20;
 bool table_is_big(int64_t n_rows, int key_bytes) { return preferred_pairs(n_rows, key_bytes) * 64 > LOCALITY_MIN_BYTES; }
 int locality_parts(int64_t table_body_bytes) {
   const int64_t f = (table_body_bytes + LOCALITY_SLICE_BYTES - 1) / LOCALITY_SLICE_BYTES;
-  return (int)std::min<int64_t>(256, std::max<int64_t>(2, f));
+  return (int)std::min<int64_t>(PART_MAX, std::max<int64_t>(2, f));
 }
-static int64_t reorder_bytes(int64_t n, int key_bytes) { return round_up(n * key_bytes, 256) + round_up(n * 4, 256) + partition_workspace_bytes(n, 256) + 256 * 8 + 256; }
+static int64_t reorder_bytes(int64_t n, int key_bytes) { return round_up(n * key_bytes, 256) + round_up(n * 4, 256) + partition_workspace_bytes(n, PART_MAX) + (PART_MAX + 1) * 8 + 256; }
 int64_t table_bytes(int64_t n_rows, int key_bytes) {
   return HEADER_BYTES + table_part_bytes(n_rows, key_bytes) + (table_is_big(n_rows, key_bytes) ? reorder_bytes(n_rows, key_bytes) : 0);
 }
@@ -71,21 +71,22 @@ ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   v.mcache = reinterpret_cast<uint32_t*>(base);
   const int64_t cache_bytes = round_up(v.nchunks * chunk_keys(key_bytes) * 4, 256);
   v.hit_list = reinterpret_cast<uint2*>(base);                  // the same bytes as the match cache plus as much again behind it
+  v.run_start = reinterpret_cast<uint32_t*>(base + cache_bytes); // grouped layout: first row-id slot of each probe row's run (second half)
   v.chunk_offsets = reinterpret_cast<unsigned long long*>(base + 2 * cache_bytes);
   v.counters = v.chunk_offsets + v.nchunks + 1;                 // [0] count<inline>, [1] count<grouped>, [2] write<grouped> tickets, [3] hit-list flag, [4] count_sparse ticket
   v.warp_counts = reinterpret_cast<uint32_t*>(base + 2 * cache_bytes + round_up((v.nchunks + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256));
   v.reorder = base + scratch_core_bytes(n_probe, key_bytes);
   return v;
 }
-// reorder area: [keys][original indices u32][offsets u64 x 257][partition workspace]
+// reorder area: [keys][row ids or original indices u32][offsets u64 x (PART_MAX + 1)][partition workspace]
 struct ReorderView { void* keys; uint32_t* idx; unsigned long long* offsets; void* ws; int64_t ws_bytes; };
 static ReorderView reorder_view(char* area, int64_t n, int key_bytes) {
   ReorderView r;
   r.keys = area;
   r.idx = reinterpret_cast<uint32_t*>(area + round_up(n * key_bytes, 256));
   r.offsets = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(r.idx) + round_up(n * 4, 256));
-  r.ws = reinterpret_cast<char*>(r.offsets) + 257 * 8 + 56;
-  r.ws_bytes = partition_workspace_bytes(n, 256);
+  r.ws = reinterpret_cast<char*>(r.offsets) + (PART_MAX + 1) * 8 + 56;
+  r.ws_bytes = partition_workspace_bytes(n, PART_MAX);
   return r;
 }
 
@@ -583,7 +584,7 @@ __device__ __forceinline__ const char* home_bucket(const char* __restrict__ body
 // exit at once. Keeping them separate keeps registers per thread (and so occupancy) at what each layout needs.
 template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
-                                                         const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache,
+                                                         const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache, uint32_t* __restrict__ run_start,
                                                          unsigned long long* __restrict__ chunk_totals, int64_t nchunks, unsigned long long* tickets,
                                                          const unsigned long long* __restrict__ sparse_flag) {
   using T = KeyTraits<K>;
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
       #pragma unroll 1
       for (int v = 0; v < VECS_PER_THREAD; v++) {
         const int64_t i0 = tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV;
-        K kv[KPV]; uint32_t mv[KPV]; Bucket b[KPV];
+        K kv[KPV]; uint32_t mv[KPV], sv[KPV]; Bucket b[KPV];
         load_vec_keys<K, VEC>(S, nS, i0, pol_s, kv);                        // rows past nS read as key 0: a harmless extra load
         #pragma unroll
         for (int e = 0; e < KPV; e++)
@@ -627,9 +628,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
         #pragma unroll
         for (int e = 0; e < KPV; e++) {
           if constexpr (mode == MODE_HASH) { mv[e] = i0 + e < nS ? finish_probe_unique<K>(body, n_pairs, kv[e], b[e]) : ROW_NONE; cnt += (mv[e] != ROW_NONE); }
-          else { mv[e] = i0 + e < nS ? (uint32_t)(group_finish(body, n_pairs, (long long)kv[e], b[e]) >> 32) : 0u; cnt += mv[e]; }
+          else {
+            // grouped: the slot's payload is (count << 32 | end of the key's row-id range). Count AND run start go to the scratch,
+            // so the write pass neither reloads the keys nor probes the table again
+            const unsigned long long pay = i0 + e < nS ? group_finish(body, n_pairs, (long long)kv[e], b[e]) : 0ULL;
+            mv[e] = (uint32_t)(pay >> 32); sv[e] = (uint32_t)pay - mv[e]; cnt += mv[e];
+          }
         }
         store_vec_u32<KPV>(mcache, i0, pol_s, mv);
+        if constexpr (mode == MODE_GROUP) store_vec_u32<KPV>(run_start, i0, pol_s, sv);
       }
       continue;
     }
@@ -1042,18 +1049,18 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     // bucketised layouts: one resident wave (idle launch ~3 us; the slice-ordered window stays tight)
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
-    k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
-    k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);  \
-    k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag); \
+    k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
+    k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);  \
+    k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag); \
     if (sparse_policy) { \
       k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
       k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
     }
     if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
       k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
-      k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag);
-      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
+      k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
+      k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag);
+      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
@@ -1070,7 +1077,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
 // on a bounded grid and the one that does not match the header exits at once (registers: 40 vs 64 per thread).
 template <typename K, bool VEC, bool GROUPED>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
-                                                         const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache,
+                                                         const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache, const uint32_t* __restrict__ run_start,
                                                          const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks, unsigned long long* tickets,
                                                          int32_t* __restrict__ outR, int32_t* __restrict__ outS,
                                                          const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
@@ -1152,23 +1159,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
       // by key slot (all lanes' runs of slot 0, then slot 1, ...). The warp expands its runs cooperatively: output element p of
       // a slot is found by a shuffle binary search over the lanes' inclusive counts, so both result columns leave as full
       // 128-byte lines and the row ids of a run are read with neighbouring lanes on neighbouring addresses.
-      K key[KPT];
-      #pragma unroll
-      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
-      const uint64_t n_pairs = hdr->n_pairs;
       const uint32_t* __restrict__ rows = reinterpret_cast<const uint32_t*>(body + hdr->rows_offset);
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       uint32_t incl[KPT], start[KPT], prow[KPT];
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_u32<KPV>(run_start, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &start[v * KPV]);
       unsigned long long wtotal = 0;
       #pragma unroll
       for (int k = 0; k < KPT; k++) {
         incl[k] = warp_inclusive_scan(m[k]);                                  // a probe row has < 2^32 matches; a warp slot total is kept in 64 bits below
-        start[k] = 0; prow[k] = 0;
-        if (m[k]) {
-          prow[k] = probe_row(elem_index<KPV>(tile_base, k));
-          const unsigned long long pay = group_finish(body, n_pairs, (long long)key[k], ld_bucket(home_bucket<int64_t>(body, n_pairs, (int64_t)key[k])));
-          start[k] = (uint32_t)pay - m[k];                                    // low half = end of the key's row range
-        }
+        prow[k] = m[k] ? probe_row(elem_index<KPV>(tile_base, k)) : 0u;       // the run start came from the count pass (no key reload, no second probe)
         wtotal += __shfl_sync(0xffffffffu, incl[k], 31);
       }
       unsigned long long* wt64 = reinterpret_cast<unsigned long long*>(scan_sm);
@@ -1217,8 +1217,8 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   { cudaError_t e = cudaMemsetAsync(sv.counters + 2, 0, sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
 #define HJ_LAUNCH_WRITE(K, V) \
-  k_write<K, V, false><<<dense_grid(k_write<K, V, false>, sv.nchunks, g_write_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3); \
-  k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);
+  k_write<K, V, false><<<dense_grid(k_write<K, V, false>, sv.nchunks, g_write_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3); \
+  k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
@@ -1372,7 +1372,6 @@ cudaError_t join_fused_async(const void* S, int64_t nS, int key_bytes, const voi
 // A CTA takes 4096 tuples, ranks them per partition with shared-memory atomics, sorts them by partition in shared memory and
 // writes each partition's run contiguously (512 tuples = 2-6 KB per run at 8 parts), so HBM / NVLink see full-width stores.
 // =========================================================================================================
-constexpr int PART_MAX = 256;
 constexpr int PART_ITEMS = 8;                                    // tuples per thread, blocked (contiguous) per thread
 constexpr int PART_TILE = BLOCK_THREADS * PART_ITEMS;            // 2048 tuples per CTA
 constexpr int PART_WARPS = BLOCK_THREADS / 32;
@@ -1506,17 +1505,18 @@ __global__ void __launch_bounds__(PSCAN_THREADS) k_part_scan(unsigned long long*
 // stalls of 29 warps per issue slot, and 1.5x the algorithmic DRAM writes from 64-byte runs evicted as partial sectors.
 constexpr int SCAT_ITEMS = 16;
 constexpr int SCAT_TILE = BLOCK_THREADS * SCAT_ITEMS;            // 4096 tuples: 16 per part and tile at 256 parts
-template <typename K>
+static_assert(PART_MAX <= 256, "ScatterSmem::spart holds part ids in a byte");
+template <typename K, bool LOCAL>
 struct ScatterSmem {
   K skeys[SCAT_TILE];
   unsigned long long delta[PART_MAX];                           // destination index of staged position i of part p: delta[p] + i
   unsigned long long gcur[PART_MAX];                            // running destination cursor of each part for this CTA
-  K* kptr[PART_MAX];
-  uint32_t* rptr[PART_MAX];
+  K* kptr[LOCAL ? 1 : PART_MAX];                                // per-part destinations: only the push into peers' buffers has more than one
+  uint32_t* rptr[LOCAL ? 1 : PART_MAX];
   unsigned int wh[PART_WARPS][PART_MAX];                        // per-warp counts, then per-warp exclusive offsets inside the part
   unsigned int lbase[PART_MAX + 1];                             // first staged position of each part
   unsigned short sidx[SCAT_TILE];                               // tile-local source position
-  unsigned char spart[SCAT_TILE];
+  unsigned char spart[SCAT_TILE];                               // part id (PART_MAX <= 256)
 };
 
 template <typename K, int SEL, bool LOCAL>
@@ -1524,10 +1524,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) k_part_scatter(const K* __re
                                                                    int n_parts, int bits, K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
                                                                    const unsigned long long* __restrict__ mat) {
   extern __shared__ __align__(16) unsigned char scat_raw[];
-  ScatterSmem<K>& sm = *reinterpret_cast<ScatterSmem<K>*>(scat_raw);
+  ScatterSmem<K, LOCAL>& sm = *reinterpret_cast<ScatterSmem<K, LOCAL>*>(scat_raw);
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC, NV = SCAT_ITEMS / KPV;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) { sm.kptr[p] = dst_keys[p]; sm.rptr[p] = dst_rows[p]; sm.gcur[p] = mat[(size_t)blockIdx.x * n_parts + p]; }
+  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) { if (!LOCAL) { sm.kptr[p] = dst_keys[p]; sm.rptr[p] = dst_rows[p]; } sm.gcur[p] = mat[(size_t)blockIdx.x * n_parts + p]; }
   K* const out_keys = dst_keys[0]; uint32_t* const out_rows = dst_rows[0];        // LOCAL: every part goes to the same pair of arrays
   const int64_t tpc = part_tiles_per_cta(n, gridDim.x);                           // the CTA's range is the one k_part_hist counted
   const int64_t lo = (int64_t)blockIdx.x * tpc * PART_TILE;
@@ -1635,8 +1635,8 @@ template <typename K, int SEL, bool LOCAL>
 static void launch_scatter_sel(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int n_parts, void* const* kp, uint32_t* const* rp,
                                const unsigned long long* mat, cudaStream_t stream) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_part_scatter<K, SEL, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<K>)); attr_set = true; }
-  k_part_scatter<K, SEL, LOCAL><<<part_grid(n), BLOCK_THREADS, sizeof(ScatterSmem<K>), stream>>>((const K*)keys, rows, row_base, n, n_parts, part_bits(n_parts),
+  if (!attr_set) { cudaFuncSetAttribute(k_part_scatter<K, SEL, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<K, LOCAL>)); attr_set = true; }
+  k_part_scatter<K, SEL, LOCAL><<<part_grid(n), BLOCK_THREADS, sizeof(ScatterSmem<K, LOCAL>), stream>>>((const K*)keys, rows, row_base, n, n_parts, part_bits(n_parts),
                                                                                               (K* const*)kp, rp, mat);
 }
 template <typename K>

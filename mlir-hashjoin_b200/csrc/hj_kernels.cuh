@@ -7,6 +7,10 @@
 namespace hj {
 
 constexpr int HEADER_BYTES = 256;              // table workspace = header + body
+// Most parts one radix-partition pass makes. 256 parts leave 33 MB table slices for 2^28 i64 build rows, with two slices live at a
+// time (50 % L2 hits in k_build_hash). 384 parts (22 MB slices) measured WORSE: 2^28 x 2^28 i64 20.6 ms vs 19.6 ms — shorter runs
+// in the scatter kernel cost more than the slices' better residency gains.
+constexpr int PART_MAX = 256;
 
 // tile geometry shared by count/scan/write (must agree between the two probe passes)
 constexpr int BLOCK_THREADS = 256;
@@ -29,6 +33,7 @@ int64_t num_chunks(int64_t n_probe, int key_bytes);
 struct ScratchView {
   uint32_t* mcache;
   uint2* hit_list;
+  uint32_t* run_start;                // grouped layout: first row-id slot of each probe row's run (the second half of the cache area)
   uint32_t* warp_counts;              // hit-list mode: entries in each of the 8 warp lists of a chunk
   unsigned long long* chunk_offsets;  // after scan: exclusive offsets; [nchunks] = total
   int64_t nchunks;

@@ -1,4 +1,5 @@
-C2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-hash-arm"
-timeout 300 $C2 > gpurun_out/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_count$|^k_write$|^k_build_dense$' -s 18 -c 6 -f -o gpurun_out/r1b_ncu_c2 $C2 > gpurun_out/ncu.log 2>&1; tail -1 gpurun_out/ncu.log | cut -c1-80
-C3="python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-hash-arm"
-timeout 300 $C3 > gpurun_out/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_count_sparse$|^k_write_sparse$' -s 9 -c 3 -f -o gpurun_out/r1b_ncu_c3 $C3 > gpurun_out/ncu.log 2>&1; tail -1 gpurun_out/ncu.log | cut -c1-80
+timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -2
+for W in c4 c5; do
+timeout 300 python bench.py --workload $W --steps 5 --no-cpu-baseline --no-e2e --no-hash-arm > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; tail -2 gpurun_out/bench_$W.err; python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_$W.json')); print('$W', d['value'], d['ms_per_step'], d['roofline']['phases_ms'], d['parity'])"
+done
