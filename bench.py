@@ -432,7 +432,7 @@ def main() -> None:
             roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:              # a reported baseline, timed on rank 0 at N = 1 only
         cpu = cpu_baseline(cfg, args.cpu_sample_log2)
         cpu.pop("seconds", None)
 
