@@ -33,13 +33,15 @@ UNIT = "tuples/s"
 
 
 # ----------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(nR, nS, out, key_bytes, matches_per_hit=1.0, table_in_hbm=True):
+def algorithmic_bytes(nR, nS, out, key_bytes, matches_per_hit=1.0, table_in_hbm=True, lookups_in_write=False):
     """inputs read once + one slot write per build row + one slot read per match candidate (when the
-    table is HBM-resident) + outputs written once. Returned per kernel so the dominant kernel gets its own share."""
+    table is HBM-resident) + outputs written once. Returned per kernel so the dominant kernel gets its own share: the slot reads
+    belong to the pass that does the lookups (the count pass, or the write pass when the count runs by range test)."""
     slot = 8 if key_bytes == 4 else 16
     build = nR * (key_bytes + 4) + nR * slot
-    count = nS * key_bytes + (out * slot if table_in_hbm else 0)
-    write = out * 8
+    lookups = out * slot if table_in_hbm else 0
+    count = nS * key_bytes + (0 if lookups_in_write else lookups)
+    write = out * 8 + (lookups if lookups_in_write else 0)
     return {"build": build, "count": count, "write": write, "total": build + count + write}
 
 
@@ -164,7 +166,9 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--c5-total-log2", type=int, default=0, help="c5 only: fix the TOTAL rows per side at 2^k (strong scaling); default 2^28 rows per GPU (weak)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5 only: peer-store partition kernel vs partition + NCCL all-to-all")
-    ap.add_argument("--layout", default="auto", choices=["auto", "hash"], help="hash = force the bucketised hash table even for dense key ranges")
+    ap.add_argument("--layout", default="auto", choices=["auto", "cache", "hash"],
+                    help="auto = library default (hjSetAllowDense(2): direct-address table for dense key ranges, counted by range test when gap-free and unique); "
+                         "cache = direct-address table with the match cache only (hjSetAllowDense(1)); hash = force the bucketised hash table (hjSetAllowDense(0))")
     ap.add_argument("--sparse", type=int, default=1, choices=[0, 1, 2], help="hjSetSparse: hit lists for selective joins (0 never, 1 sampled on the device, 2 always)")
     ap.add_argument("--dense-waves", type=int, default=None, help="hjSetDenseWaves (experiment): grid of the direct-address probe kernels")
     ap.add_argument("--no-hash-arm", action="store_true", help="skip the extra forced-hash-layout measurement")
@@ -238,7 +242,8 @@ def main() -> None:
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
-    lib.hjSetAllowDense(0 if args.layout == "hash" else 1)
+    DENSE_POLICY = {"hash": 0, "cache": 1, "auto": 2}
+    lib.hjSetAllowDense(DENSE_POLICY[args.layout])
     lib.hjSetSparse(args.sparse)
     if args.dense_waves is not None:
         lib.hjSetDenseWaves(args.dense_waves)
@@ -251,6 +256,7 @@ def main() -> None:
         return out_buf["R"][:n], out_buf["S"][:n]
     n_out = [0]
     launches = [0]
+    range_policy = [args.layout == "auto"]                     # hjSetAllowDense(2): k_count_range and k_write_range are queued too
     phase_ms = {"build": [], "count": [], "write": []}
 
     def step(timed: bool):
@@ -281,7 +287,7 @@ def main() -> None:
         # not chosen exit at once; they are launches all the same)
         chunk_rows = 16384 if dS.element_size() == 4 else 1024
         launches[0] += 13 + (1 if dS.numel() >= (1 << 20) and args.sparse else 0) + 3 + (2 if args.sparse else 0) \
-            + (2 if dS.numel() > 16384 * chunk_rows else 1) + 2 + (1 if args.sparse else 0)
+            + (2 if dS.numel() > 16384 * chunk_rows else 1) + 2 + (1 if args.sparse else 0) + (2 if range_policy[0] else 0)
         return ev, (outR, outS)
 
     def run_timed(steps, warmup, sample_clocks):
@@ -318,6 +324,7 @@ def main() -> None:
         return dev_ms_max / steps, wall_ms_max / steps, phases, clocks, last
 
     ms_per_step, wall_ms_per_step, phase_ms, clocks, last = run_timed(args.steps, args.warmup, True)
+    table_layout = lib.hjTableLayout(table.storage.data_ptr(), None) if not (args.workload == "c5" and world > 1) else 0   # 1 = direct-address, +0x100 = counted by range
     timed_launches = launches[0]
     tot_out = torch.tensor([n_out[0]], dtype=torch.int64, device=dev)
     if world > 1:
@@ -368,10 +375,16 @@ def main() -> None:
     if args.layout == "auto" and not args.no_hash_arm and not (args.workload == "c5" and world > 1):
         lib.hjSetAllowDense(0)
         h_ms, _, h_ph, _, _ = run_timed(max(3, args.steps // 3), 3, False)
-        lib.hjSetAllowDense(1)
         hash_arm = {"value": (nR_job + nS_job) / (h_ms / 1e3), "unit": UNIT, "ms_per_step": h_ms,
                     "phases_ms": {k: sum(v) / len(v) for k, v in h_ph.items() if v},
                     "note": "hjSetAllowDense(0): same inputs, direct-address layout disabled"}
+        if table_layout & 0x100:                              # the default counted by range test: show the match-cache variant of the same layout too
+            lib.hjSetAllowDense(1)
+            c_ms, _, c_ph, _, _ = run_timed(max(3, args.steps // 3), 3, False)
+            hash_arm["direct_address_with_match_cache"] = {"value": (nR_job + nS_job) / (c_ms / 1e3), "unit": UNIT, "ms_per_step": c_ms,
+                                                           "phases_ms": {k: sum(v) / len(v) for k, v in c_ph.items() if v},
+                                                           "note": "hjSetAllowDense(1): direct-address table, lookups in the count pass, match cache"}
+        lib.hjSetAllowDense(DENSE_POLICY[args.layout])
 
     # ---- single-pass probe (hjJoinFused): same build, then lookup + look-back + write in one kernel into a result of |S| pairs ---
     fused_arm = None
@@ -406,7 +419,7 @@ def main() -> None:
     peak, peak_src = measured_peak_gbs()
     out_per_gpu = n_out[0]
     ab = algorithmic_bytes(b.n, p.n if args.workload != "c5" else p.n // world, out_per_gpu, kb,
-                           table_in_hbm=lib.hjTableBytes(b.n, kb) > 96 * 2**20)
+                           table_in_hbm=lib.hjTableBytes(b.n, kb) > 96 * 2**20, lookups_in_write=bool(table_layout & 0x100))
     roofline = None
     c5_phases = None
     if "partition_exchange" in phase_ms and phase_ms["partition_exchange"]:
@@ -420,7 +433,7 @@ def main() -> None:
     if phase_ms.get("count"):
         k_ms = {k: sum(v) / len(v) for k, v in phase_ms.items()}
         dom = max(k_ms, key=k_ms.get)
-        kernel = {"build": "build sequence (k_minmax, k_clear, k_build_dense | k_build_hash, ...)", "count": "k_count | k_count_sparse (+ k_sample_hits, k_scan_blocks and the 8-byte result-size readback)", "write": "k_write | k_write_sparse"}[dom]
+        kernel = {"build": "build sequence (k_minmax, k_clear, k_build_dense | k_build_hash, ...)", "count": "k_count | k_count_sparse | k_count_range (+ k_sample_hits, k_scan_blocks and the 8-byte result-size readback)", "write": "k_write | k_write_sparse | k_write_range"}[dom]
         ach = ab[dom] / (k_ms[dom] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "algorithmic_bytes": ab[dom], "kernel_ms": k_ms[dom], "peak_source": peak_src,
@@ -429,7 +442,7 @@ def main() -> None:
                             "frac": ab["total"] / (ms_per_step / 1e3) / 1e9 / peak}}
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom)
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom if args.workload == "c2" and args.layout == "auto" else None)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:              # a reported baseline, timed on rank 0 at N = 1 only
@@ -442,7 +455,8 @@ def main() -> None:
             "config": {"workload": workload_name(args, cfg), "build_rows": nR_job, "probe_rows": nS_job, "result_pairs": int(tot_out.item()),
                        "l2_hygiene": "inputs larger than L2 (probe column >= 1 GiB per GPU streams through every step)",
                        "timing": "CUDA events on the launching stream per step, summed over steps, max over ranks",
-                       "wall_ms_per_step": wall_ms_per_step, "table_layout": args.layout},
+                       "wall_ms_per_step": wall_ms_per_step, "table_layout": args.layout,
+                       "table_layout_chosen": {0: "bucketised hash", 1: "direct-address", 2: "grouped"}.get(table_layout & 0xFF, "?") + (", count by range test" if table_layout & 0x100 else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches, "clocks": clocks, "parity": parity, "hash_layout": hash_arm, "fused_single_pass": fused_arm}
     if c5_phases is not None:
         line["c5_phases"] = c5_phases

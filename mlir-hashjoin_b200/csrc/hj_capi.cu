@@ -46,7 +46,8 @@ std::map<const void*, LegacyTable> g_tables;
 // ---- host-side notes about device workspaces: which tables may be beyond L2 reach (set by hjBuild, read by hjCount) and
 // which scratches hold a slice-ordered copy of the probe relation (set by hjCount, read by hjWrite)
 std::mutex g_note_mu;
-std::map<const void*, bool> g_table_big;
+struct TableNote { bool big; bool range; };
+std::map<const void*, TableNote> g_table_big;
 std::map<const void*, int> g_scratch_reordered;
 
 // ---- hjJoinHost cache -------------------------------------------------------------------------------------
@@ -168,7 +169,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
   if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, "hjBuild", "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
   if (reinterpret_cast<uintptr_t>(dTable) & 15) return fail(HJ_ERR_ARG, "hjBuild", "table workspace must be 16-byte aligned");
   if (tableBytes < hj::table_bytes(nR, keyBytes)) return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
-  { std::lock_guard<std::mutex> lk(g_note_mu); g_table_big[dTable] = hj::table_is_big(nR, keyBytes); }
+  { std::lock_guard<std::mutex> lk(g_note_mu); g_table_big[dTable] = TableNote{hj::table_is_big(nR, keyBytes), hj::allow_dense() == 2}; }
   HJ_CUDA("hjBuild", hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, S_(stream)));
   return HJ_OK;
 }
@@ -179,9 +180,9 @@ static int32_t count_async(const void* dS, int64_t nS, int32_t keyBytes, const v
   if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjCount", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
   if (reinterpret_cast<uintptr_t>(dScratch) & 15) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 16-byte aligned");
   if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
-  bool big = true; int reordered = 0;                      // unknown table (not built through this process): look at its header
-  { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_table_big.find(dTable); if (it != g_table_big.end()) big = it->second; }
-  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, big, &reordered, carryRows, dProbePayload, probeRowBase, S_(stream)));
+  bool big = true, range = true; int reordered = 0;        // unknown table (not built through this process): look at its header, queue every kernel
+  { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_table_big.find(dTable); if (it != g_table_big.end()) { big = it->second.big; range = it->second.range; } }
+  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, big, range, &reordered, carryRows, dProbePayload, probeRowBase, S_(stream)));
   { std::lock_guard<std::mutex> lk(g_note_mu); g_scratch_reordered[dScratch] = reordered; }
   return HJ_OK;
 }
@@ -210,6 +211,13 @@ int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* 
   return (int64_t)*host;
 }
 
+int32_t hjTableLayout(const void* dTable, void* stream) {
+  if (!dTable) return fail(HJ_ERR_ARG, "hjTableLayout", "null table");
+  uint32_t mode = 0, all_present = 0;
+  HJ_CUDA("hjTableLayout", hj::read_table_mode(dTable, &mode, &all_present, S_(stream)));
+  return (int32_t)(mode | (all_present ? 0x100u : 0u));
+}
+
 int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream) {
   if (!dScratch || !key_ok(keyBytes) || nS < 0) return fail(HJ_ERR_ARG, "hjProbePath", "bad argument");
   unsigned long long* host = pinned_total();
@@ -229,9 +237,11 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjWrite", "null pointer or bad key width");
-  int reordered = 0;
-  { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_scratch_reordered.find(dScratch); if (it != g_scratch_reordered.end()) reordered = it->second; }
-  HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, reordered, S_(stream)));
+  int reordered = 0; bool range = true;
+  { std::lock_guard<std::mutex> lk(g_note_mu);
+    auto it = g_scratch_reordered.find(dScratch); if (it != g_scratch_reordered.end()) reordered = it->second;
+    auto tn = g_table_big.find(dTable); if (tn != g_table_big.end()) range = tn->second.range; }
+  HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, reordered, range, S_(stream)));
   return HJ_OK;
 }
 
@@ -246,7 +256,7 @@ int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dT
   if ((reinterpret_cast<uintptr_t>(dScratch) & 15) || scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjJoinFused", "scratch workspace misaligned or too small (see hjScratchBytes)");
   HJ_CUDA("hjJoinFused", hj::join_fused_async(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, capacity, dProbePayload, probeRowBase, S_(stream)));
   uint32_t mode = 0;
-  HJ_CUDA("hjJoinFused", hj::read_table_mode(dTable, &mode, S_(stream)));
+  HJ_CUDA("hjJoinFused", hj::read_table_mode(dTable, &mode, nullptr, S_(stream)));
   if (mode == 2) return fail(HJ_ERR_STATE, "hjJoinFused", "build keys are not unique (grouped table): use hjCount + hjWrite");
   return hjCountResult(dScratch, nS, keyBytes, stream);
 }

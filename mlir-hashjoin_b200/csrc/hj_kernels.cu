@@ -183,9 +183,10 @@ __global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restric
   if (__syncthreads_or(dup) && threadIdx.x == 0) hdr->has_dups = 1;
 }
 
-// count_by_range: experimental (hjSetAllowDense(2)). A unique build whose keys are exactly [kmin, kmax] lets the count pass
-// skip the table (a probe key matches iff it is in range) and moves the single lookup per row into the write pass.
-// Measured on C2 it trades 0.9 ms of count for 1.0 ms of write (profiles/README.md), so it is off by default.
+// count_by_range (hjSetAllowDense(2), the default): a unique build whose keys are exactly [kmin, kmax] lets the count pass skip the
+// table (a probe key matches iff it is in range) and moves the single lookup per row into the write pass. With the generic kernels
+// it traded 0.9 ms of count for 1.0 ms of write on config 2 (2.10 vs 1.98 ms); with k_count_range / k_write_range (below) the step
+// takes 1.84 ms instead of 1.99 ms.
 __global__ void k_fallback_prepare(TableHeader* hdr, int count_by_range) {
   if (hdr->need_fallback) { hdr->mode = MODE_HASH; hdr->dense_range = 0; hdr->has_dups = 0; }
   else if (count_by_range && hdr->mode == MODE_DENSE && hdr->dense_range == hdr->n_rows) hdr->all_present = 1;
@@ -434,7 +435,7 @@ static unsigned resident_grid(Kern kern, int64_t needed_blocks) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(needed_blocks, (int64_t)per_sm * num_sms()));
 }
 
-static int g_allow_dense = 1;
+static int g_allow_dense = 2;   // 0 hash only, 1 direct-address layout with the match cache, 2 (default) + count by range for gap-free unique key ranges
 static int g_locality = 1;
 // Grid of the direct-address probe kernels: 0 = one chunk per CTA, k = at most k resident waves striding over the chunks.
 // Measured on config 2 (20 steps): count 1.231 / 1.248 / 1.233 / 1.231 ms and write 0.536 / 0.597 / 0.591 / 0.555 ms for k = 0 / 1 / 2 / 4.
@@ -466,10 +467,10 @@ static cudaError_t read_header(const void* table, TableHeader* out, cudaStream_t
   return e;
 }
 
-cudaError_t read_table_mode(const void* table, uint32_t* mode, cudaStream_t stream) {
+cudaError_t read_table_mode(const void* table, uint32_t* mode, uint32_t* all_present, cudaStream_t stream) {
   TableHeader h;
   cudaError_t e = read_header(table, &h, stream);
-  if (e == cudaSuccess) *mode = h.mode;
+  if (e == cudaSuccess) { *mode = h.mode; if (all_present) *all_present = h.all_present; }
   return e;
 }
 
@@ -590,10 +591,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
   if (MODE != MODE_GROUP && *sparse_flag) return;                  // selective join: k_count_sparse takes it
+  if (MODE == MODE_DENSE && hdr->all_present) return;              // gap-free unique key range: k_count_range takes it
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
   __shared__ unsigned long long red[33];
   constexpr uint32_t mode = MODE;
-  const bool all_present = MODE == MODE_DENSE && hdr->all_present != 0;
   const uint64_t n_pairs = hdr->n_pairs;
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
@@ -644,14 +645,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
     #pragma unroll
     for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
     uint32_t m[KPT];
-    if (all_present) {
-      // unique build whose keys are exactly [kmin, kmax]: a probe key matches iff it is in range. No table access and
-      // no match cache here; the write pass does the (single) lookup per matching row.
-      #pragma unroll
-      for (int k = 0; k < KPT; k++)
-        cnt += ((unsigned long long)((long long)key[k] - kmin) < drange && elem_index<KPV>(tile_base, k) < nS);
-      continue;
-    }
     if constexpr (mode == MODE_DENSE) {
       // direct addressing: one 4-byte load per in-range key, all KPT in flight
       #pragma unroll
@@ -967,6 +960,112 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count_dense_tma(const int32_t
 }
 
 // =========================================================================================================
+// K2r / K4r  count by range (hjSetAllowDense(2)): a unique build whose keys are exactly [kmin, kmax] (direct-address layout with
+// every slot taken; k_fallback_prepare sets all_present) lets the count pass skip the table — a probe key matches iff it is in
+// range — and drop the match cache; the write pass does the one lookup per matching row. The ranking of a tile's hits needs only
+// the range test, so in the write pass the ballots and the block barrier run while the lookups are in flight.
+// =========================================================================================================
+template <typename K, bool VEC>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_count_range(const K* __restrict__ S, int64_t nS, const TableHeader* __restrict__ hdr,
+                                                               unsigned long long* __restrict__ chunk_totals, int64_t nchunks) {
+  using T = KeyTraits<K>;
+  using UK = typename std::make_unsigned<K>::type;
+  if (hdr->mode != MODE_DENSE || !hdr->all_present) return;
+  constexpr int KPV = T::KEYS_PER_VEC, CHUNK_ROWS = chunk_keys((int)sizeof(K)), NV = CHUNK_ROWS / (BLOCK_THREADS * KPV);   // vectors per thread and chunk: 16 (i32) / 2 (i64)
+  constexpr int UNROLL = NV < 8 ? NV : 8;
+  __shared__ unsigned long long red[33];
+  const UK kmin = (UK)hdr->kmin, drange = (UK)hdr->dense_range;
+  const uint64_t pol_s = policy_evict_first();
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t chunk_base = chunk * CHUNK_ROWS;
+    const uint32_t lim = (uint32_t)(nS - chunk_base < CHUNK_ROWS ? nS - chunk_base : CHUNK_ROWS);
+    const K* __restrict__ Sc = S + chunk_base;
+    uint32_t cnt = 0;
+    if (VEC && lim == CHUNK_ROWS) {
+      #pragma unroll 1
+      for (int v0 = 0; v0 < NV; v0 += UNROLL) {
+        int4 x[UNROLL];
+        #pragma unroll
+        for (int u = 0; u < UNROLL; u++) x[u] = ld_stream_v4(Sc + ((v0 + u) * BLOCK_THREADS + threadIdx.x) * KPV, pol_s);
+        #pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+          K key[KPV]; memcpy(key, &x[u], 16);
+          #pragma unroll
+          for (int e = 0; e < KPV; e++) cnt += ((UK)key[e] - kmin) < drange;
+        }
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < lim; i += BLOCK_THREADS) cnt += ((UK)Sc[i] - kmin) < drange;
+    }
+    const unsigned long long total = block_reduce_sum((unsigned long long)cnt, red);
+    if (threadIdx.x == 0) chunk_totals[chunk] = total;
+  }
+}
+
+template <typename K, bool VEC>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,
+                                                               const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks,
+                                                               int32_t* __restrict__ outR, int32_t* __restrict__ outS,
+                                                               const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
+  using T = KeyTraits<K>;
+  using UK = typename std::make_unsigned<K>::type;
+  if (hdr->mode != MODE_DENSE || !hdr->all_present) return;
+  constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
+  constexpr int CHUNK_ROWS = chunk_keys((int)sizeof(K));
+  __shared__ uint32_t warp_totals[2][WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const UK kmin = (UK)hdr->kmin, drange = (UK)hdr->dense_range;
+  const uint32_t* __restrict__ tab = reinterpret_cast<const uint32_t*>(body);
+  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    unsigned long long out_base = chunk_offsets[chunk];
+    if (chunk_offsets[chunk + 1] == out_base) continue;                        // nothing to emit for this chunk (uniform)
+    const int64_t chunk_base = chunk * CHUNK_ROWS;
+    const uint32_t lim = (uint32_t)(nS - chunk_base < CHUNK_ROWS ? nS - chunk_base : CHUNK_ROWS);
+    const K* __restrict__ Sc = S + chunk_base;
+    int par = 0;
+    #pragma unroll 1
+    for (uint32_t tile_off = 0; tile_off < lim; tile_off += TILE, par ^= 1) {
+      K key[KPT]; uint32_t pos[KPT], m[KPT]; bool hit[KPT];
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) pos[k] = tile_off + ((k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV);
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys32<K, VEC>(Sc, lim, pos[v * KPV], pol_s, &key[v * KPV]);
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        const UK off = (UK)key[k] - kmin;
+        hit[k] = off < drange && pos[k] < lim;
+        m[k] = hit[k] ? ld_keep_u32(tab + off, pol_t) : ROW_NONE;              // in flight while the hits are ranked below
+      }
+      unsigned mask[KPT];
+      uint32_t wtotal = 0;
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, hit[k]); wtotal += __popc(mask[k]); }
+      uint32_t* wt = warp_totals[par];
+      if (lane == 0) wt[warp] = wtotal;
+      __syncthreads();
+      uint32_t wbase = 0, ttotal = 0;
+      #pragma unroll
+      for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[w]; wbase += w < warp ? x : 0u; ttotal += x; }
+      unsigned long long o = out_base + wbase;
+      #pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        if (hit[k]) {
+          const unsigned long long dst = o + __popc(mask[k] & lt);
+          const uint32_t j = (uint32_t)chunk_base + pos[k];
+          st_stream_u32(outR + dst, m[k], pol_s);
+          st_stream_u32(outS + dst, probe_payload ? probe_payload[j] : probe_row_base + j, pol_s);
+        }
+        o += __popc(mask[k]);
+      }
+      out_base += ttotal;
+    }
+    __syncthreads();                                                            // warp_totals is reused by the next chunk
+  }
+}
+
+// =========================================================================================================
 // K3  scan of chunk totals -> exclusive chunk offsets, total at [nchunks]      (replaces join_v1.mlir:371-420)
 // =========================================================================================================
 // Two short launches: every CTA scans 16 384 totals in place (thread-contiguous 128-byte runs, one block scan), publishing its
@@ -1016,7 +1115,9 @@ static void launch_scan(unsigned long long* t, int64_t n, unsigned long long* bl
   if (nb > 1) k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums);
 }
 
-cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, int* reordered,
+int allow_dense() { return g_allow_dense; }
+
+cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool range_hint, int* reordered,
                              bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
   ScratchView sv = scratch_view(scratch, nS, key_bytes);
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
@@ -1052,6 +1153,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
     k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);  \
     k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag); \
+    if (range_hint) k_count_range<K, V><<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks); \
     if (sparse_policy) { \
       k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
       k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
@@ -1060,7 +1162,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
       k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
       k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
       k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag);
-      if (g_allow_dense == 2) k_count<int32_t, true, MODE_DENSE><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
+      if (range_hint) k_count_range<int32_t, true><<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, hdr, sv.chunk_offsets, sv.nchunks);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
@@ -1084,6 +1186,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
                                                          const unsigned long long* __restrict__ sparse_flag) {
   if ((hdr->mode == MODE_GROUP) != GROUPED) return;
   if (!GROUPED && *sparse_flag) return;                              // hit-list mode: k_write_sparse takes it
+  if (!GROUPED && hdr->all_present) return;                          // count-by-range mode: k_write_range takes it
   using T = KeyTraits<K>;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
   // probe row id of position j of the relation the kernel reads: S may be a slice-ordered copy (perm = original index)
@@ -1094,10 +1197,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   __shared__ uint32_t warp_totals[2][BLOCK_THREADS / 32];
   __shared__ unsigned long long scan_sm[33];
   constexpr bool dups = GROUPED;
-  const bool all_present = !GROUPED && hdr->all_present != 0;
-  const long long kmin = hdr->kmin;
-  const unsigned long long drange = hdr->dense_range;
-  const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
+  const uint64_t pol_s = policy_evict_first();
   constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
   #pragma unroll 1
   __shared__ long long ticket;
@@ -1112,19 +1212,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
     const int64_t tile_base = chunk_base + (int64_t)tile * TILE;
     if (tile_base >= nS) break;
     uint32_t m[KPT];
-    if (all_present) {
-      K key[KPT];
-      #pragma unroll
-      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
-      #pragma unroll
-      for (int k = 0; k < KPT; k++) {
-        const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
-        m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
-      }
-    } else {
-      #pragma unroll
-      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
-    }
+    #pragma unroll
+    for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
 
     if constexpr (!dups) {
       // unique build: the cache already holds the build row. Output order is free (the result is a multiset,
@@ -1205,7 +1294,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
 }
 
 cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered, cudaStream_t stream) {
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered, bool range_hint,
+                        cudaStream_t stream) {
   ScratchView sv = scratch_view(const_cast<void*>(scratch), nS, key_bytes);
   if (sv.nchunks == 0) return cudaSuccess;
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
@@ -1222,6 +1312,12 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
+  if (range_hint && !reordered) {
+    if (key_bytes == 4) { if (vec) k_write_range<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base);
+                          else     k_write_range<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base); }
+    else                { if (vec) k_write_range<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base);
+                          else     k_write_range<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base); }
+  }
   if (g_sparse && !g_tma_count)
     k_write_sparse<<<(unsigned)std::min<int64_t>(PERSIST_GRID, (sv.nchunks + BLOCK_THREADS / 32 - 1) / (BLOCK_THREADS / 32)), BLOCK_THREADS, 0, stream>>>(
         hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, chunk_keys(key_bytes), outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);

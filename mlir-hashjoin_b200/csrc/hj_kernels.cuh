@@ -59,17 +59,19 @@ cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t
 // carry_rows: the probe row ids (payload column or row base) are known now, so a slice-ordered copy carries THEM (REORDER_ROWS)
 // instead of the original index (REORDER_INDEX); write_pairs must then be given the same ids or none.
 constexpr int REORDER_NONE = 0, REORDER_INDEX = 1, REORDER_ROWS = 2;
-cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, int* reordered,
+// range_hint: the table may have been built under hjSetAllowDense(2) (count by range): queue k_count_range / k_write_range too.
+int allow_dense();
+cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool range_hint, int* reordered,
                              bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
 // K4: write pairs.
 cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered,
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered, bool range_hint,
                         cudaStream_t stream);
 
 // K2+K3+K4 fused (single pass, decoupled look-back): unique layouts only; the total lands where count_rows_async puts it.
 cudaError_t join_fused_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch, int32_t* outR, int32_t* outS, int64_t capacity,
                              const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
-cudaError_t read_table_mode(const void* table, uint32_t* mode, cudaStream_t stream);
+cudaError_t read_table_mode(const void* table, uint32_t* mode, uint32_t* all_present, cudaStream_t stream);
 
 // K5: radix partition by the key hash (multi-GPU shuffle feed).  Two launches: histogram, scatter.
 //   counts: u64[n_parts] (device, zeroed by the call); offsets computed on device; keys/rows scattered so that

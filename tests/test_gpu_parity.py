@@ -10,16 +10,17 @@ from oracle.binding import sorted_pairs
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "hash", "range", "lists", "hash-lists"])
+@pytest.fixture(autouse=True, params=["auto", "hash", "cache", "lists", "hash-lists"])
 def layout(request, lib):
-    """Every parity case runs under each table / probe policy: the direct-address layout allowed (dense key ranges take it, and
-    fall back to the hash layout on a duplicate), the bucketised hash layout forced, count-by-range, and the first two again with
-    the hit-list probe path (hjSetSparse(2)) forced instead of the match cache."""
-    lib.hjSetAllowDense({"auto": 1, "hash": 0, "range": 2, "lists": 1, "hash-lists": 0}[request.param])
+    """Every parity case runs under each table / probe policy: the default (direct-address layout for dense key ranges, counted by
+    range test when the range is gap-free and unique, falling back to the hash layout on a duplicate), the bucketised hash layout
+    forced, the direct-address layout with the match cache only, and the last two again with the hit-list probe path
+    (hjSetSparse(2)) forced instead of the match cache."""
+    lib.hjSetAllowDense({"auto": 2, "hash": 0, "cache": 1, "lists": 1, "hash-lists": 0}[request.param])
     lib.hjSetSparse(2 if "lists" in request.param else 1)
     lib.hjSetDupSample(0 if request.param == "hash" else 1)       # "hash" keeps the attempt-inline-then-abort path under test
     yield request.param
-    lib.hjSetAllowDense(1)
+    lib.hjSetAllowDense(2)
     lib.hjSetSparse(1)
     lib.hjSetDupSample(1)
 
@@ -107,7 +108,7 @@ def test_selective_join_takes_hit_lists(lib, cuda, oracle, layout):
         join.buildTable(dR, table)
         n = join.countRows(dS, table)
         sv_flag = join.debug_sparse_flag(table, dS)
-        if layout in ("auto", "hash"):
+        if layout in ("auto", "hash", "cache"):
             assert sv_flag == int(expect_lists), (frac, sv_flag)
         elif "lists" in layout:
             assert sv_flag == 1

@@ -1,5 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -2
-for W in c4 c5; do
-timeout 300 python bench.py --workload $W --steps 5 --no-cpu-baseline --no-e2e --no-hash-arm > gpurun_out/bench_$W.json 2> gpurun_out/bench_$W.err; tail -2 gpurun_out/bench_$W.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_$W.json')); print('$W', d['value'], d['ms_per_step'], d['roofline']['phases_ms'], d['parity'])"
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/r1b_bench_c2.json 2> gpurun_out/r1b_bench_c2.err; tail -2 gpurun_out/r1b_bench_c2.err
+C2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-hash-arm"
+timeout 300 $C2 > gpurun_out/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_count_range$|^k_write_range$' -s 6 -c 2 -f -o gpurun_out/r1b_ncu_c2_range $C2 > gpurun_out/ncu.log 2>&1; tail -1 gpurun_out/ncu.log | cut -c1-80
