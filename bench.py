@@ -324,7 +324,10 @@ def main() -> None:
         return dev_ms_max / steps, wall_ms_max / steps, phases, clocks, last
 
     ms_per_step, wall_ms_per_step, phase_ms, clocks, last = run_timed(args.steps, args.warmup, True)
-    table_layout = lib.hjTableLayout(table.storage.data_ptr(), None) if not (args.workload == "c5" and world > 1) else 0   # 1 = direct-address, +0x100 = counted by range
+    table_layout = lib.hjTableLayout(table.storage.data_ptr(), None) if not (args.workload == "c5" and world > 1) else 0   # 1 = direct-address, +0x100 = gap-free and unique
+    hit_lists = bool(table.scratch is not None and table_layout and lib.hjProbePath(table.scratch.data_ptr(), dS.numel(), kb, None) == 1)
+    if hit_lists:
+        table_layout &= 0xFF                                  # selective join: the device-side sample chose hit lists over count-by-range
     timed_launches = launches[0]
     tot_out = torch.tensor([n_out[0]], dtype=torch.int64, device=dev)
     if world > 1:
@@ -456,7 +459,7 @@ def main() -> None:
                        "l2_hygiene": "inputs larger than L2 (probe column >= 1 GiB per GPU streams through every step)",
                        "timing": "CUDA events on the launching stream per step, summed over steps, max over ranks",
                        "wall_ms_per_step": wall_ms_per_step, "table_layout": args.layout,
-                       "table_layout_chosen": {0: "bucketised hash", 1: "direct-address", 2: "grouped"}.get(table_layout & 0xFF, "?") + (", count by range test" if table_layout & 0x100 else "")},
+                       "table_layout_chosen": {0: "bucketised hash", 1: "direct-address", 2: "grouped"}.get(table_layout & 0xFF, "?") + (", count by range test" if table_layout & 0x100 else "") + (", hit lists" if hit_lists else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches, "clocks": clocks, "parity": parity, "hash_layout": hash_arm, "fused_single_pass": fused_arm}
     if c5_phases is not None:
         line["c5_phases"] = c5_phases

@@ -445,11 +445,14 @@ static int g_count_waves = 2, g_write_waves = 0;
 void set_dense_waves(int k) { g_count_waves = g_write_waves = k; }
 template <typename Kern>
 static unsigned dense_grid(Kern kern, int64_t nchunks, int waves) {
-  if (waves <= 0) return (unsigned)nchunks;
+  if (waves <= 0) return (unsigned)std::min<int64_t>(nchunks, 16384);      // one chunk per CTA up to config 2's size, striding beyond (idle-launch cost)
   return (unsigned)std::min<int64_t>(nchunks, (int64_t)waves * resident_grid(kern, nchunks));
 }
 static int g_dup_sample = 1;   // look at a sample of the build keys for duplicates before trying the inline (unique-key) layout
 void set_dup_sample(int on) { g_dup_sample = on; }
+// k_count_range / k_write_range: one chunk per CTA up to 16 384 chunks (config 2 exactly), striding beyond: when they are NOT the
+// kernels chosen, a launch of 65 536 CTAs that exit at once costs 37 us (config 3), one of 16 384 costs 10 us.
+static unsigned range_grid(int64_t nchunks) { return (unsigned)std::min<int64_t>(nchunks, 16384); }
 static int g_sparse = 1;       // hit lists for selective joins: 0 never, 1 sampled on the device, 2 always (unique layouts)
 void set_sparse(int policy) { g_sparse = policy; }
 static int g_tma_count = 0;    // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
@@ -523,6 +526,8 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
   return cudaGetLastError();
 }
 
+// (Measured and removed: raising cudaLimitPersistingL2CacheSize to its maximum, 79 MB, so that the table's L2::evict_last lines get
+// the set-aside: config 2 1.84 -> 2.22 ms, forced hash 4.34 -> 6.47 ms. The streams lose more L2 than the table gains.)
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
                         void* table, int64_t table_bytes_, cudaStream_t stream) {
   if (table_bytes_ < table_bytes(nR, key_bytes)) return cudaErrorInvalidValue;      // sized by hjTableBytes, nothing less
@@ -682,7 +687,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_hits(const K* __restr
                                                                 unsigned long long* __restrict__ flag, int policy) {
   __shared__ unsigned long long red[33];
   const uint32_t mode = hdr->mode;
-  if (mode == MODE_GROUP || hdr->all_present) return;            // flag stays 0 (grouped: the cache holds counts; all_present: no cache at all)
+  if (mode == MODE_GROUP) return;                                // flag stays 0 (grouped: the cache holds counts)
   if (policy == 2) { if (threadIdx.x == 0) *flag = 1ULL; return; }
   const uint64_t n_pairs = hdr->n_pairs;
   const long long kmin = hdr->kmin;
@@ -967,10 +972,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count_dense_tma(const int32_t
 // =========================================================================================================
 template <typename K, bool VEC>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count_range(const K* __restrict__ S, int64_t nS, const TableHeader* __restrict__ hdr,
-                                                               unsigned long long* __restrict__ chunk_totals, int64_t nchunks) {
+                                                               unsigned long long* __restrict__ chunk_totals, int64_t nchunks,
+                                                               const unsigned long long* __restrict__ sparse_flag) {
   using T = KeyTraits<K>;
   using UK = typename std::make_unsigned<K>::type;
-  if (hdr->mode != MODE_DENSE || !hdr->all_present) return;
+  if (hdr->mode != MODE_DENSE || !hdr->all_present || *sparse_flag) return;     // few rows hit: hit lists read the keys once, this path twice
   constexpr int KPV = T::KEYS_PER_VEC, CHUNK_ROWS = chunk_keys((int)sizeof(K)), NV = CHUNK_ROWS / (BLOCK_THREADS * KPV);   // vectors per thread and chunk: 16 (i32) / 2 (i64)
   constexpr int UNROLL = NV < 8 ? NV : 8;
   __shared__ unsigned long long red[33];
@@ -1006,10 +1012,11 @@ template <typename K, bool VEC>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,
                                                                const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks,
                                                                int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                               const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base) {
+                                                               const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
+                                                               const unsigned long long* __restrict__ sparse_flag) {
   using T = KeyTraits<K>;
   using UK = typename std::make_unsigned<K>::type;
-  if (hdr->mode != MODE_DENSE || !hdr->all_present) return;
+  if (hdr->mode != MODE_DENSE || !hdr->all_present || *sparse_flag) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
   constexpr int CHUNK_ROWS = chunk_keys((int)sizeof(K));
   __shared__ uint32_t warp_totals[2][WARPS];
@@ -1153,7 +1160,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
     k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);  \
     k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag); \
-    if (range_hint) k_count_range<K, V><<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks); \
+    if (range_hint) k_count_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag); \
     if (sparse_policy) { \
       k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
       k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
@@ -1162,7 +1169,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
       k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
       k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
       k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag);
-      if (range_hint) k_count_range<int32_t, true><<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, hdr, sv.chunk_offsets, sv.nchunks);
+      if (range_hint) k_count_range<int32_t, true><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag);
     } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
@@ -1313,10 +1320,10 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
   if (range_hint && !reordered) {
-    if (key_bytes == 4) { if (vec) k_write_range<int32_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base);
-                          else     k_write_range<int32_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base); }
-    else                { if (vec) k_write_range<int64_t, true><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base);
-                          else     k_write_range<int64_t, false><<<grid, BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base); }
+    if (key_bytes == 4) { if (vec) k_write_range<int32_t, true><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3);
+                          else     k_write_range<int32_t, false><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3); }
+    else                { if (vec) k_write_range<int64_t, true><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3);
+                          else     k_write_range<int64_t, false><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3); }
   }
   if (g_sparse && !g_tma_count)
     k_write_sparse<<<(unsigned)std::min<int64_t>(PERSIST_GRID, (sv.nchunks + BLOCK_THREADS / 32 - 1) / (BLOCK_THREADS / 32)), BLOCK_THREADS, 0, stream>>>(
