@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q 2>&1 | tail -3
 n=2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --workload c5 --steps 5 --no-cpu-baseline > gpurun_out/bench_c5_${n}gpu.json 2> gpurun_out/bench_c5_${n}gpu.err; tail -2 gpurun_out/bench_c5_${n}gpu.err | cut -c1-300; python -c "
-import json; d=json.load(open('gpurun_out/bench_c5_${n}gpu.json')); print($n, d['value'], d['ms_per_step'], d['config']['workload'], d['roofline'].get('phases_ms'), d.get('parity'))"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 20 > gpurun_out/r1b_bench_c2_${n}gpu_range.json 2> gpurun_out/r1b_bench_c2_${n}gpu_range.err; tail -2 gpurun_out/r1b_bench_c2_${n}gpu_range.err | cut -c1-200
+python -c "
+import json; d=json.load(open('gpurun_out/r1b_bench_c2_${n}gpu_range.json')); print($n, round(d['value']/1e9,2), 'G/s', round(d['ms_per_step'],3), 'ms', d['config']['table_layout_chosen'], d['roofline']['phases_ms'], d['parity'], d['e2e'] and d['e2e']['ms_per_step'], d['cpu_baseline'])"
