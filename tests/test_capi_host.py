@@ -101,3 +101,23 @@ def test_no_cpu_fallback(lib):
     from mlir_hashjoin_b200 import _lib, join
     with pytest.raises(_lib.HashJoinError):
         join.buildTable(torch.arange(4, dtype=torch.int32), join.HashTable(torch.empty(1024, dtype=torch.uint8), 4, 4))
+
+
+def test_argument_validation_of_native_entry_points(lib):
+    """Bad arguments are refused on the host, before any CUDA call: negative status, a message in hjLastErrorString, nothing thrown."""
+    buf = np.zeros(4096, np.uint8)
+    p = buf.ctypes.data
+    assert lib.hjScratchBytes(1 << 20, 4) >= 8 << 20                     # match cache + as much again for the hit lists / run starts
+    assert lib.hjCountRows(None, 10, 4, p, p, buf.size, None, 0, None) < 0          # null probe relation
+    assert lib.hjCountRows(p, 10, 3, p, p, buf.size, None, 0, None) < 0             # key width
+    assert lib.hjCountAsyncRows(p, (1 << 32) + 1, 4, p, p, buf.size, None, 0, None) < 0   # more probe rows than 32-bit row ids
+    assert lib.hjCountRows(p, 1 << 20, 4, p, p, 1024, None, 0, None) < 0            # scratch too small
+    assert lib.hjJoinFused(p, 10, 4, p, None, 0, p, p, 10, None, 0, None) < 0        # no scratch
+    assert lib.hjJoinFused(p, 10, 4, p, p, buf.size, None, None, 10, None, 0, None) < 0   # capacity without result columns
+    assert lib.hjTableLayout(None, None) < 0
+    assert lib.hjProbePath(None, 10, 4, None) < 0
+    assert lib.hjPartitionWorkspaceBytes(1 << 20, 8) > 0
+    assert lib.hjLastErrorString()
+    for setter in (lib.hjSetAllowDense, lib.hjSetSparse, lib.hjSetDupSample):  # switches are plain host state: callable without a device
+        setter(1)
+    lib.hjSetAllowDense(2)
