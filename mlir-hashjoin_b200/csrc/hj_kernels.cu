@@ -644,14 +644,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
         store_vec_u32<KPV>(mcache, i0, pol_s, mv);
         if constexpr (mode == MODE_GROUP) store_vec_u32<KPV>(run_start, i0, pol_s, sv);
       }
-      continue;
-    }
-    K key[KPT];
-    #pragma unroll
-    for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
-    uint32_t m[KPT];
-    if constexpr (mode == MODE_DENSE) {
+    } else {
       // direct addressing: one 4-byte load per in-range key, all KPT in flight
+      K key[KPT];
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
+      uint32_t m[KPT];
       #pragma unroll
       for (int k = 0; k < KPT; k++) {
         const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
@@ -659,9 +657,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
       }
       #pragma unroll
       for (int k = 0; k < KPT; k++) cnt += (m[k] != ROW_NONE);
+      #pragma unroll
+      for (int v = 0; v < VECS_PER_THREAD; v++) store_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
     }
-    #pragma unroll
-    for (int v = 0; v < VECS_PER_THREAD; v++) store_vec_u32<KPV>(mcache, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &m[v * KPV]);
   }
   cnt = block_reduce_sum(cnt, red);
   if (threadIdx.x == 0) chunk_totals[chunk] = cnt;
@@ -1153,8 +1151,7 @@ cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const 
     else                k_sample_hits<int64_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.counters + 3, sparse_policy);
   }
   if (sv.nchunks > 0) {
-    const unsigned grid = (unsigned)sv.nchunks;                               // direct-address layout: one chunk per CTA
-    // bucketised layouts: one resident wave (idle launch ~3 us; the slice-ordered window stays tight)
+    // direct-address layout: dense_grid(); bucketised layouts: one resident wave (idle launch ~3 us; the slice-ordered window stays tight)
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
     k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
@@ -1206,8 +1203,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   constexpr bool dups = GROUPED;
   const uint64_t pol_s = policy_evict_first();
   constexpr int CHUNK_TILES = chunk_tiles((int)sizeof(K));
-  #pragma unroll 1
   __shared__ long long ticket;
+  #pragma unroll 1
   for (long long chunk = GROUPED ? next_ticket(tickets, &ticket) : (long long)blockIdx.x; chunk < nchunks;
        chunk = GROUPED ? next_ticket(tickets, &ticket) : chunk + gridDim.x) {
   const int64_t chunk_base = chunk * (TILE * CHUNK_TILES);
@@ -1307,7 +1304,6 @@ cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void*
   if (sv.nchunks == 0) return cudaSuccess;
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
-  const unsigned grid = (unsigned)sv.nchunks;                                  // unique layouts (the common case): one chunk per CTA measures 10 % faster
   const void* S = S_in; const uint32_t* perm = nullptr;
   if (reordered != REORDER_NONE) { ReorderView rv = reorder_view(sv.reorder, nS, key_bytes); S = rv.keys; perm = rv.idx; }
   if (reordered == REORDER_ROWS) { probe_payload = nullptr; probe_row_base = 0; }      // perm already holds the probe row ids
@@ -1629,7 +1625,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) k_part_scatter(const K* __re
   extern __shared__ __align__(16) unsigned char scat_raw[];
   ScatterSmem<K, LOCAL>& sm = *reinterpret_cast<ScatterSmem<K, LOCAL>*>(scat_raw);
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC, NV = SCAT_ITEMS / KPV;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5;
   for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) { if (!LOCAL) { sm.kptr[p] = dst_keys[p]; sm.rptr[p] = dst_rows[p]; } sm.gcur[p] = mat[(size_t)blockIdx.x * n_parts + p]; }
   K* const out_keys = dst_keys[0]; uint32_t* const out_rows = dst_rows[0];        // LOCAL: every part goes to the same pair of arrays
   const int64_t tpc = part_tiles_per_cta(n, gridDim.x);                           // the CTA's range is the one k_part_hist counted
