@@ -21,7 +21,12 @@
  * CUDA runtime API on the current device (primary context), so pointers from mgpuMemAlloc / cudaMalloc / torch are
  * valid.  Entry points of groups A and B and the `hashJoin*` functions are synchronous on return; `hj*` functions
  * are asynchronous on the stream they are given unless documented otherwise.  Nothing throws across this boundary:
- * failures return a negative status (and print one line to stderr); hjLastErrorString() has the text.
+ * failures return a negative status (and print one line to stderr); hjLastErrorString() has the text (per calling thread).
+ * Threads and devices: the `hj*` functions keep no per-call state on the host — layout decisions live in the device-resident table
+ * header and scratch counters, small readbacks land in a pinned block owned by the calling thread — so different host threads may
+ * drive different (table, scratch, stream) triples concurrently, on any device (the current device at the call is used). One table
+ * may be probed from several streams at once with distinct scratch workspaces. The legacy group B entry points and hjJoinHost cache
+ * their workspaces per process under a mutex: callable from any thread, serialised.
  * There is NO CPU fallback: without a CUDA device every join entry point fails with HJ_ERR_CUDA.
  */
 #ifndef HASHJOIN_B200_H
@@ -36,7 +41,7 @@ extern "C" {
 #define HJ_OK 0
 #define HJ_ERR_ARG (-22)     /* bad argument: null pointer, non-unit stride, misaligned or too-small workspace */
 #define HJ_ERR_CUDA (-5)     /* CUDA runtime error (no device, launch failure, out of memory) */
-#define HJ_ERR_STATE (-2)    /* legacy surface: countRows/probeRelation on a table that was never built */
+#define HJ_ERR_STATE (-2)    /* count / write on a table that was never built (or built for the other key width); hjJoinFused on a layout it cannot probe */
 
 /* StridedMemRefType<T,1> as passed by llvm.emit_c_interface (Experiments/passing-memrefs.mlir:10, join_v1.ll:106-111) */
 typedef struct { void* allocated; void* aligned; int64_t offset; int64_t sizes[1]; int64_t strides[1]; } HjMemRef1D;
@@ -110,10 +115,30 @@ int32_t _mlir_ciface_hashJoinWriteI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef
 /* ---- C2. native C surface: device pointers + explicit stream (cudaStream_t passed as void*) ---------------- */
 int64_t hjTableBytes(int64_t nR, int32_t keyBytes);            /* keyBytes: 4 or 8 */
 int64_t hjScratchBytes(int64_t nS, int32_t keyBytes);
-/* K0+K1. payload == NULL: build row id = rowBase + i (join_v1.mlir:232). Asynchronous. */
+/* K0+K1. payload == NULL: build row id = rowBase + i (join_v1.mlir:232). Row id 0xFFFFFFFF is reserved (EMPTY): rowBase + nR must
+ * stay below it and payload values must not be 0xFFFFFFFF. dTable: 64-byte aligned (buckets are 32-byte vector loads paired into
+ * 64-byte DRAM atoms). Asynchronous, except that a table beyond L2 reach reads its own header back once (one stream sync). */
 int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase,
                 void* dTable, int64_t tableBytes, void* stream);
-/* K2+K3, asynchronous; hjCountResult copies the total back and synchronises the stream; hjCount does both. */
+/* hjBuild with the table's policy stated per call instead of taken from the process defaults (hjSet*). The policy is stored in the
+ * table header; every later hjCount / hjWrite on that table follows it, so tables built under different policies coexist.
+ * policy = HJ_POLICY_DEFAULT or an OR of: HJ_POLICY_DENSE_* (one of), HJ_POLICY_RADIX, HJ_POLICY_LISTS_* (one of), HJ_POLICY_DUP_SAMPLE. */
+#define HJ_POLICY_DEFAULT 0xFFFFFFFFu
+#define HJ_POLICY_DENSE_OFF 0u          /* never the direct-address layout */
+#define HJ_POLICY_DENSE_CACHE 1u        /* direct-address layout for dense key ranges, lookups in the count pass (match cache) */
+#define HJ_POLICY_DENSE_RANGE 2u        /* + gap-free unique ranges are counted by range test alone (library default) */
+#define HJ_POLICY_RADIX (1u << 2)       /* tables beyond L2 reach (> 48 MB of buckets): radix join instead of a global hash table (default on) */
+#define HJ_POLICY_LISTS_NEVER (0u << 3)
+#define HJ_POLICY_LISTS_SAMPLED (1u << 3) /* hit lists for selective joins, decided on the device from a probe-key sample (default) */
+#define HJ_POLICY_LISTS_ALWAYS (2u << 3)
+#define HJ_POLICY_DUP_SAMPLE (1u << 5)  /* sample the build keys for duplicates before attempting a unique-key layout (default on) */
+#define HJ_POLICY_TMA_COUNT (1u << 6)   /* experimental: TMA-staged streams in the direct-address count kernel (slower; default off) */
+int32_t hjBuildEx(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase,
+                  void* dTable, int64_t tableBytes, uint32_t policy, void* stream);
+uint32_t hjDefaultPolicy(void);          /* the policy word hjBuild would use now */
+/* K2+K3; hjCountResult copies the total back and synchronises the stream; hjCount does both. */
+/* hjCountAsync queues the count; it first reads the table header back (256 bytes: one stream sync) so that only the kernels of the
+ * layout actually built are launched. dScratch: 256-byte aligned. HJ_ERR_STATE when dTable holds no table for this key width. */
 int32_t hjCountAsync(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream);
 int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream);
 int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream);
@@ -122,8 +147,8 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
 /* hjCount / hjCountAsync for callers that already know the probe row ids at count time: the ids hjWrite would be given (payload
- * column, else probeRowBase + j). When the probe relation is reordered by table slice (tables beyond L2 reach) the copy then carries
- * these ids instead of the original index, and hjWrite needs no random gather through it (2^28 rows: ~4 ms). hjWrite must be called
+ * column, else probeRowBase + j). When the probe relation is radix-partitioned (tables beyond L2 reach) the copy then carries
+ * these ids instead of the original index, and hjWrite needs no random gather through a payload column. hjWrite must be called
  * with the same dProbePayload / probeRowBase afterwards. */
 int32_t hjCountAsyncRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
                          const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
@@ -133,7 +158,7 @@ int64_t hjCountRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dT
  * decoupled look-back over the tiles' match counts, pairs streamed straight into the result columns; no match cache and no second
  * pass over the probe relation. The reference's call sequence (count, allocate, probe: join_v1.mlir:591,604-605) cannot use
  * it. Returns the number of pairs; pairs beyond `capacity` are counted but not written. HJ_ERR_STATE when the build keys were not
- * unique (use hjCount + hjWrite). Synchronous. */
+ * unique or the table is radix-partitioned (use hjCount + hjWrite). Synchronous. */
 int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
                     int32_t* dOutR, int32_t* dOutS, int64_t capacity, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
 /* K5. Radix partition on the key hash into nParts (<= 256) contiguous ranges; dOffsets: u64[nParts+1]. Asynchronous. */
@@ -162,8 +187,8 @@ int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32
  * 2 (default): additionally a unique, gap-free key range (dense surrogate keys) is counted by range test alone and looked up once, in
  * the write pass (config 2: 1.84 instead of 1.99 ms). The policy in force at hjBuild decides. */
 void hjSetAllowDense(int32_t on);
-/* 1 (default): hash tables beyond L2 reach (> 48 MB) are built and probed in table-slice order (the relation is radix-partitioned
- * on the bucket hash first); 0 probes in input order. Costs one header readback (a stream sync) per build and per count. */
+/* 1 (default): build relations whose hash table would not stay in L2 (> 48 MB of buckets) are joined by radix partitioning (two
+ * passes, <= 65 536 partitions) and shared-memory tables; 0 builds one hash table in global memory and probes in input order. */
 void hjSetLocality(int32_t on);
 /* 1: the direct-address count kernel moves its two streams with TMA bulk copies (cp.async.bulk, per-warp mbarriers); 0 (default): LDG/STG.
  * Experimental: measured 3.7x slower on config 2 (profiles/README.md). */
@@ -179,7 +204,7 @@ void hjSetDenseWaves(int32_t k);
  * when they find some (the inline, unique-key build is otherwise attempted and aborted); 0: always attempt the inline layout. */
 void hjSetDupSample(int32_t on);
 /* Layout the last hjBuild gave this table (diagnostic; one header readback): 0 = bucketised hash (unique keys), 1 = direct-address,
- * 2 = grouped (duplicate keys); + 0x100 when the direct-address table is gap-free and unique, i.e. the count pass runs by range test. */
+ * 2 = grouped (duplicate keys), 3 = radix-partitioned (beyond L2 reach); + 0x100 when the direct-address table is gap-free and unique, i.e. the count pass runs by range test. */
 int32_t hjTableLayout(const void* dTable, void* stream);
 /* Which probe path the last hjCount on this scratch took: 0 = match cache, 1 = hit lists (diagnostic; one 8-byte readback). */
 int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream);

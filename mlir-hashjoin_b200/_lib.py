@@ -59,6 +59,8 @@ _SIGNATURES = {
     "hjTableBytes": (_i64, [_i64, _i32]),
     "hjScratchBytes": (_i64, [_i64, _i32]),
     "hjBuild": (_i32, [_vp, _i64, _i32, _vp, _u32, _vp, _i64, _vp]),
+    "hjBuildEx": (_i32, [_vp, _i64, _i32, _vp, _u32, _vp, _i64, _u32, _vp]),
+    "hjDefaultPolicy": (_u32, []),
     "hjCountAsync": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     "hjCountResult": (_i64, [_vp, _i64, _i32, _vp]),
     "hjCount": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),

@@ -33,11 +33,26 @@ def _stale(target: Path, sources) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into lib/libhashjoin_b200.so for sm_100a. Returns the path."""
-    srcs = [CSRC / "hj_kernels.cu", CSRC / "hj_capi.cu"]
+    srcs = sorted(CSRC.glob("hj_*.cu"))
     deps = srcs + [CSRC / "hj_common.cuh", CSRC / "hj_kernels.cuh", PKG.parent / "include" / "hashjoin_b200.h"]
     LIB.parent.mkdir(parents=True, exist_ok=True)
     if force or _stale(LIB, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, srcs)]
+        # one nvcc per translation unit, side by side (objects under lib/obj, git-ignored), then one link
+        obj_dir = LIB.parent / "obj"
+        obj_dir.mkdir(exist_ok=True)
+        jobs = []
+        for src in srcs:
+            obj = obj_dir / (src.stem + ".o")
+            cmd = [_nvcc(), *NVCC_FLAGS, "-c", "-o", str(obj), str(src)]
+            if verbose:
+                print(" ".join(cmd))
+            jobs.append((subprocess.Popen(cmd), cmd, obj))
+        objs = []
+        for proc, cmd, obj in jobs:
+            if proc.wait() != 0:
+                raise subprocess.CalledProcessError(proc.returncode, cmd)
+            objs.append(str(obj))
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *objs]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -31,24 +31,10 @@ int32_t cuda_fail(const char* where, cudaError_t e) { return fail(HJ_ERR_CUDA, w
 inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline bool key_ok(int32_t kb) { return kb == 4 || kb == 8; }
 
-// pinned 8-byte landing zone for the result-size readback
-unsigned long long* pinned_total() {
-  static unsigned long long* p = nullptr;
-  if (!p && cudaMallocHost(&p, 64) != cudaSuccess) p = nullptr;
-  return p;
-}
-
 // ---- legacy surface state: B200 tables cached per caller-visible head pointer -----------------------------
 struct LegacyTable { void* table = nullptr; int64_t table_bytes = 0; void* scratch = nullptr; int64_t scratch_bytes = 0; bool built = false; };
 std::mutex g_mu;
 std::map<const void*, LegacyTable> g_tables;
-
-// ---- host-side notes about device workspaces: which tables may be beyond L2 reach (set by hjBuild, read by hjCount) and
-// which scratches hold a slice-ordered copy of the probe relation (set by hjCount, read by hjWrite)
-std::mutex g_note_mu;
-struct TableNote { bool big; bool range; };
-std::map<const void*, TableNote> g_table_big;
-std::map<const void*, int> g_scratch_reordered;
 
 // ---- hjJoinHost cache -------------------------------------------------------------------------------------
 struct DevBuf {
@@ -164,26 +150,38 @@ int32_t check(int32_t*, int32_t* rAligned, int64_t rOff, int64_t rSize, int64_t,
 int64_t hjTableBytes(int64_t nR, int32_t keyBytes) { return (nR < 0 || !key_ok(keyBytes)) ? HJ_ERR_ARG : hj::table_bytes(nR, keyBytes); }
 int64_t hjScratchBytes(int64_t nS, int32_t keyBytes) { return (nS < 0 || !key_ok(keyBytes)) ? HJ_ERR_ARG : hj::scratch_bytes(nS, keyBytes); }
 
-int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase, void* dTable, int64_t tableBytes, void* stream) {
-  if (!key_ok(keyBytes) || nR < 0 || (nR > 0 && !dR) || !dTable) return fail(HJ_ERR_ARG, "hjBuild", "null pointer or bad key width");
-  if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, "hjBuild", "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
-  if (reinterpret_cast<uintptr_t>(dTable) & 15) return fail(HJ_ERR_ARG, "hjBuild", "table workspace must be 16-byte aligned");
-  if (tableBytes < hj::table_bytes(nR, keyBytes)) return fail(HJ_ERR_ARG, "hjBuild", "table workspace too small (see hjTableBytes)");
-  { std::lock_guard<std::mutex> lk(g_note_mu); g_table_big[dTable] = TableNote{hj::table_is_big(nR, keyBytes), hj::allow_dense() == 2}; }
-  HJ_CUDA("hjBuild", hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, S_(stream)));
+static int32_t build_checked(const char* who, const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase, void* dTable, int64_t tableBytes,
+                             uint32_t policy, void* stream) {
+  if (!key_ok(keyBytes) || nR < 0 || (nR > 0 && !dR) || !dTable) return fail(HJ_ERR_ARG, who, "null pointer or bad key width");
+  if (nR > 0xFFFFFFFELL) return fail(HJ_ERR_ARG, who, "more than 2^32-2 build rows (row ids are 32-bit, join_v1.mlir:604)");
+  if (!dPayload && (uint64_t)rowBase + (uint64_t)nR > 0xFFFFFFFFULL) return fail(HJ_ERR_ARG, who, "rowBase + nR reaches 0xFFFFFFFF, the EMPTY row id");
+  // buckets are read with 32-byte vector loads and paired into 64-byte DRAM atoms: the workspace must be aligned to that
+  if (reinterpret_cast<uintptr_t>(dTable) & 63) return fail(HJ_ERR_ARG, who, "table workspace must be 64-byte aligned");
+  if (tableBytes < hj::table_bytes(nR, keyBytes)) return fail(HJ_ERR_ARG, who, "table workspace too small (see hjTableBytes)");
+  HJ_CUDA(who, hj::build_table(dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, policy, S_(stream)));
   return HJ_OK;
 }
+int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase, void* dTable, int64_t tableBytes, void* stream) {
+  return build_checked("hjBuild", dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, hj::default_policy(), stream);
+}
+int32_t hjBuildEx(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase, void* dTable, int64_t tableBytes, uint32_t policy, void* stream) {
+  if (policy == HJ_POLICY_DEFAULT) policy = hj::default_policy();
+  else if ((policy & 3u) == 3u || ((policy >> 3) & 3u) == 3u || (policy >> 7)) return fail(HJ_ERR_ARG, "hjBuildEx", "unknown policy bits");
+  return build_checked("hjBuildEx", dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, policy, stream);
+}
+uint32_t hjDefaultPolicy(void) { return hj::default_policy(); }
 
 static int32_t count_async(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
                            bool carryRows, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjCount", "null pointer or bad key width");
   if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjCount", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
-  if (reinterpret_cast<uintptr_t>(dScratch) & 15) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 16-byte aligned");
+  if (carryRows && !dProbePayload && (uint64_t)probeRowBase + (uint64_t)nS > 0x100000000ULL) return fail(HJ_ERR_ARG, "hjCount", "probeRowBase + nS exceeds 2^32");
+  if (reinterpret_cast<uintptr_t>(dTable) & 63) return fail(HJ_ERR_ARG, "hjCount", "table workspace must be 64-byte aligned");
+  if (reinterpret_cast<uintptr_t>(dScratch) & 255) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 256-byte aligned");
   if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
-  bool big = true, range = true; int reordered = 0;        // unknown table (not built through this process): look at its header, queue every kernel
-  { std::lock_guard<std::mutex> lk(g_note_mu); auto it = g_table_big.find(dTable); if (it != g_table_big.end()) { big = it->second.big; range = it->second.range; } }
-  HJ_CUDA("hjCount", hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, big, range, &reordered, carryRows, dProbePayload, probeRowBase, S_(stream)));
-  { std::lock_guard<std::mutex> lk(g_note_mu); g_scratch_reordered[dScratch] = reordered; }
+  cudaError_t e = hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, carryRows, dProbePayload, probeRowBase, S_(stream));
+  if (e == cudaErrorInvalidValue) return fail(HJ_ERR_STATE, "hjCount", "the table workspace holds no table built for this key width (call hjBuild first)");
+  if (e != cudaSuccess) return cuda_fail("hjCount", e);
   return HJ_OK;
 }
 
@@ -203,12 +201,10 @@ int64_t hjCountRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dT
 
 int64_t hjCountResult(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream) {
   if (!dScratch || !key_ok(keyBytes) || nS < 0) return fail(HJ_ERR_ARG, "hjCountResult", "bad argument");
-  unsigned long long* host = pinned_total();
-  if (!host) return fail(HJ_ERR_CUDA, "hjCountResult", "cudaMallocHost failed");
   hj::ScratchView sv = hj::scratch_view(const_cast<void*>(dScratch), nS, keyBytes);
-  HJ_CUDA("hjCountResult", cudaMemcpyAsync(host, sv.chunk_offsets + sv.nchunks, 8, cudaMemcpyDeviceToHost, S_(stream)));
-  HJ_CUDA("hjCountResult", cudaStreamSynchronize(S_(stream)));
-  return (int64_t)*host;
+  unsigned long long total = 0;
+  HJ_CUDA("hjCountResult", hj::readback(&total, sv.counters + hj::CTR_TOTAL, 8, S_(stream)));
+  return (int64_t)total;
 }
 
 int32_t hjTableLayout(const void* dTable, void* stream) {
@@ -220,12 +216,10 @@ int32_t hjTableLayout(const void* dTable, void* stream) {
 
 int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream) {
   if (!dScratch || !key_ok(keyBytes) || nS < 0) return fail(HJ_ERR_ARG, "hjProbePath", "bad argument");
-  unsigned long long* host = pinned_total();
-  if (!host) return fail(HJ_ERR_CUDA, "hjProbePath", "cudaMallocHost failed");
   hj::ScratchView sv = hj::scratch_view(const_cast<void*>(dScratch), nS, keyBytes);
-  HJ_CUDA("hjProbePath", cudaMemcpyAsync(host + 1, sv.counters + 3, 8, cudaMemcpyDeviceToHost, S_(stream)));
-  HJ_CUDA("hjProbePath", cudaStreamSynchronize(S_(stream)));
-  return host[1] ? 1 : 0;
+  unsigned long long flag = 0;
+  HJ_CUDA("hjProbePath", hj::readback(&flag, sv.counters + hj::CTR_SPARSE, 8, S_(stream)));
+  return flag ? 1 : 0;
 }
 
 int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes, void* stream) {
@@ -237,11 +231,10 @@ int64_t hjCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
 int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch,
                 int32_t* dOutR, int32_t* dOutS, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjWrite", "null pointer or bad key width");
-  int reordered = 0; bool range = true;
-  { std::lock_guard<std::mutex> lk(g_note_mu);
-    auto it = g_scratch_reordered.find(dScratch); if (it != g_scratch_reordered.end()) reordered = it->second;
-    auto tn = g_table_big.find(dTable); if (tn != g_table_big.end()) range = tn->second.range; }
-  HJ_CUDA("hjWrite", hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, reordered, range, S_(stream)));
+  if ((reinterpret_cast<uintptr_t>(dTable) & 63) || (reinterpret_cast<uintptr_t>(dScratch) & 255)) return fail(HJ_ERR_ARG, "hjWrite", "misaligned table or scratch workspace");
+  cudaError_t e = hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, S_(stream));
+  if (e == cudaErrorInvalidValue) return fail(HJ_ERR_STATE, "hjWrite", "the table workspace holds no table built for this key width");
+  if (e != cudaSuccess) return cuda_fail("hjWrite", e);
   return HJ_OK;
 }
 
@@ -253,11 +246,12 @@ int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dT
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch || capacity < 0 || (capacity > 0 && (!dOutR || !dOutS)))
     return fail(HJ_ERR_ARG, "hjJoinFused", "null pointer or bad key width");
   if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjJoinFused", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
-  if ((reinterpret_cast<uintptr_t>(dScratch) & 15) || scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjJoinFused", "scratch workspace misaligned or too small (see hjScratchBytes)");
+  if ((reinterpret_cast<uintptr_t>(dScratch) & 255) || (reinterpret_cast<uintptr_t>(dTable) & 63) || scratchBytes < hj::scratch_bytes(nS, keyBytes))
+    return fail(HJ_ERR_ARG, "hjJoinFused", "workspace misaligned or scratch too small (see hjScratchBytes)");
   HJ_CUDA("hjJoinFused", hj::join_fused_async(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, capacity, dProbePayload, probeRowBase, S_(stream)));
   uint32_t mode = 0;
   HJ_CUDA("hjJoinFused", hj::read_table_mode(dTable, &mode, nullptr, S_(stream)));
-  if (mode == 2) return fail(HJ_ERR_STATE, "hjJoinFused", "build keys are not unique (grouped table): use hjCount + hjWrite");
+  if (mode >= 2) return fail(HJ_ERR_STATE, "hjJoinFused", "grouped (duplicate build keys) or radix (beyond L2 reach) table: use hjCount + hjWrite");
   return hjCountResult(dScratch, nS, keyBytes, stream);
 }
 
@@ -268,13 +262,13 @@ int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, 
   if (!key_ok(keyBytes) || n < 0 || (n > 0 && (!dKeys || !dOutKeys || !dOutRows)) || !dOffsets || !dWorkspace)
     return fail(HJ_ERR_ARG, "hjPartition", "null pointer or bad key width");
   HJ_CUDA("hjPartition", hj::radix_partition(dKeys, dRows, rowBase, n, keyBytes, nParts, dOutKeys, dOutRows,
-                                             reinterpret_cast<unsigned long long*>(dOffsets), dWorkspace, workspaceBytes, 0, S_(stream)));
+                                             reinterpret_cast<unsigned long long*>(dOffsets), dWorkspace, workspaceBytes, S_(stream)));
   return HJ_OK;
 }
 
 int32_t hjPartitionCount(const void* dKeys, int64_t n, int32_t keyBytes, int32_t nParts, uint64_t* dCounts, void* dWorkspace, int64_t workspaceBytes, void* stream) {
   if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dKeys) || !dCounts || !dWorkspace) return fail(HJ_ERR_ARG, "hjPartitionCount", "null pointer or bad key width");
-  HJ_CUDA("hjPartitionCount", hj::partition_count(dKeys, n, keyBytes, nParts, reinterpret_cast<unsigned long long*>(dCounts), dWorkspace, workspaceBytes, 0, S_(stream)));
+  HJ_CUDA("hjPartitionCount", hj::partition_count(dKeys, n, keyBytes, nParts, reinterpret_cast<unsigned long long*>(dCounts), dWorkspace, workspaceBytes, S_(stream)));
   return HJ_OK;
 }
 
@@ -289,11 +283,12 @@ int32_t hjPartitionPush(const void* dKeys, const uint32_t* dRows, uint32_t rowBa
 
 int32_t hjPairDigest(const int32_t* dOutR, const int32_t* dOutS, int64_t n, uint64_t* hostOut2, void* stream) {
   if (!hostOut2 || n < 0 || (n > 0 && (!dOutR || !dOutS))) return fail(HJ_ERR_ARG, "hjPairDigest", "bad argument");
-  static unsigned long long* d = nullptr;
-  if (!d) HJ_CUDA("hjPairDigest", cudaMalloc(&d, 16));
-  HJ_CUDA("hjPairDigest", hj::pair_digest(dOutR, dOutS, n, d, S_(stream)));
-  HJ_CUDA("hjPairDigest", cudaMemcpyAsync(hostOut2, d, 16, cudaMemcpyDeviceToHost, S_(stream)));
-  HJ_CUDA("hjPairDigest", cudaStreamSynchronize(S_(stream)));
+  unsigned long long* d = nullptr;                                 // per call (stream-ordered): no buffer shared between threads or devices
+  HJ_CUDA("hjPairDigest", cudaMallocAsync(&d, 16, S_(stream)));
+  cudaError_t e = hj::pair_digest(dOutR, dOutS, n, d, S_(stream));
+  if (e == cudaSuccess) e = hj::readback(hostOut2, d, 16, S_(stream));
+  cudaFreeAsync(d, S_(stream));
+  if (e != cudaSuccess) return cuda_fail("hjPairDigest", e);
   return HJ_OK;
 }
 
@@ -312,6 +307,7 @@ int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64
 // Pairs are appended chunk by chunk (probe_row = chunk base + local row), which is a valid order for a multiset result.
 int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes, int32_t* hOutR, int32_t* hOutS, int64_t capacity) {
   if (!key_ok(keyBytes) || nR < 0 || nS < 0 || (nR > 0 && !hR) || (nS > 0 && !hS)) return fail(HJ_ERR_ARG, "hjJoinHost", "bad argument");
+  if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjJoinHost", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
   std::lock_guard<std::mutex> lk(g_mu);
   const int64_t chunk_rows = (int64_t)1 << 24;                        // multiple of the kernel chunk (16 384 / 8 192 rows)
   const int64_t nch = (nS + chunk_rows - 1) / chunk_rows;
@@ -426,8 +422,7 @@ int32_t hashJoinWriteI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEM
 // =========================================================================================================
 // B. the reference's join entry points (join_v1.mlir:43-176), expanded ABI.
 // The caller's chained-table arrays (head / lkey / lrow / lnext, join_v1.mlir:25-39) are only a HANDLE here: the
-// B200 table lives in a workspace this library owns, keyed by the head pointer.  The caller's prefixSumArray
-// (8 bytes per probe row, join_v1.mlir:588) is big enough for the match cache and is used as scratch when it is.
+// B200 table and its probe-side scratch live in workspaces this library owns, keyed by the head pointer.
 // Timer prints are kept where the reference's wrappers have them (join_v1.mlir:65,72,97,105,128,137,164,174).
 // =========================================================================================================
 int64_t calculateNumberOfBlocks(int64_t totalThreads, int64_t threadsPerBlock) {             // join_v1.mlir:43-52
@@ -482,21 +477,18 @@ int64_t countRows(HJ_MEMREF(int32_t, S), int64_t nS, HJ_MEMREF(int32_t, head), H
   if (it == g_tables.end() || !it->second.built) return fail(HJ_ERR_STATE, "countRows", "hash table was never built (call buildTable first)");
   LegacyTable& t = it->second;
   const int64_t need = hj::scratch_bytes(nS, 4);
-  void* scratch = nullptr; int64_t sbytes = 0;
-  int64_t* pfx = mr_ptr(prefixAligned, prefixOff);
-  if (pfx && mr_ok(prefixSize, prefixStride) && prefixSize * 8 >= need && (reinterpret_cast<uintptr_t>(pfx) & 15) == 0) { scratch = pfx; sbytes = prefixSize * 8; }
-  else {
-    if (t.scratch_bytes < need) {
-      if (t.scratch) cudaFree(t.scratch);
-      t.scratch = nullptr; t.scratch_bytes = 0;
-      cudaError_t e = cudaMalloc(&t.scratch, (size_t)need);
-      if (e != cudaSuccess) return cuda_fail("countRows", e);
-      t.scratch_bytes = need;
-    }
-    scratch = t.scratch; sbytes = t.scratch_bytes;
+  // the caller's prefixSumArray (8 bytes per probe row, join_v1.mlir:588) is never large enough for the probe-side scratch (match cache,
+  // offsets, radix area): the library keeps its own, cached with the table
+  (void)prefixAligned; (void)prefixOff; (void)prefixSize; (void)prefixStride;
+  if (t.scratch_bytes < need) {
+    if (t.scratch) cudaFree(t.scratch);
+    t.scratch = nullptr; t.scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&t.scratch, (size_t)need);
+    if (e != cudaSuccess) return cuda_fail("countRows", e);
+    t.scratch_bytes = need;
   }
   startTimer();
-  int64_t total = hjCount(mr_ptr(SAligned, SOff), nS, 4, t.table, scratch, sbytes, nullptr);
+  int64_t total = hjCount(mr_ptr(SAligned, SOff), nS, 4, t.table, t.scratch, t.scratch_bytes, nullptr);
   endTimer();
   return total;
 }
@@ -511,10 +503,9 @@ void probeRelation(HJ_MEMREF(int32_t, S), int64_t nS, int32_t hashTableSize, HJ_
   auto it = g_tables.find(mr_ptr(headAligned, headOff));
   if (it == g_tables.end() || !it->second.built) { fail(HJ_ERR_STATE, "probeRelation", "hash table was never built"); return; }
   LegacyTable& t = it->second;
-  const int64_t need = hj::scratch_bytes(nS, 4);
-  int64_t* pfx = mr_ptr(prefixAligned, prefixOff);
-  const void* scratch = (pfx && mr_ok(prefixSize, prefixStride) && prefixSize * 8 >= need && (reinterpret_cast<uintptr_t>(pfx) & 15) == 0) ? (const void*)pfx : (const void*)t.scratch;
-  if (!scratch) { fail(HJ_ERR_STATE, "probeRelation", "countRows was not called on this table"); return; }
+  (void)prefixAligned; (void)prefixOff; (void)prefixSize; (void)prefixStride;
+  const void* scratch = t.scratch;
+  if (!scratch || t.scratch_bytes < hj::scratch_bytes(nS, 4)) { fail(HJ_ERR_STATE, "probeRelation", "countRows was not called on this table"); return; }
   startTimer();
   int32_t rc = hjWrite(mr_ptr(SAligned, SOff), nS, 4, t.table, scratch, mr_ptr(outRAligned, outROff), mr_ptr(outSAligned, outSOff), nullptr, 0, nullptr);
   if (rc == HJ_OK) { cudaError_t e = cudaStreamSynchronize(nullptr); if (e != cudaSuccess) cuda_fail("probeRelation", e); }
@@ -525,7 +516,6 @@ void hashJoinRelease(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_tables) { if (kv.second.table) cudaFree(kv.second.table); if (kv.second.scratch) cudaFree(kv.second.scratch); }
   g_tables.clear();
-  { std::lock_guard<std::mutex> lk2(g_note_mu); g_table_big.clear(); g_scratch_reordered.clear(); }
   g_hR.release(); g_hS.release(); g_hT.release(); g_hSc.release(); g_hOr.release(); g_hOs.release();
 }
 

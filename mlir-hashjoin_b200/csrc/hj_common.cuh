@@ -18,7 +18,9 @@ namespace hj {
 
 constexpr uint32_t ROW_NONE = 0xFFFFFFFFu;     // never a valid row id: EMPTY marker lives in the row half of a slot
 constexpr uint32_t HJ_MAGIC = 0x424A4833u;
-constexpr uint32_t MODE_HASH = 0, MODE_DENSE = 1, MODE_GROUP = 2;
+constexpr uint32_t MODE_HASH = 0, MODE_DENSE = 1, MODE_GROUP = 2, MODE_RADIX = 3;
+// probe path the last count on a scratch took (scratch counters[CTR_PATH]); the write pass launches exactly that path's kernel
+constexpr uint32_t PATH_CACHE = 0, PATH_LISTS = 1, PATH_RANGE = 2, PATH_RADIX = 3;
 
 // Device-resident table header (first HEADER_BYTES of the table workspace). Written by the build kernels, read
 // (uniformly) by count/write, so no host round trip is needed to pick the layout.
@@ -38,7 +40,11 @@ struct TableHeader {
   unsigned long long rows_offset; // grouped layout: byte offset of the u32 row-id array inside the body
   unsigned long long group_cursor;// grouped layout: bump allocator over the row-id array
   unsigned long long n_groups;    // grouped layout: distinct build keys
-  unsigned long long work[4];     // ticket counters of the slice-ordered build kernels (hash, group count, group fill)
+  unsigned long long work[4];     // ticket counters of the bounded-grid build kernels (hash, group count, group fill)
+  uint32_t policy;                // hjBuildEx flags in force for this table (HJ_POLICY_*): the probe passes follow the TABLE, not a process global
+  uint32_t rj_bits1, rj_bits2;    // radix layout: 2^(bits1 + bits2) partitions of the build relation, partition id = top bits of radix_hash(key)
+  uint32_t pad0;
+  unsigned long long rj_keys_off, rj_rows_off, rj_offs_off;   // radix layout: byte offsets (inside the body) of the partitioned keys, row ids, u32 offsets[parts + 1]
 };
 static_assert(sizeof(TableHeader) <= HEADER_BYTES, "header too large");
 
@@ -53,6 +59,11 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {          // spl
 }
 
 template <typename K> struct KeyTraits;
+
+// 32-bit hash of the radix join: the TOP bits pick the partition (two passes of <= 8 bits), the LOW bits the slot of the shared-memory table
+template <typename K> __host__ __device__ __forceinline__ uint32_t radix_hash(K key);
+template <> __host__ __device__ __forceinline__ uint32_t radix_hash<int32_t>(int32_t key) { return mix32((uint32_t)key + 0x68E31DA4u); }
+template <> __host__ __device__ __forceinline__ uint32_t radix_hash<int64_t>(int64_t key) { const uint64_t h = mix64((uint64_t)key + 0x2545F4914F6CDD1DULL); return (uint32_t)(h >> 32) ^ (uint32_t)h; }
 
 template <> struct KeyTraits<int32_t> {
   static constexpr int SLOTS = 4;             // slots per 32-byte bucket
@@ -110,6 +121,18 @@ __device__ __forceinline__ uint32_t ld_keep_u32(const uint32_t* p, uint64_t pol)
   uint32_t r;
   asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
+}
+
+// scalar streaming loads (coalesced per warp at any alignment: the partition kernels read segments that start anywhere)
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p, uint64_t pol);
+template <> __device__ __forceinline__ int32_t ld_stream<int32_t>(const int32_t* p, uint64_t pol) {
+  int32_t r; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol)); return r;
+}
+template <> __device__ __forceinline__ uint32_t ld_stream<uint32_t>(const uint32_t* p, uint64_t pol) {
+  uint32_t r; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol)); return r;
+}
+template <> __device__ __forceinline__ int64_t ld_stream<int64_t>(const int64_t* p, uint64_t pol) {
+  long long r; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol)); return (int64_t)r;
 }
 
 // One 32-byte bucket as four 64-bit words (SASS: LDG.E.ELL2.256).

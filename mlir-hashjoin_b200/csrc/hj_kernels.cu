@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "hj_common.cuh"
 #include "hj_kernels.cuh"
@@ -39,31 +40,29 @@ static int64_t table_part_bytes(int64_t n_rows, int key_bytes) {
   const int64_t group_bytes = round_up(n_rows * 4, 64) + ((5 * n_rows / 4 + 3) / 4 + 4) * 64;
   return round_up(std::max(inline_bytes, group_bytes), 256);
 }
-// Tables beyond L2 reach (tools/membench: random lookups stop hitting L2 past ~64 MB) are built and probed in
-// table-slice order: the relation is first radix-partitioned (K5) on the SAME hash bits that pick the bucket pair, so
-// consecutive CTAs touch one slice of the table at a time and the slice stays L2-resident.
+// Tables beyond L2 reach (tools/membench: random lookups stop hitting L2 past ~64 MB of table) are not hash tables in global memory at
+// all: both relations are radix-partitioned (K5, two passes) until a build partition fits a shared-memory table, and joined partition
+// by partition (K7, hj_radix.cu). The workspace still holds room for the bucketised layouts (policy bit HJ_POLICY_RADIX off).
 constexpr int64_t LOCALITY_MIN_BYTES = (int64_t)48 << 20;
-constexpr int64_t LOCALITY_SLICE_BYTES = (int64_t)8 << 20;
 bool table_is_big(int64_t n_rows, int key_bytes) { return preferred_pairs(n_rows, key_bytes) * 64 > LOCALITY_MIN_BYTES; }
-int locality_parts(int64_t table_body_bytes) {
-  const int64_t f = (table_body_bytes + LOCALITY_SLICE_BYTES - 1) / LOCALITY_SLICE_BYTES;
-  return (int)std::min<int64_t>(PART_MAX, std::max<int64_t>(2, f));
-}
-static int64_t reorder_bytes(int64_t n, int key_bytes) { return round_up(n * key_bytes, 256) + round_up(n * 4, 256) + partition_workspace_bytes(n, PART_MAX) + (PART_MAX + 1) * 8 + 256; }
 int64_t table_bytes(int64_t n_rows, int key_bytes) {
-  return HEADER_BYTES + table_part_bytes(n_rows, key_bytes) + (table_is_big(n_rows, key_bytes) ? reorder_bytes(n_rows, key_bytes) : 0);
+  int64_t body = table_part_bytes(n_rows, key_bytes);
+  if (table_is_big(n_rows, key_bytes)) body = std::max(body, round_up(radix_table_bytes(n_rows, key_bytes), 256));
+  return HEADER_BYTES + body;
 }
 int64_t num_chunks(int64_t n_probe, int key_bytes) {
   const int64_t c = chunk_keys(key_bytes);
   return (n_probe + c - 1) / c;
 }
-constexpr int SCRATCH_COUNTERS = 8, SCRATCH_SCAN_BLOCKS = 264;     // counters, then one total per 16 384 chunks for the two-level scan
+constexpr int SCRATCH_SCAN_BLOCKS = 264;     // one total per 16 384 entries for the two-level scan
+// entries of the offsets array: one per chunk (bucketised / direct-address layouts) or one per work item (radix layout), whichever is more
+static int64_t scratch_offsets_len(int64_t n_probe, int key_bytes) { return std::max(num_chunks(n_probe, key_bytes), radix_max_items(n_probe)); }
 static int64_t scratch_core_bytes(int64_t n_probe, int key_bytes) {
   const int64_t nc = num_chunks(n_probe, key_bytes);
-  return 2 * round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((nc + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256) + round_up(nc * (BLOCK_THREADS / 32) * 4, 256);
+  return 2 * round_up(nc * chunk_keys(key_bytes) * 4, 256) + round_up((scratch_offsets_len(n_probe, key_bytes) + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256) + round_up(nc * (BLOCK_THREADS / 32) * 4, 256);
 }
-// match cache + hit positions + chunk offsets + room to reorder the probe relation (keys and original indices) for big tables
-int64_t scratch_bytes(int64_t n_probe, int key_bytes) { return scratch_core_bytes(n_probe, key_bytes) + reorder_bytes(n_probe, key_bytes) + 256; }
+// match cache + hit positions + offsets + counters + the radix layout's partitioned copy of the probe relation
+int64_t scratch_bytes(int64_t n_probe, int key_bytes) { return scratch_core_bytes(n_probe, key_bytes) + radix_scratch_bytes(n_probe, key_bytes) + 256; }
 ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   ScratchView v;
   char* base = reinterpret_cast<char*>(scratch);
@@ -73,21 +72,12 @@ ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
   v.hit_list = reinterpret_cast<uint2*>(base);                  // the same bytes as the match cache plus as much again behind it
   v.run_start = reinterpret_cast<uint32_t*>(base + cache_bytes); // grouped layout: first row-id slot of each probe row's run (second half)
   v.chunk_offsets = reinterpret_cast<unsigned long long*>(base + 2 * cache_bytes);
-  v.counters = v.chunk_offsets + v.nchunks + 1;                 // [0] count<inline>, [1] count<grouped>, [2] write<grouped> tickets, [3] hit-list flag, [4] count_sparse ticket
-  v.warp_counts = reinterpret_cast<uint32_t*>(base + 2 * cache_bytes + round_up((v.nchunks + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256));
-  v.reorder = base + scratch_core_bytes(n_probe, key_bytes);
+  const int64_t noff = scratch_offsets_len(n_probe, key_bytes);
+  v.counters = v.chunk_offsets + noff + 1;                      // CTR_* below
+  v.scan_sums = v.counters + SCRATCH_COUNTERS;
+  v.warp_counts = reinterpret_cast<uint32_t*>(base + 2 * cache_bytes + round_up((noff + 1 + SCRATCH_COUNTERS + SCRATCH_SCAN_BLOCKS) * 8, 256));
+  v.radix = base + scratch_core_bytes(n_probe, key_bytes);
   return v;
-}
-// reorder area: [keys][row ids or original indices u32][offsets u64 x (PART_MAX + 1)][partition workspace]
-struct ReorderView { void* keys; uint32_t* idx; unsigned long long* offsets; void* ws; int64_t ws_bytes; };
-static ReorderView reorder_view(char* area, int64_t n, int key_bytes) {
-  ReorderView r;
-  r.keys = area;
-  r.idx = reinterpret_cast<uint32_t*>(area + round_up(n * key_bytes, 256));
-  r.offsets = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(r.idx) + round_up(n * 4, 256));
-  r.ws = reinterpret_cast<char*>(r.offsets) + (PART_MAX + 1) * 8 + 56;
-  r.ws_bytes = partition_workspace_bytes(n, PART_MAX);
-  return r;
 }
 
 // =========================================================================================================
@@ -97,7 +87,8 @@ static ReorderView reorder_view(char* area, int64_t n, int key_bytes) {
 // =========================================================================================================
 constexpr int DENSE_MAX_FACTOR = 4;     // direct addressing when (kmax - kmin + 1) <= 4 x build rows and it fits
 
-__global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned long long n_rows, unsigned long long body_bytes, unsigned long long pairs) {
+__global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned long long n_rows, unsigned long long body_bytes, unsigned long long pairs, uint32_t policy) {
+  hdr->policy = policy; hdr->rj_bits1 = hdr->rj_bits2 = 0; hdr->rj_keys_off = hdr->rj_rows_off = hdr->rj_offs_off = 0;
   hdr->magic = HJ_MAGIC; hdr->key_bytes = key_bytes; hdr->mode = MODE_HASH; hdr->has_dups = 0; hdr->need_fallback = 0; hdr->all_present = 0;
   hdr->n_pairs = pairs; hdr->n_rows = n_rows; hdr->kmin = 0x7FFFFFFFFFFFFFFFLL; hdr->kmax = -0x7FFFFFFFFFFFFFFFLL - 1;
   hdr->dense_range = 0; hdr->body_bytes = body_bytes; hdr->pairs_cap = body_bytes / 64;
@@ -128,7 +119,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_minmax(const K* __restrict__ 
 
 __global__ void k_decide(TableHeader* hdr, int allow_dense) {
   const unsigned long long n = hdr->n_rows;
-  if (n == 0 || !allow_dense) return;
+  if (n == 0 || !allow_dense || hdr->has_dups) return;             // duplicates proven by the sample: the direct-address build would only be aborted
   const unsigned long long range = (unsigned long long)hdr->kmax - (unsigned long long)hdr->kmin + 1ULL;   // wraps to 0 on the full 64-bit span
   if (range != 0 && range <= DENSE_MAX_FACTOR * n && range * 4 <= hdr->body_bytes && range <= 0xFFFFFFFFULL) {
     hdr->mode = MODE_DENSE; hdr->dense_range = range;
@@ -163,7 +154,6 @@ template <typename K>
 __global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restrict__ R, int64_t nR, TableHeader* hdr) {
   __shared__ long long keys_sm[DUPS_SAMPLES];
   __shared__ unsigned short slots[DUPS_SLOTS];                   // sample id + 1, 0 = empty
-  if (hdr->mode != MODE_HASH) return;
   const uint32_t first = blockIdx.x * DUPS_SAMPLES;               // this CTA's samples: global ids [first, first + DUPS_SAMPLES)
   for (int s = threadIdx.x; s < DUPS_SLOTS; s += DUPS_THREADS) slots[s] = 0;
   for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) keys_sm[i] = (long long)R[sample_pos(first + i, (uint64_t)nR)];
@@ -243,9 +233,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_dense(const K* __restri
 // Insert into the bucketised table: read the bucket once, CAS the first slot seen EMPTY; a failed CAS returns the
 // occupant, which is final, so every earlier slot of the probe sequence has been compared with `key` by the time the
 // insert lands -> duplicate detection is exact (the later of two equal keys always sees the earlier one).
-// Insert into the bucketised table: read the bucket once, CAS the first slot seen EMPTY; a failed CAS returns the
-// occupant, which is final, so every earlier slot of the probe sequence has been compared with `key` by the time the
-// insert lands -> duplicate detection is exact (the later of two equal keys always sees the earlier one).
 // Measured alternatives on 2^28 i64 rows (build phase 15.0 ms): claiming slot 0 BLIND with CAS.128, four claims in flight per
 // thread and 8 keys per ticket: 17.8 ms (1.4 CAS per key instead of 1.03); loading the home buckets of a vector up front (48
 // registers instead of 32): k_build_hash 8.4 -> 9.4 ms. tools/membench4 (profiles/r1_membench4_insert_cost.jsonl): an L2-resident
@@ -269,7 +256,7 @@ __device__ __forceinline__ bool insert_one(char* body, uint64_t n_pairs, K key, 
 }
 
 template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ perm,
+__global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restrict__ R, int64_t nR,
                                                               const uint32_t* __restrict__ payload, uint32_t row_base, char* body, TableHeader* hdr) {
   if (hdr->mode != MODE_HASH || hdr->has_dups) return;             // has_dups before the first insert: k_sample_dups found duplicates
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
@@ -287,8 +274,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_build_hash(const K* __restric
     #pragma unroll
     for (int e = 0; e < KPV; e++) {
       if (i0 + e < nR) {
-        const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);        // R may be a slice-ordered copy: perm = original index
-        const uint32_t row = payload ? payload[idx] : row_base + idx;
+        const uint32_t row = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
         dup |= insert_one<K>(body, n_pairs, key[e], row, &hdr->has_dups);
       }
     }
@@ -387,7 +373,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_offsets(char* body, Tab
 }
 
 template <typename K, bool VEC>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restrict__ R, int64_t nR, const uint32_t* __restrict__ perm,
+__global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restrict__ R, int64_t nR,
                                                               const uint32_t* __restrict__ payload, uint32_t row_base, char* body, TableHeader* hdr) {
   if (hdr->mode != MODE_GROUP) return;
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
@@ -407,8 +393,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_group_fill(const K* __restric
       if (i0 + e < nR) {
         unsigned long long* pay = group_slot(body, n_pairs, (long long)key[e], false);
         const unsigned long long old = atomicAdd(pay, 1ULL);      // low half is the write cursor of this key's range
-        const uint32_t idx = perm ? perm[i0 + e] : (uint32_t)(i0 + e);
-        rows[(uint32_t)old] = payload ? payload[idx] : row_base + idx;
+        rows[(uint32_t)old] = payload ? payload[i0 + e] : row_base + (uint32_t)(i0 + e);
       }
     }
     blk = ticket_advance(&tq, it, pending);
@@ -435,40 +420,48 @@ static unsigned resident_grid(Kern kern, int64_t needed_blocks) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(needed_blocks, (int64_t)per_sm * num_sms()));
 }
 
+// ---- policy: process defaults (hjSet*), frozen into the table header by every build (hjBuildEx can state them per table) ----
 static int g_allow_dense = 2;   // 0 hash only, 1 direct-address layout with the match cache, 2 (default) + count by range for gap-free unique key ranges
-static int g_locality = 1;
+static int g_locality = 1;      // radix join for tables beyond L2 reach
+static int g_dup_sample = 1;    // look at a sample of the build keys for duplicates before trying the inline (unique-key) layout
+static int g_sparse = 1;        // hit lists for selective joins: 0 never, 1 sampled on the device, 2 always (unique layouts)
+static int g_tma_count = 0;     // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
+void set_dup_sample(int on) { g_dup_sample = on; }
+void set_sparse(int policy) { g_sparse = policy; }
+void set_tma_count(int on) { g_tma_count = on; }
+void set_allow_dense(int on) { g_allow_dense = on; }
+void set_locality(int on) { g_locality = on; }
+uint32_t default_policy() {
+  return (uint32_t)(g_allow_dense & 3) | (g_locality ? POLICY_RADIX : 0u) | ((uint32_t)(g_sparse & 3) << POLICY_SPARSE_SHIFT) | (g_dup_sample ? POLICY_DUP_SAMPLE : 0u) |
+         (g_tma_count ? POLICY_TMA_COUNT : 0u);
+}
 // Grid of the direct-address probe kernels: 0 = one chunk per CTA, k = at most k resident waves striding over the chunks.
 // Measured on config 2 (20 steps): count 1.231 / 1.248 / 1.233 / 1.231 ms and write 0.536 / 0.597 / 0.591 / 0.555 ms for k = 0 / 1 / 2 / 4.
-// The count kernel therefore runs two waves (when it is NOT the chosen kernel — selective joins take k_count_sparse — its launch
-// costs ~3 us instead of ~37 us at 2^30 probe rows) and the write kernel keeps one chunk per CTA.
 static int g_count_waves = 2, g_write_waves = 0;
 void set_dense_waves(int k) { g_count_waves = g_write_waves = k; }
 template <typename Kern>
 static unsigned dense_grid(Kern kern, int64_t nchunks, int waves) {
-  if (waves <= 0) return (unsigned)std::min<int64_t>(nchunks, 16384);      // one chunk per CTA up to config 2's size, striding beyond (idle-launch cost)
+  if (waves <= 0) return (unsigned)std::min<int64_t>(nchunks, 16384);      // one chunk per CTA up to config 2's size, striding beyond
   return (unsigned)std::min<int64_t>(nchunks, (int64_t)waves * resident_grid(kern, nchunks));
 }
-static int g_dup_sample = 1;   // look at a sample of the build keys for duplicates before trying the inline (unique-key) layout
-void set_dup_sample(int on) { g_dup_sample = on; }
-// k_count_range / k_write_range: one chunk per CTA up to 16 384 chunks (config 2 exactly), striding beyond: when they are NOT the
-// kernels chosen, a launch of 65 536 CTAs that exit at once costs 37 us (config 3), one of 16 384 costs 10 us.
 static unsigned range_grid(int64_t nchunks) { return (unsigned)std::min<int64_t>(nchunks, 16384); }
-static int g_sparse = 1;       // hit lists for selective joins: 0 never, 1 sampled on the device, 2 always (unique layouts)
-void set_sparse(int policy) { g_sparse = policy; }
-static int g_tma_count = 0;    // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
-void set_tma_count(int on) { g_tma_count = on; }
-void set_allow_dense(int on) { g_allow_dense = on; }
-void set_locality(int on) { g_locality = on; }
-constexpr int PART_SEL_OWNER = 0, PART_SEL_TABLE = 1, PART_SEL_GROUP = 2;
 
-static cudaError_t read_header(const void* table, TableHeader* out, cudaStream_t stream) {
-  static TableHeader* pinned = nullptr;
-  if (!pinned) { cudaError_t e = cudaMallocHost(&pinned, sizeof(TableHeader)); if (e != cudaSuccess) return e; }
-  cudaError_t e = cudaMemcpyAsync(pinned, table, sizeof(TableHeader), cudaMemcpyDeviceToHost, stream);
+// Small device -> host readbacks (table header, scratch counters, result size) land in a pinned block that belongs to the calling
+// THREAD: two host threads driving two streams never share a landing zone.
+static void* pinned_block() {
+  thread_local void* p = nullptr;
+  if (!p && cudaMallocHost(&p, 1024) != cudaSuccess) p = nullptr;
+  return p;
+}
+cudaError_t readback(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t stream) {
+  char* pin = reinterpret_cast<char*>(pinned_block());
+  if (!pin || bytes > 1024) return cudaErrorMemoryAllocation;
+  cudaError_t e = cudaMemcpyAsync(pin, dev_src, bytes, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  if (e == cudaSuccess) *out = *pinned;
+  if (e == cudaSuccess) memcpy(host_dst, pin, bytes);
   return e;
 }
+static cudaError_t read_header(const void* table, TableHeader* out, cudaStream_t stream) { return readback(out, table, sizeof(TableHeader), stream); }
 
 cudaError_t read_table_mode(const void* table, uint32_t* mode, uint32_t* all_present, cudaStream_t stream) {
   TableHeader h;
@@ -478,68 +471,60 @@ cudaError_t read_table_mode(const void* table, uint32_t* mode, uint32_t* all_pre
 }
 
 template <typename K>
-static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32_t row_base, char* body, TableHeader* hdr, int64_t pairs,
-                                bool big, char* reorder_area, cudaStream_t stream) {
+static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload, uint32_t row_base, char* body, int64_t body_bytes, TableHeader* hdr, int64_t pairs,
+                                bool big, uint32_t policy, cudaStream_t stream) {
   constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
   const int64_t threads = (nR + KPV - 1) / KPV;
   const unsigned grid = (unsigned)std::min<int64_t>(PERSIST_GRID, (threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
   if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
-  k_decide<<<1, 1, 0, stream>>>(hdr, g_allow_dense);
-  if (nR >= DUPS_MIN_ROWS && g_dup_sample) k_sample_dups<K><<<DUPS_CTAS, DUPS_THREADS, 0, stream>>>(R, nR, hdr);
-  // A table beyond L2 reach that did not get the direct-address layout is built in table-slice order: one host look at the
-  // header (the only sync in the build, and only for big tables), then K5 reorders (key, original index) by slice.
-  const K* Rb = R; const uint32_t* perm = nullptr;
-  if (big && nR > 0 && g_locality) {
+  if (nR >= DUPS_MIN_ROWS && (policy & POLICY_DUP_SAMPLE)) k_sample_dups<K><<<DUPS_CTAS, DUPS_THREADS, 0, stream>>>(R, nR, hdr);
+  k_decide<<<1, 1, 0, stream>>>(hdr, (int)(policy & POLICY_DENSE_MASK));
+  // A table beyond L2 reach that did not get the direct-address layout is not built at all: one host look at the header (the only
+  // sync in the build, and only for big tables), then the relation is radix-partitioned and the partitioned copy is the table (K7).
+  if (big && nR > 0 && (policy & POLICY_RADIX)) {
     TableHeader h;
     cudaError_t e = read_header(hdr, &h, stream);
     if (e != cudaSuccess) return e;
-    if (h.mode == MODE_HASH) {
-      ReorderView rv = reorder_view(reorder_area, nR, (int)sizeof(K));
-      // duplicates already known: order by the slices of the grouped table the build goes to (for i64 keys both hashes are the same)
-      // the reorder carries the FINAL row ids (payload value or row_base + index), read tile by tile next to the keys: looking the
-      // payload up through the carried index afterwards is a random 4-byte gather per row (2^28 rows: +4 ms of DRAM sector traffic)
-      e = radix_partition(R, payload, row_base, nR, (int)sizeof(K), locality_parts(pairs * 64), rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes,
-                          h.has_dups ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
-      if (e != cudaSuccess) return e;
-      Rb = reinterpret_cast<const K*>(rv.keys); perm = rv.idx; payload = nullptr; row_base = 0;
-    }
+    if (h.mode != MODE_DENSE) return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
   }
-  const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0, vecb = (reinterpret_cast<uintptr_t>(Rb) & 15) == 0;
+  const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0;
   const int64_t need = (threads + BLOCK_THREADS - 1) / BLOCK_THREADS;
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 0);
   if (nR == 0) return cudaGetLastError();
-  if (vec) k_build_dense<K, true><<<resident_grid(k_build_dense<K, true>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
-  else     k_build_dense<K, false><<<resident_grid(k_build_dense<K, false>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
-  k_fallback_prepare<<<1, 1, 0, stream>>>(hdr, g_allow_dense == 2);
-  k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
-  if (vecb) k_build_hash<K, true><<<resident_grid(k_build_hash<K, true>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
-  else      k_build_hash<K, false><<<resident_grid(k_build_hash<K, false>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  if (policy & POLICY_DENSE_MASK) {
+    if (vec) k_build_dense<K, true><<<resident_grid(k_build_dense<K, true>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
+    else     k_build_dense<K, false><<<resident_grid(k_build_dense<K, false>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, reinterpret_cast<uint32_t*>(body), hdr);
+    k_fallback_prepare<<<1, 1, 0, stream>>>(hdr, (policy & POLICY_DENSE_MASK) == 2);
+    k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 1);
+  }
+  if (vec) k_build_hash<K, true><<<resident_grid(k_build_hash<K, true>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  else     k_build_hash<K, false><<<resident_grid(k_build_hash<K, false>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
   // duplicates found: rebuild in the grouped layout (every kernel below exits at once otherwise)
   k_group_prepare<<<1, 1, 0, stream>>>(hdr);
   k_clear<<<clear_grid, BLOCK_THREADS, 0, stream>>>(hdr, reinterpret_cast<int4*>(body), 2);
-  if (vecb) k_group_count<K, true><<<resident_grid(k_group_count<K, true>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
-  else      k_group_count<K, false><<<resident_grid(k_group_count<K, false>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, body, hdr);
+  if (vec) k_group_count<K, true><<<resident_grid(k_group_count<K, true>, need), BLOCK_THREADS, 0, stream>>>(R, nR, body, hdr);
+  else     k_group_count<K, false><<<resident_grid(k_group_count<K, false>, need), BLOCK_THREADS, 0, stream>>>(R, nR, body, hdr);
   k_group_offsets<<<clear_grid, BLOCK_THREADS, 0, stream>>>(body, hdr);
-  if (vecb) k_group_fill<K, true><<<resident_grid(k_group_fill<K, true>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
-  else      k_group_fill<K, false><<<resident_grid(k_group_fill<K, false>, need), BLOCK_THREADS, 0, stream>>>(Rb, nR, perm, payload, row_base, body, hdr);
+  if (vec) k_group_fill<K, true><<<resident_grid(k_group_fill<K, true>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
+  else     k_group_fill<K, false><<<resident_grid(k_group_fill<K, false>, need), BLOCK_THREADS, 0, stream>>>(R, nR, payload, row_base, body, hdr);
   return cudaGetLastError();
 }
 
 // (Measured and removed: raising cudaLimitPersistingL2CacheSize to its maximum, 79 MB, so that the table's L2::evict_last lines get
 // the set-aside: config 2 1.84 -> 2.22 ms, forced hash 4.34 -> 6.47 ms. The streams lose more L2 than the table gains.)
 cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base,
-                        void* table, int64_t table_bytes_, cudaStream_t stream) {
+                        void* table, int64_t table_bytes_, uint32_t policy, cudaStream_t stream) {
   if (table_bytes_ < table_bytes(nR, key_bytes)) return cudaErrorInvalidValue;      // sized by hjTableBytes, nothing less
   const int64_t pairs = preferred_pairs(nR, key_bytes);
   if (pairs > (int64_t)1 << 32) return cudaErrorInvalidValue;
   TableHeader* hdr = reinterpret_cast<TableHeader*>(table);
   char* body = reinterpret_cast<char*>(table) + HEADER_BYTES;
-  const int64_t part_bytes = table_part_bytes(nR, key_bytes);                       // the reorder area (big tables) sits behind it
+  const int64_t part_bytes = table_part_bytes(nR, key_bytes);
   const bool big = table_is_big(nR, key_bytes);
-  k_init_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)key_bytes, (unsigned long long)nR, (unsigned long long)part_bytes, (unsigned long long)pairs);
-  if (key_bytes == 4) return launch_build<int32_t>((const int32_t*)R, nR, payload, row_base, body, hdr, pairs, big, body + part_bytes, stream);
-  return launch_build<int64_t>((const int64_t*)R, nR, payload, row_base, body, hdr, pairs, big, body + part_bytes, stream);
+  k_init_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)key_bytes, (unsigned long long)nR, (unsigned long long)part_bytes, (unsigned long long)pairs, policy);
+  if (key_bytes == 4) return launch_build<int32_t>((const int32_t*)R, nR, payload, row_base, body, table_bytes_ - HEADER_BYTES, hdr, pairs, big, policy, stream);
+  return launch_build<int64_t>((const int64_t*)R, nR, payload, row_base, body, table_bytes_ - HEADER_BYTES, hdr, pairs, big, policy, stream);
 }
 
 // =========================================================================================================
@@ -832,11 +817,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count_sparse(const K* __restr
 }
 
 // Write pass of the hit-list mode: one warp per chunk copies the chunk's eight warp lists to their final offsets (coalesced both
-// ways) and turns probe positions into probe row ids (slice-ordered copy -> original index -> payload / row base, like k_write).
+// ways) and turns probe positions into probe row ids (payload / row base, like k_write).
 __global__ void __launch_bounds__(BLOCK_THREADS) k_write_sparse(const TableHeader* __restrict__ hdr, const uint2* __restrict__ hit_list, const uint32_t* __restrict__ warp_counts,
                                                                 const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks, int chunk_rows,
                                                                 int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                                const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
+                                                                const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
                                                                 const unsigned long long* __restrict__ sparse_flag) {
   if (!*sparse_flag || hdr->mode == MODE_GROUP) return;
   const int lane = threadIdx.x & 31;
@@ -871,9 +856,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write_sparse(const TableHeade
         const uint32_t v = v0 + u * 32 + lane;
         if (v < tot) {
           const uint32_t j = base + e[u].y;                                                // positions are chunk-relative
-          const uint32_t idx = perm ? perm[j] : j;
           st_stream_u32(outR + o + v, e[u].x, pol_s);
-          st_stream_u32(outS + o + v, probe_payload ? probe_payload[idx] : probe_row_base + idx, pol_s);
+          st_stream_u32(outS + o + v, probe_payload ? probe_payload[j] : probe_row_base + j, pol_s);
         }
       }
     }
@@ -1077,7 +1061,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restri
 // block total; the second launch (only when there is more than one block) adds the preceding blocks' totals. A single CTA
 // looping over the array took 61 us for config 3's 65 536 chunks and would take ~1 ms for 2^30 i64 rows (1 M chunks).
 constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 16, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocks(unsigned long long* __restrict__ t, int64_t n, unsigned long long* __restrict__ block_sums) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocks(unsigned long long* __restrict__ t, int64_t n, unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ total_out) {
   __shared__ unsigned long long sm[33];
   const int64_t i0 = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
   unsigned long long v[SCAN_ITEMS], sum = 0;
@@ -1100,9 +1084,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocks(unsigned long long
     #pragma unroll
     for (int e = 0; e < SCAN_ITEMS; e++) if (i0 + e < n) t[i0 + e] = v[e];
   }
-  if (threadIdx.x == 0) { block_sums[blockIdx.x] = total; if (gridDim.x == 1) t[n] = total; }
+  if (threadIdx.x == 0) { block_sums[blockIdx.x] = total; if (gridDim.x == 1) { t[n] = total; if (total_out) *total_out = total; } }
 }
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* __restrict__ t, int64_t n, const unsigned long long* __restrict__ block_sums) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* __restrict__ t, int64_t n, const unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ total_out) {
   __shared__ unsigned long long sm[33];
   unsigned long long mine = 0;
   for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) mine += block_sums[b];
@@ -1112,67 +1096,57 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* _
     #pragma unroll
     for (int e = 0; e < SCAN_ITEMS; e++) if (i0 + e < n) t[i0 + e] += base;
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) t[n] = base + block_sums[blockIdx.x];
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { t[n] = base + block_sums[blockIdx.x]; if (total_out) *total_out = t[n]; }
 }
-static void launch_scan(unsigned long long* t, int64_t n, unsigned long long* block_sums, cudaStream_t stream) {
+// t[0 .. n) := exclusive prefix, t[n] := total (also stored at *total_out when given). block_sums: ceil(n / 16 384) entries of scratch.
+void launch_scan(unsigned long long* t, int64_t n, unsigned long long* block_sums, unsigned long long* total_out, cudaStream_t stream) {
   const unsigned nb = (unsigned)std::max<int64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-  k_scan_blocks<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums);
-  if (nb > 1) k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums);
+  k_scan_blocks<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums, total_out);
+  if (nb > 1) k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(t, n, block_sums, total_out);
 }
 
-int allow_dense() { return g_allow_dense; }
-
-cudaError_t count_rows_async(const void* S_in, int64_t nS, int key_bytes, const void* table, void* scratch, bool big_hint, bool range_hint, int* reordered,
+// The count pass looks at the table header first (one 256-byte readback: a stream sync) and launches exactly the kernels of the layout
+// it finds, under the policy the table was BUILT with. Only the hit-list decision stays on the device (k_sample_hits -> CTR_SPARSE): for
+// the unique layouts the match-cache / range kernel and the hit-list kernel are both queued and one of them exits at once.
+cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch,
                              bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
   ScratchView sv = scratch_view(scratch, nS, key_bytes);
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
-  const void* S = S_in;
-  *reordered = REORDER_NONE;
-  if (big_hint && nS > 0 && g_locality) {
-    TableHeader h;
-    cudaError_t e = read_header(table, &h, stream);
-    if (e != cudaSuccess) return e;
-    if (h.mode != MODE_DENSE && (int64_t)h.n_pairs * 64 > LOCALITY_MIN_BYTES) {
-      ReorderView rv = reorder_view(sv.reorder, nS, key_bytes);
-      // carry_rows: the caller already knows the probe row ids (payload column / row base), so the reorder carries them instead of
-      // the original index and the write pass needs no gather through it
-      e = radix_partition(S_in, carry_rows ? probe_payload : nullptr, carry_rows ? probe_row_base : 0u, nS, key_bytes, locality_parts((int64_t)h.n_pairs * 64),
-                          rv.keys, rv.idx, rv.offsets, rv.ws, rv.ws_bytes, h.mode == MODE_GROUP ? PART_SEL_GROUP : PART_SEL_TABLE, stream);
-      if (e != cudaSuccess) return e;
-      S = rv.keys; *reordered = carry_rows ? REORDER_ROWS : REORDER_INDEX;
-    }
-  }
+  TableHeader h;
+  { cudaError_t e = read_header(table, &h, stream); if (e != cudaSuccess) return e; }
+  if (h.magic != HJ_MAGIC || (int)h.key_bytes != key_bytes) return cudaErrorInvalidValue;          // never built, or built for the other key width
   { cudaError_t e = cudaMemsetAsync(sv.counters, 0, SCRATCH_COUNTERS * sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
-  const unsigned long long* sparse_flag = sv.counters + 3;
-  const int sparse_policy = g_tma_count ? 0 : g_sparse;
+  if (carry_rows) { cudaError_t e = cudaMemsetAsync(sv.counters + CTR_CARRIED, 1, 1, stream); if (e != cudaSuccess) return e; }
+  unsigned long long* total_out = sv.counters + CTR_TOTAL;
+  if (h.mode == MODE_RADIX)
+    return radix_count(S, nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.scan_sums, sv.counters + CTR_TICKET_RADIX, total_out, carry_rows, probe_payload, probe_row_base, stream);
+  const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
+  const bool tma = (h.policy & POLICY_TMA_COUNT) != 0;
+  const int sparse_policy = (tma || h.mode == MODE_GROUP) ? 0 : (int)((h.policy >> POLICY_SPARSE_SHIFT) & 3);
+  const bool by_range = h.mode == MODE_DENSE && h.all_present;
   if (nS > 0 && (sparse_policy == 2 || (sparse_policy == 1 && nS >= SPARSE_MIN_ROWS))) {
-    if (key_bytes == 4) k_sample_hits<int32_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.counters + 3, sparse_policy);
-    else                k_sample_hits<int64_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.counters + 3, sparse_policy);
+    if (key_bytes == 4) k_sample_hits<int32_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.counters + CTR_SPARSE, sparse_policy);
+    else                k_sample_hits<int64_t><<<1, SAMPLE_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.counters + CTR_SPARSE, sparse_policy);
   }
   if (sv.nchunks > 0) {
-    // direct-address layout: dense_grid(); bucketised layouts: one resident wave (idle launch ~3 us; the slice-ordered window stays tight)
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
-    k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
-    k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);  \
-    k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag); \
-    if (range_hint) k_count_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag); \
-    if (sparse_policy) { \
-      k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
-      k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + 4, sparse_flag); \
+    if (h.mode == MODE_GROUP) k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP, sparse_flag); \
+    else if (h.mode == MODE_HASH) { \
+      k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_HASH, sparse_flag);  \
+      if (sparse_policy) k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_SPARSE, sparse_flag); \
+    } else { \
+      if (by_range) k_count_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag); \
+      else if (tma && sizeof(K) == 4 && V) k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets); \
+      else k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
+      if (sparse_policy) k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_SPARSE, sparse_flag); \
     }
-    if (key_bytes == 4 && vec && g_tma_count) {                            // TMA-staged streams for the direct-address layout
-      k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets);
-      k_count<int32_t, true, MODE_HASH><<<resident_grid(k_count<int32_t, true, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag);
-      k_count<int32_t, true, MODE_GROUP><<<resident_grid(k_count<int32_t, true, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 1, sparse_flag);
-      if (range_hint) k_count_range<int32_t, true><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag);
-    } else
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
     else                { if (vec) { HJ_LAUNCH_COUNT(int64_t, true) } else { HJ_LAUNCH_COUNT(int64_t, false) } }
 #undef HJ_LAUNCH_COUNT
   }
-  launch_scan(sv.chunk_offsets, sv.nchunks, sv.counters + SCRATCH_COUNTERS, stream);
+  launch_scan(sv.chunk_offsets, sv.nchunks, sv.scan_sums, total_out, stream);
   return cudaGetLastError();
 }
 
@@ -1186,18 +1160,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
                                                          const TableHeader* __restrict__ hdr, const uint32_t* __restrict__ mcache, const uint32_t* __restrict__ run_start,
                                                          const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks, unsigned long long* tickets,
                                                          int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
+                                                         const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
                                                          const unsigned long long* __restrict__ sparse_flag) {
   if ((hdr->mode == MODE_GROUP) != GROUPED) return;
   if (!GROUPED && *sparse_flag) return;                              // hit-list mode: k_write_sparse takes it
   if (!GROUPED && hdr->all_present) return;                          // count-by-range mode: k_write_range takes it
   using T = KeyTraits<K>;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT;
-  // probe row id of position j of the relation the kernel reads: S may be a slice-ordered copy (perm = original index)
-  auto probe_row = [&](int64_t j) -> uint32_t {
-    const uint32_t idx = perm ? perm[j] : (uint32_t)j;
-    return probe_payload ? probe_payload[idx] : probe_row_base + idx;
-  };
+  auto probe_row = [&](int64_t j) -> uint32_t { return probe_payload ? probe_payload[j] : probe_row_base + (uint32_t)j; };
   __shared__ uint32_t warp_totals[2][BLOCK_THREADS / 32];
   __shared__ unsigned long long scan_sm[33];
   constexpr bool dups = GROUPED;
@@ -1297,33 +1267,48 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
   }
 }
 
-cudaError_t write_pairs(const void* S_in, int64_t nS, int key_bytes, const void* table, const void* scratch,
-                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, int reordered, bool range_hint,
-                        cudaStream_t stream) {
+// The write pass reads the table header and the scratch counters back (one sync) and launches the ONE kernel of the path the count
+// pass took: grouped / radix by the table's layout, hit lists by the device-side flag, range by all_present, else the match cache.
+cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
+                        int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
   ScratchView sv = scratch_view(const_cast<void*>(scratch), nS, key_bytes);
-  if (sv.nchunks == 0) return cudaSuccess;
+  if (nS == 0) return cudaSuccess;
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
-  const void* S = S_in; const uint32_t* perm = nullptr;
-  if (reordered != REORDER_NONE) { ReorderView rv = reorder_view(sv.reorder, nS, key_bytes); S = rv.keys; perm = rv.idx; }
-  if (reordered == REORDER_ROWS) { probe_payload = nullptr; probe_row_base = 0; }      // perm already holds the probe row ids
+  TableHeader h; unsigned long long ctr[SCRATCH_COUNTERS];
+  {
+    char* pin = reinterpret_cast<char*>(pinned_block());
+    if (!pin) return cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMemcpyAsync(pin, table, sizeof(TableHeader), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pin + HEADER_BYTES, sv.counters, sizeof(ctr), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    memcpy(&h, pin, sizeof(h)); memcpy(ctr, pin + HEADER_BYTES, sizeof(ctr));
+  }
+  if (h.magic != HJ_MAGIC || (int)h.key_bytes != key_bytes) return cudaErrorInvalidValue;
+  if (ctr[CTR_TOTAL] == 0) return cudaSuccess;                      // nothing to emit (join_v1.mlir:600-601 skips the probe too)
+  { cudaError_t e = cudaMemsetAsync(sv.counters + CTR_TICKET_GROUP_W, 0, 8, stream);                 // the write pass may be repeated after one count
+    if (e == cudaSuccess) e = cudaMemsetAsync(sv.counters + CTR_TICKET_RADIX_W, 0, 8, stream);
+    if (e != cudaSuccess) return e; }
+  const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
+  if (h.mode == MODE_RADIX) {
+    if (ctr[CTR_CARRIED]) { probe_payload = nullptr; probe_row_base = 0; }           // the partitioned copy already holds the probe row ids
+    return radix_write(nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.counters + CTR_TICKET_RADIX_W, outR, outS, ctr[CTR_CARRIED] != 0, probe_payload, probe_row_base, stream);
+  }
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
-  { cudaError_t e = cudaMemsetAsync(sv.counters + 2, 0, sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
+  const bool grouped = h.mode == MODE_GROUP, lists = !grouped && ctr[CTR_SPARSE] != 0, by_range = !grouped && !lists && h.mode == MODE_DENSE && h.all_present;
+  if (lists) {
+    k_write_sparse<<<(unsigned)std::min<int64_t>(PERSIST_GRID, (sv.nchunks + BLOCK_THREADS / 32 - 1) / (BLOCK_THREADS / 32)), BLOCK_THREADS, 0, stream>>>(
+        hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, chunk_keys(key_bytes), outR, outS, probe_payload, probe_row_base, sparse_flag);
+    return cudaGetLastError();
+  }
 #define HJ_LAUNCH_WRITE(K, V) \
-  k_write<K, V, false><<<dense_grid(k_write<K, V, false>, sv.nchunks, g_write_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3); \
-  k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + 2, outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);
+  if (grouped) k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP_W, outR, outS, probe_payload, probe_row_base, sparse_flag); \
+  else if (by_range) k_write_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sparse_flag); \
+  else k_write<K, V, false><<<dense_grid(k_write<K, V, false>, sv.nchunks, g_write_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP_W, outR, outS, probe_payload, probe_row_base, sparse_flag);
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
 #undef HJ_LAUNCH_WRITE
-  if (range_hint && !reordered) {
-    if (key_bytes == 4) { if (vec) k_write_range<int32_t, true><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3);
-                          else     k_write_range<int32_t, false><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3); }
-    else                { if (vec) k_write_range<int64_t, true><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3);
-                          else     k_write_range<int64_t, false><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const int64_t*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sv.counters + 3); }
-  }
-  if (g_sparse && !g_tma_count)
-    k_write_sparse<<<(unsigned)std::min<int64_t>(PERSIST_GRID, (sv.nchunks + BLOCK_THREADS / 32 - 1) / (BLOCK_THREADS / 32)), BLOCK_THREADS, 0, stream>>>(
-        hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, chunk_keys(key_bytes), outR, outS, perm, probe_payload, probe_row_base, sv.counters + 3);
   return cudaGetLastError();
 }
 
@@ -1448,348 +1433,17 @@ cudaError_t join_fused_async(const void* S, int64_t nS, int key_bytes, const voi
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
   const int64_t ntiles = (nS + tile_keys(key_bytes) - 1) / tile_keys(key_bytes);
   unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(sv.mcache);      // the match cache is not needed: reuse it (8 B per tile)
-  unsigned long long* total = sv.chunk_offsets + sv.nchunks;                              // same slot the two-phase path reports in
+  unsigned long long* total = sv.counters + CTR_TOTAL;                                    // same slot the two-phase path reports in
   cudaError_t e = cudaMemsetAsync(sv.counters, 0, SCRATCH_COUNTERS * sizeof(unsigned long long), stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(total, 0, 8, stream);
   if (e == cudaSuccess && ntiles > 0) e = cudaMemsetAsync(tile_state, 0, (size_t)ntiles * 8, stream);
   if (e != cudaSuccess || ntiles == 0) return e;
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_FUSED(K, V) \
   k_join_fused<K, V, MODE_DENSE><<<resident_grid(k_join_fused<K, V, MODE_DENSE>, ntiles), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, tile_state, sv.counters, ntiles, outR, outS, (unsigned long long)capacity, probe_payload, probe_row_base, total); \
-  k_join_fused<K, V, MODE_HASH><<<resident_grid(k_join_fused<K, V, MODE_HASH>, ntiles), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, tile_state, sv.counters + 1, ntiles, outR, outS, (unsigned long long)capacity, probe_payload, probe_row_base, total);
+  k_join_fused<K, V, MODE_HASH><<<resident_grid(k_join_fused<K, V, MODE_HASH>, ntiles), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, tile_state, sv.counters + CTR_TICKET_GROUP, ntiles, outR, outS, (unsigned long long)capacity, probe_payload, probe_row_base, total);
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_FUSED(int32_t, true) } else { HJ_LAUNCH_FUSED(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_FUSED(int64_t, true) } else { HJ_LAUNCH_FUSED(int64_t, false) } }
 #undef HJ_LAUNCH_FUSED
-  return cudaGetLastError();
-}
-
-// =========================================================================================================
-// K5  radix partition on the key hash.  Feeds the multi-GPU shuffle two ways:
-//   radix_partition       local: partition p occupies [offsets[p], offsets[p+1]) of out_keys / out_rows (then NCCL all-to-all)
-//   partition_push        fused with the exchange: every (key, row) is stored straight into the receive buffer of the
-//                         rank that owns its partition, through peer-mapped pointers (NVLink), no intermediate copy
-// A CTA takes 4096 tuples, ranks them per partition with shared-memory atomics, sorts them by partition in shared memory and
-// writes each partition's run contiguously (512 tuples = 2-6 KB per run at 8 parts), so HBM / NVLink see full-width stores.
-// =========================================================================================================
-constexpr int PART_ITEMS = 8;                                    // tuples per thread, blocked (contiguous) per thread
-constexpr int PART_TILE = BLOCK_THREADS * PART_ITEMS;            // 2048 tuples per CTA
-constexpr int PART_WARPS = BLOCK_THREADS / 32;
-
-// SEL 0: an independent hash (which rank owns the key).  SEL 1 / 2: the SAME hash bits that pick the bucket pair in the
-// inline (1) or grouped (2) table, so a partition is a contiguous slice of the table.
-template <typename K, int SEL>
-__device__ __forceinline__ uint32_t part_of(K key, int n_parts) {
-  if (SEL == 0) return (uint32_t)(((uint64_t)KeyTraits<K>::part_hash(key) * (uint32_t)n_parts) >> 32);
-  if (SEL == 1 && sizeof(K) == 4) return (uint32_t)(((uint64_t)mix32((uint32_t)key) * (uint32_t)n_parts) >> 32);
-  return (uint32_t)__umul64hi(mix64((uint64_t)(long long)key), (uint64_t)n_parts);
-}
-
-// lanes of the warp whose `p` equals mine, from `bits` ballots (the classic warp multisplit; cheaper than MATCH.ANY here)
-__device__ __forceinline__ unsigned same_part_mask(uint32_t p, int bits) {
-  unsigned m = 0xffffffffu;
-  for (int b = 0; b < bits; b++) {
-    const unsigned bal = __ballot_sync(0xffffffffu, (p >> b) & 1u);
-    m &= ((p >> b) & 1u) ? bal : ~bal;
-  }
-  return m;
-}
-
-// tile loader: coalesced 16-byte vectors; tile-local index of element e of this thread: ((e / KPV) * 256 + t) * KPV + e % KPV
-template <typename K>
-__device__ __forceinline__ int part_li(int e) {
-  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
-  return ((e / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (e % KPV);
-}
-template <typename K>
-__device__ __forceinline__ void part_load(const K* __restrict__ keys, int64_t base, int count, bool aligned, uint64_t pol, K (&key)[PART_ITEMS]) {
-  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC;
-  #pragma unroll
-  for (int v = 0; v < PART_ITEMS / KPV; v++) {
-    const int l0 = (v * BLOCK_THREADS + threadIdx.x) * KPV;
-    if (aligned && l0 + KPV <= count) { int4 x = ld_stream_v4(keys + base + l0, pol); memcpy(&key[v * KPV], &x, 16); }
-    else {
-      #pragma unroll
-      for (int e = 0; e < KPV; e++) key[v * KPV + e] = (l0 + e < count) ? keys[base + l0 + e] : K(0);
-    }
-  }
-}
-
-// Two-pass, atomic-free partition. The tiles are dealt to a fixed grid of G persistent CTAs (contiguous tile ranges);
-//   pass 1 (k_part_hist)    every CTA counts its tuples per part                      -> mat[cta][part]
-//   scan   (k_part_scan)    start[part] + prefix over the CTAs                         -> mat[cta][part] = first destination element
-//   pass 2 (k_part_scatter) the same CTA walks the same tiles with running cursors in shared memory
-// (global atomics on the few per-part cursors serialise at about one per clock: 2.7 M of them cost > 1 ms at 2^28 tuples).
-constexpr int PART_GRID = 148 * 6;
-
-__host__ __device__ inline int64_t part_tiles_per_cta(int64_t n, int grid) { const int64_t nt = (n + PART_TILE - 1) / PART_TILE; return (nt + grid - 1) / grid; }
-
-template <typename K, int SEL>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_part_hist(const K* __restrict__ keys, int64_t n, int n_parts, int bits, unsigned long long* __restrict__ mat,
-                                                             unsigned long long* __restrict__ totals) {
-  __shared__ unsigned int wh[PART_WARPS][PART_MAX];               // one private histogram per warp: no atomics, no contention
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int p = lane; p < n_parts; p += 32) wh[warp][p] = 0;
-  __syncwarp();
-  const int64_t tpc = part_tiles_per_cta(n, gridDim.x);
-  const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
-  const uint64_t pol = policy_evict_first();
-  for (int64_t tile = blockIdx.x * tpc; tile < (blockIdx.x + 1) * tpc; tile++) {
-    const int64_t base = tile * PART_TILE;
-    if (base >= n) break;
-    const int count = (int)(n - base < PART_TILE ? n - base : PART_TILE);
-    K key[PART_ITEMS];
-    part_load<K>(keys, base, count, aligned, pol, key);
-    #pragma unroll
-    for (int e = 0; e < PART_ITEMS; e++)
-      if (part_li<K>(e) < count) atomicAdd(&wh[warp][part_of<K, SEL>(key[e], n_parts)], 1u);    // warp-private counters: only same-warp lanes collide
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) {
-    unsigned long long t = 0;
-    #pragma unroll
-    for (int w = 0; w < PART_WARPS; w++) t += wh[w][p];
-    mat[(size_t)blockIdx.x * n_parts + p] = t;
-    if (t) atomicAdd(&totals[p], t);                              // <= one atomic per (CTA, part): 888 per address, all parts in parallel
-  }
-}
-
-// mat[cta][part] := start[part] + prefix over the CTAs, where start[part] = exclusive scan of the part totals (local partition;
-// also written to offsets[]) or the caller's cursors (push into peers' buffers). One CTA of 32 warps per group of 32 parts: lane =
-// part, warp = a contiguous run of CTA rows, so every load is a coalesced 256-byte row segment and all of a thread's loads are in
-// flight together. The part totals come from k_part_hist (atomics). History: one thread per part walking the 888 rows serially took
-// 0.17 ms per call; one warp per part with strided lanes 0.46 ms (454 K uncoalesced sector requests from a single SM).
-constexpr int PSCAN_THREADS = 1024;
-__global__ void __launch_bounds__(PSCAN_THREADS) k_part_scan(unsigned long long* __restrict__ mat, int grid, int n_parts, const unsigned long long* __restrict__ totals,
-                                                             unsigned long long* __restrict__ offsets, const unsigned long long* __restrict__ start_in) {
-  __shared__ unsigned long long sm[33];
-  __shared__ unsigned long long ex[PART_MAX];
-  __shared__ unsigned long long wsum[32][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {                                                                           // every CTA scans the (<= 256) totals for itself
-    unsigned long long all, e = block_exclusive_scan((int)threadIdx.x < n_parts ? totals[threadIdx.x] : 0ULL, sm, &all);
-    if ((int)threadIdx.x < n_parts) {
-      ex[threadIdx.x] = e;
-      if (offsets && blockIdx.x == 0) { offsets[threadIdx.x] = e; if ((int)threadIdx.x == n_parts - 1) offsets[n_parts] = all; }
-    }
-  }
-  const int p = blockIdx.x * 32 + lane;
-  const int per_warp = (grid + 31) / 32, r0 = warp * per_warp;
-  const int rows = r0 < grid ? (grid - r0 < per_warp ? grid - r0 : per_warp) : 0;
-  unsigned long long sum = 0;
-  if (p < n_parts) {
-    #pragma unroll 8
-    for (int i = 0; i < rows; i++) sum += mat[(size_t)(r0 + i) * n_parts + p];
-  }
-  wsum[warp][lane] = sum;
-  __syncthreads();
-  if (p < n_parts) {
-    unsigned long long run = start_in ? start_in[p] : ex[p];
-    for (int w = 0; w < warp; w++) run += wsum[w][lane];
-    for (int i0 = 0; i0 < rows; i0 += 8) {                                    // second look at the same rows (L1/L2 hits), eight loads in flight
-      unsigned long long v[8];
-      #pragma unroll
-      for (int i = 0; i < 8; i++) v[i] = i0 + i < rows ? mat[(size_t)(r0 + i0 + i) * n_parts + p] : 0ULL;
-      #pragma unroll
-      for (int i = 0; i < 8; i++) if (i0 + i < rows) { mat[(size_t)(r0 + i0 + i) * n_parts + p] = run; run += v[i]; }
-    }
-  }
-}
-
-// dst_keys[p] / dst_rows[p]: base pointer of partition p's destination (all equal for a local partition, peer-mapped
-// receive buffers for the fused push). A CTA walks its tuples in tiles of SCAT_TILE = 4096 (16 per thread): ranks them per
-// (warp, part) with warp-private shared-memory counters, turns the counters into tile positions with two small scans, stages keys,
-// tile-local source positions and part ids partition-sorted in shared memory, and writes each part's run as one contiguous
-// stream. The first version (2048-tuple tiles, the part hash recomputed in the output loop, 64-bit pointer loads per tuple) ran
-// latency- and barrier-bound: ncu on 2^28 i64 tuples x 256 parts showed 4.1 ms, 25 % DRAM, 27 % issue, barrier + long-scoreboard
-// stalls of 29 warps per issue slot, and 1.5x the algorithmic DRAM writes from 64-byte runs evicted as partial sectors.
-constexpr int SCAT_ITEMS = 16;
-constexpr int SCAT_TILE = BLOCK_THREADS * SCAT_ITEMS;            // 4096 tuples: 16 per part and tile at 256 parts
-static_assert(PART_MAX <= 256, "ScatterSmem::spart holds part ids in a byte");
-template <typename K, bool LOCAL>
-struct ScatterSmem {
-  K skeys[SCAT_TILE];
-  unsigned long long delta[PART_MAX];                           // destination index of staged position i of part p: delta[p] + i
-  unsigned long long gcur[PART_MAX];                            // running destination cursor of each part for this CTA
-  K* kptr[LOCAL ? 1 : PART_MAX];                                // per-part destinations: only the push into peers' buffers has more than one
-  uint32_t* rptr[LOCAL ? 1 : PART_MAX];
-  unsigned int wh[PART_WARPS][PART_MAX];                        // per-warp counts, then per-warp exclusive offsets inside the part
-  unsigned int lbase[PART_MAX + 1];                             // first staged position of each part
-  unsigned short sidx[SCAT_TILE];                               // tile-local source position
-  unsigned char spart[SCAT_TILE];                               // part id (PART_MAX <= 256)
-};
-
-template <typename K, int SEL, bool LOCAL>
-__global__ void __launch_bounds__(BLOCK_THREADS, 3) k_part_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base, int64_t n,
-                                                                   int n_parts, int bits, K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
-                                                                   const unsigned long long* __restrict__ mat) {
-  extern __shared__ __align__(16) unsigned char scat_raw[];
-  ScatterSmem<K, LOCAL>& sm = *reinterpret_cast<ScatterSmem<K, LOCAL>*>(scat_raw);
-  constexpr int KPV = KeyTraits<K>::KEYS_PER_VEC, NV = SCAT_ITEMS / KPV;
-  const int warp = threadIdx.x >> 5;
-  for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) { if (!LOCAL) { sm.kptr[p] = dst_keys[p]; sm.rptr[p] = dst_rows[p]; } sm.gcur[p] = mat[(size_t)blockIdx.x * n_parts + p]; }
-  K* const out_keys = dst_keys[0]; uint32_t* const out_rows = dst_rows[0];        // LOCAL: every part goes to the same pair of arrays
-  const int64_t tpc = part_tiles_per_cta(n, gridDim.x);                           // the CTA's range is the one k_part_hist counted
-  const int64_t lo = (int64_t)blockIdx.x * tpc * PART_TILE;
-  const int64_t hi = lo + tpc * PART_TILE < n ? lo + tpc * PART_TILE : n;
-  const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
-  const uint64_t pol = policy_evict_first();
-  K key[SCAT_ITEMS];
-  auto load_tile = [&](int64_t base) {                            // coalesced 16-byte vectors; rows past the CTA's range read as key 0 and are never ranked
-    const int count = (int)(hi - base < SCAT_TILE ? hi - base : SCAT_TILE);
-    #pragma unroll
-    for (int v = 0; v < NV; v++) {
-      const int l0 = (v * BLOCK_THREADS + threadIdx.x) * KPV;
-      if (aligned && l0 + KPV <= count) { const int4 x = ld_stream_v4(keys + base + l0, pol); memcpy(&key[v * KPV], &x, 16); }
-      else {
-        #pragma unroll
-        for (int e = 0; e < KPV; e++) key[v * KPV + e] = (l0 + e < count) ? keys[base + l0 + e] : K(0);
-      }
-    }
-  };
-  if (lo < hi) load_tile(lo);
-  for (int64_t base = lo; base < hi; base += SCAT_TILE) {
-    const int count = (int)(hi - base < SCAT_TILE ? hi - base : SCAT_TILE);
-    for (int p = threadIdx.x; p < PART_WARPS * PART_MAX; p += BLOCK_THREADS) (&sm.wh[0][0])[p] = 0;
-    __syncthreads();                                              // also orders the previous tile's output loop before restaging
-    uint32_t pr[SCAT_ITEMS];                                      // part << 16 | rank inside (warp, part)
-    #pragma unroll
-    for (int e = 0; e < SCAT_ITEMS; e++) {
-      const int li = ((e / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (e % KPV);
-      pr[e] = 0xFFFFFFFFu;
-      if (li < count) {
-        const uint32_t p = part_of<K, SEL>(key[e], n_parts);
-        pr[e] = (p << 16) | atomicAdd(&sm.wh[warp][p], 1u);       // rank inside (warp, part); warp-private counters
-      }
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < n_parts; p += BLOCK_THREADS) {  // per part: exclusive offsets of the warps, and the part total
-      unsigned int run = 0;
-      #pragma unroll
-      for (int w = 0; w < PART_WARPS; w++) { const unsigned int t = sm.wh[w][p]; sm.wh[w][p] = run; run += t; }
-      sm.lbase[p] = run;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {                                       // exclusive scan of the part totals (<= 256: 8 per lane); cursors advance here
-      unsigned int v[PART_MAX / 32], sum = 0;
-      #pragma unroll
-      for (int q = 0; q < PART_MAX / 32; q++) { const int p = threadIdx.x * (PART_MAX / 32) + q; v[q] = p < n_parts ? sm.lbase[p] : 0u; sum += v[q]; }
-      const unsigned int inc = warp_inclusive_scan(sum);
-      unsigned int run = inc - sum;
-      #pragma unroll
-      for (int q = 0; q < PART_MAX / 32; q++) {
-        const int p = threadIdx.x * (PART_MAX / 32) + q;
-        if (p < n_parts) { sm.lbase[p] = run; const unsigned long long g = sm.gcur[p]; sm.delta[p] = g - run; sm.gcur[p] = g + v[q]; }
-        run += v[q];
-      }
-      if (threadIdx.x == 31) sm.lbase[n_parts] = inc;
-    }
-    __syncthreads();
-    #pragma unroll
-    for (int e = 0; e < SCAT_ITEMS; e++) {
-      if (pr[e] != 0xFFFFFFFFu) {
-        const uint32_t p = pr[e] >> 16, pos = sm.lbase[p] + sm.wh[warp][p] + (pr[e] & 0xFFFFu);
-        sm.skeys[pos] = key[e];
-        sm.sidx[pos] = (unsigned short)(((e / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (e % KPV));
-        sm.spart[pos] = (unsigned char)p;
-      }
-    }
-    __syncthreads();
-    // the keys are staged: their registers take the NEXT tile's loads, which are in flight while this tile's runs are written
-    // (ncu: the first use of the loaded keys held 36 % of the stall samples with the loads at the top of the tile)
-    if (base + SCAT_TILE < hi) load_tile(base + SCAT_TILE);
-    #pragma unroll 4
-    for (int i = threadIdx.x; i < count; i += BLOCK_THREADS) {    // partition-sorted: consecutive i -> consecutive destination addresses
-      const K k = sm.skeys[i];
-      const uint32_t p = sm.spart[i];
-      const unsigned long long d = sm.delta[p] + (unsigned)i;
-      const int64_t src = base + sm.sidx[i];
-      const uint32_t r = rows ? rows[src] : row_base + (uint32_t)src;
-      if (LOCAL) { out_keys[d] = k; out_rows[d] = r; }
-      else { sm.kptr[p][d] = k; sm.rptr[p][d] = r; }
-    }
-  }
-}
-
-__global__ void k_part_local_ptrs(void** kp, uint32_t** rp, void* out_keys, uint32_t* out_rows, int n_parts) {
-  for (int p = threadIdx.x; p < n_parts; p += blockDim.x) { kp[p] = out_keys; rp[p] = out_rows; }
-}
-
-// workspace: mat u64[PART_GRID][P] | key ptrs [P] | row ptrs [P] | part totals u64[P]
-int64_t partition_workspace_bytes(int64_t, int n_parts) { return (int64_t)PART_GRID * n_parts * 8 + (int64_t)3 * n_parts * 8 + 64; }
-static unsigned long long* part_totals(void* workspace, int n_parts) {
-  return reinterpret_cast<unsigned long long*>(workspace) + (size_t)PART_GRID * n_parts + (size_t)2 * n_parts;
-}
-
-static inline int part_bits(int n_parts) { int b = 0; while ((1 << b) < n_parts) b++; return b; }
-static inline int part_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(PART_GRID, (n + PART_TILE - 1) / PART_TILE)); }
-
-template <typename K>
-static void launch_hist(const void* keys, int64_t n, int n_parts, unsigned long long* mat, unsigned long long* totals, int sel, cudaStream_t stream) {
-  const int grid = part_grid(n), bits = part_bits(n_parts);
-  if (sel == PART_SEL_TABLE)      k_part_hist<K, 1><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, n, n_parts, bits, mat, totals);
-  else if (sel == PART_SEL_GROUP) k_part_hist<K, 2><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, n, n_parts, bits, mat, totals);
-  else                            k_part_hist<K, 0><<<grid, BLOCK_THREADS, 0, stream>>>((const K*)keys, n, n_parts, bits, mat, totals);
-}
-template <typename K, int SEL, bool LOCAL>
-static void launch_scatter_sel(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int n_parts, void* const* kp, uint32_t* const* rp,
-                               const unsigned long long* mat, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_part_scatter<K, SEL, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<K, LOCAL>)); attr_set = true; }
-  k_part_scatter<K, SEL, LOCAL><<<part_grid(n), BLOCK_THREADS, sizeof(ScatterSmem<K, LOCAL>), stream>>>((const K*)keys, rows, row_base, n, n_parts, part_bits(n_parts),
-                                                                                              (K* const*)kp, rp, mat);
-}
-template <typename K>
-static void launch_scatter(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int n_parts, void* const* kp, uint32_t* const* rp,
-                           const unsigned long long* mat, int sel, bool local, cudaStream_t stream) {
-  if (sel == PART_SEL_TABLE)      launch_scatter_sel<K, 1, true>(keys, rows, row_base, n, n_parts, kp, rp, mat, stream);      // table-slice reorders are always local
-  else if (sel == PART_SEL_GROUP) launch_scatter_sel<K, 2, true>(keys, rows, row_base, n, n_parts, kp, rp, mat, stream);
-  else if (local)                 launch_scatter_sel<K, 0, true>(keys, rows, row_base, n, n_parts, kp, rp, mat, stream);
-  else                            launch_scatter_sel<K, 0, false>(keys, rows, row_base, n, n_parts, kp, rp, mat, stream);
-}
-
-// pass 1 + totals: counts[p] (device) = tuples of partition p; the per-CTA matrix stays in the workspace for the scatter
-cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_parts, unsigned long long* counts, void* workspace, int64_t workspace_bytes,
-                            int sel, cudaStream_t stream) {
-  if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
-  unsigned long long* mat = reinterpret_cast<unsigned long long*>(workspace);
-  unsigned long long* totals = part_totals(workspace, n_parts);
-  { cudaError_t e = cudaMemsetAsync(totals, 0, (size_t)n_parts * 8, stream); if (e != cudaSuccess) return e; }
-  if (key_bytes == 4) launch_hist<int32_t>(keys, n, n_parts, mat, totals, sel, stream);
-  else                launch_hist<int64_t>(keys, n, n_parts, mat, totals, sel, stream);
-  if (counts) {                                                    // totals only; the matrix keeps the raw counts for the later scan
-    cudaError_t e = cudaMemcpyAsync(counts, totals, (size_t)n_parts * 8, cudaMemcpyDeviceToDevice, stream);
-    if (e != cudaSuccess) return e;
-  }
-  return cudaGetLastError();
-}
-
-cudaError_t radix_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
-                            void* out_keys, uint32_t* out_rows, unsigned long long* offsets, void* workspace, int64_t workspace_bytes,
-                            int sel, cudaStream_t stream) {
-  if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
-  unsigned long long* mat = reinterpret_cast<unsigned long long*>(workspace);
-  void** kp = reinterpret_cast<void**>(mat + (size_t)PART_GRID * n_parts);
-  uint32_t** rp = reinterpret_cast<uint32_t**>(kp + n_parts);
-  cudaError_t e = partition_count(keys, n, key_bytes, n_parts, nullptr, workspace, workspace_bytes, sel, stream);
-  if (e != cudaSuccess) return e;
-  k_part_scan<<<(n_parts + 31) / 32, PSCAN_THREADS, 0, stream>>>(mat, part_grid(n), n_parts, part_totals(workspace, n_parts), offsets, nullptr);
-  k_part_local_ptrs<<<1, 256, 0, stream>>>(kp, rp, out_keys, out_rows, n_parts);
-  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, kp, rp, mat, sel, true, stream);
-  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, kp, rp, mat, sel, true, stream);
-  return cudaGetLastError();
-}
-
-// Fused partition + exchange: peer_keys[p] / peer_rows[p] are DEVICE arrays of peer-mapped receive-buffer pointers,
-// cursors[p] holds the first element of this rank's region in partition p's receive buffer (from the all-gathered count
-// matrix). Must follow partition_count() on the same keys and workspace.
-cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
-                           void* const* peer_keys, uint32_t* const* peer_rows, const unsigned long long* cursors, void* workspace, int64_t workspace_bytes,
-                           cudaStream_t stream) {
-  if (n_parts < 1 || n_parts > PART_MAX || workspace_bytes < partition_workspace_bytes(n, n_parts)) return cudaErrorInvalidValue;
-  unsigned long long* mat = reinterpret_cast<unsigned long long*>(workspace);
-  k_part_scan<<<(n_parts + 31) / 32, PSCAN_THREADS, 0, stream>>>(mat, part_grid(n), n_parts, part_totals(workspace, n_parts), nullptr, cursors);
-  if (key_bytes == 4) launch_scatter<int32_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, mat, PART_SEL_OWNER, false, stream);
-  else                launch_scatter<int64_t>(keys, rows, row_base, n, n_parts, peer_keys, peer_rows, mat, PART_SEL_OWNER, false, stream);
   return cudaGetLastError();
 }
 

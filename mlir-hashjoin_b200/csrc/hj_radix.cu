@@ -1,0 +1,290 @@
+// hj_radix.cu — K7: radix join for build relations whose hash table would not stay in L2 (> 48 MB of buckets).
+//
+// Replaces, for those sizes, the global open-addressing table (K1/K2/K4 in hj_kernels.cu; the reference's chained table,
+// join_v1.mlir:25-39,213-277) by the plan the reference lists as left out (projectDescription.md:24, "partitioned hash-join"):
+//   build   both passes of K5 (hj_partition.cu) split the build relation into 2^(b1+b2) partitions of <= ~4 096 (key, row id) tuples on
+//           the top bits of radix_hash(key); the partitioned copy + its offsets ARE the table (no clear, no global atomics);
+//   count   the probe relation is partitioned the same way; a work item = (partition, <= 16 384 probe tuples of it). A CTA takes items
+//           by ticket, builds the partition's table in SHARED memory (8 192 slots, one ATOMS.CAS per tuple on the row word — EMPTY is
+//           the row id 0xFFFFFFFF, so every key value stays legal), streams its probe tuples through it and writes the item's match
+//           count; K3 (the same scan as the other layouts) turns item counts into offsets and the total;
+//   write   the same items again: the table is rebuilt with row ids, every warp ranks the matches of its 32 probe tuples with a ballot,
+//           claims a run of the item's output range with one shared-memory atomic and stores the pairs (order is free: shared.cpp:168-171).
+// Duplicate build keys need nothing special (equal keys sit in one probe sequence and every occupied slot of it is compared); a partition
+// larger than the table (heavy skew) is joined in rounds of RJ_CAP build tuples; a hot probe key only makes more items.
+#include <algorithm>
+#include <cstdio>
+#include "hj_common.cuh"
+#include "hj_kernels.cuh"
+
+namespace hj {
+
+constexpr int RJ_THREADS = 512;
+constexpr int RJ_SLOTS = 8192;          // shared-memory table slots
+constexpr int RJ_CAP = 5632;            // build tuples per round (load factor <= 0.69)
+constexpr int RJ_TARGET = 4096;         // partitions are sized so that the AVERAGE build partition is at most this (sigma = 64 for uniform hashes)
+constexpr int RJ_ITEM_ROWS = 16384;     // probe tuples per work item
+constexpr int RJ_MAX_BITS = 16;         // two passes of <= 8 bits
+
+static inline int64_t r256(int64_t x) { return (x + 255) / 256 * 256; }
+
+void radix_bits(int64_t n_build, int* bits1, int* bits2) {
+  int bits = 2;
+  while (bits < RJ_MAX_BITS && ((int64_t)RJ_TARGET << bits) < n_build) bits++;
+  *bits1 = (bits + 1) / 2; *bits2 = bits - *bits1;
+}
+int64_t radix_max_items(int64_t n_probe) { return (n_probe + RJ_ITEM_ROWS - 1) / RJ_ITEM_ROWS + ((int64_t)1 << RJ_MAX_BITS) + 1; }
+
+// ---- table body in the radix layout: [keys][row ids][offsets u32 x (parts + 1)][pass-1 keys][pass-1 row ids][partition workspace] ----
+struct RadixArea { char* keys; uint32_t* rows; uint32_t* offsets; char* tmp_keys; uint32_t* tmp_rows; void* ws; int64_t ws_bytes; };
+static int64_t radix_area_bytes(int64_t n, int key_bytes, int bits1, int bits2) {
+  return 2 * (r256(n * key_bytes) + r256(n * 4)) + r256((((int64_t)1 << (bits1 + bits2)) + 1) * 4) + radix_partition2_workspace_bytes(n, bits1, bits2);
+}
+static RadixArea radix_area(char* base, int64_t n, int key_bytes, int bits1, int bits2) {
+  RadixArea a;
+  a.keys = base; base += r256(n * key_bytes);
+  a.rows = reinterpret_cast<uint32_t*>(base); base += r256(n * 4);
+  a.offsets = reinterpret_cast<uint32_t*>(base); base += r256((((int64_t)1 << (bits1 + bits2)) + 1) * 4);
+  a.tmp_keys = base; base += r256(n * key_bytes);
+  a.tmp_rows = reinterpret_cast<uint32_t*>(base); base += r256(n * 4);
+  a.ws = base; a.ws_bytes = radix_partition2_workspace_bytes(n, bits1, bits2);
+  return a;
+}
+int64_t radix_table_bytes(int64_t n_build, int key_bytes) {
+  int b1, b2; radix_bits(n_build, &b1, &b2);
+  return radix_area_bytes(n_build, key_bytes, b1, b2);
+}
+// probe side: the partition count is the TABLE's, unknown when the scratch is sized: room for the most partitions there can be
+struct RadixScratch { RadixArea a; unsigned long long* item_start; RjItem* items; int64_t max_items; };
+static int64_t radix_items_bytes(int64_t n_probe) {
+  return r256((((int64_t)1 << RJ_MAX_BITS) + 1 + 264) * 8) + r256(radix_max_items(n_probe) * (int64_t)sizeof(RjItem));
+}
+int64_t radix_scratch_bytes(int64_t n_probe, int key_bytes) { return radix_area_bytes(n_probe, key_bytes, 8, 8) + radix_items_bytes(n_probe); }
+static RadixScratch radix_scratch(char* base, int64_t n_probe, int key_bytes, int bits1, int bits2) {
+  RadixScratch s;
+  s.max_items = radix_max_items(n_probe);
+  s.item_start = reinterpret_cast<unsigned long long*>(base);
+  s.items = reinterpret_cast<RjItem*>(base + r256((((int64_t)1 << RJ_MAX_BITS) + 1 + 264) * 8));
+  s.a = radix_area(base + radix_items_bytes(n_probe), n_probe, key_bytes, bits1, bits2);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// build: partition the build relation, record the layout in the header
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_rj_header(TableHeader* hdr, uint32_t bits1, uint32_t bits2, unsigned long long keys_off, unsigned long long rows_off, unsigned long long offs_off) {
+  hdr->mode = MODE_RADIX; hdr->rj_bits1 = bits1; hdr->rj_bits2 = bits2; hdr->rj_keys_off = keys_off; hdr->rj_rows_off = rows_off; hdr->rj_offs_off = offs_off;
+}
+
+cudaError_t radix_build(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base, TableHeader* hdr, char* body, int64_t body_bytes,
+                        cudaStream_t stream) {
+  int b1, b2; radix_bits(nR, &b1, &b2);
+  if (body_bytes < radix_area_bytes(nR, key_bytes, b1, b2)) return cudaErrorInvalidValue;
+  const RadixArea a = radix_area(body, nR, key_bytes, b1, b2);
+  cudaError_t e = radix_partition2(R, payload, row_base, nR, key_bytes, b1, b2, a.tmp_keys, a.tmp_rows, a.keys, a.rows, a.offsets, a.ws, a.ws_bytes, stream);
+  if (e != cudaSuccess) return e;
+  k_rj_header<<<1, 1, 0, stream>>>(hdr, (uint32_t)b1, (uint32_t)b2, (unsigned long long)(a.keys - body), (unsigned long long)(reinterpret_cast<char*>(a.rows) - body),
+                                   (unsigned long long)(reinterpret_cast<char*>(a.offsets) - body));
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// work items
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rj_item_counts(const uint32_t* __restrict__ offR, const uint32_t* __restrict__ offS, uint32_t n_parts, unsigned long long* __restrict__ item_start) {
+  const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= n_parts) return;
+  const uint32_t ns = offS[q + 1] - offS[q], nr = offR[q + 1] - offR[q];
+  item_start[q] = (ns && nr) ? (ns + RJ_ITEM_ROWS - 1) / RJ_ITEM_ROWS : 0u;      // a partition without build tuples matches nothing: no items
+}
+__global__ void __launch_bounds__(256) k_rj_items(const uint32_t* __restrict__ offR, const uint32_t* __restrict__ offS, uint32_t n_parts,
+                                                  const unsigned long long* __restrict__ item_start, RjItem* __restrict__ items) {
+  const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= n_parts) return;
+  const unsigned long long first = item_start[q], cnt = item_start[q + 1] - first;
+  const uint32_t s0 = offS[q], s1 = offS[q + 1], r0 = offR[q], r1 = offR[q + 1];
+  for (unsigned long long j = 0; j < cnt; j++) {
+    const uint32_t a = s0 + (uint32_t)j * RJ_ITEM_ROWS;
+    items[first + j] = RjItem{a, s1 - a < (uint32_t)RJ_ITEM_ROWS ? s1 : a + RJ_ITEM_ROWS, r0, r1};
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the join kernel: WRITE = false counts the matches of every item, WRITE = true emits them at the item's offset
+// ---------------------------------------------------------------------------------------------------------
+template <typename K> struct RjSmem { K tkey[RJ_SLOTS]; uint32_t trow[RJ_SLOTS]; };
+
+template <typename K>
+__device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, uint32_t r0, uint32_t nr, bool with_rows, uint64_t pol) {
+  #pragma unroll
+  for (int i = 0; i < RJ_SLOTS / (RJ_THREADS * 4); i++) reinterpret_cast<uint4*>(sm.trow)[i * RJ_THREADS + threadIdx.x] = make_uint4(ROW_NONE, ROW_NONE, ROW_NONE, ROW_NONE);
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < nr; i0 += RJ_THREADS * 4) {
+    K key[4]; uint32_t row[4];
+    #pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t i = i0 + u * RJ_THREADS + threadIdx.x;
+      key[u] = i < nr ? ld_stream<K>(Rk + r0 + i, pol) : K(0);
+      row[u] = (with_rows && i < nr) ? ld_stream<uint32_t>(Rr + r0 + i, pol) : 0u;           // counting needs no row ids: any value but EMPTY marks the slot
+    }
+    #pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (i0 + u * RJ_THREADS + threadIdx.x < nr) {
+        uint32_t slot = radix_hash<K>(key[u]) & (RJ_SLOTS - 1);
+        while (atomicCAS(&sm.trow[slot], ROW_NONE, row[u]) != ROW_NONE) slot = (slot + 1) & (RJ_SLOTS - 1);   // nr <= RJ_CAP < RJ_SLOTS: there is a free slot
+        sm.tkey[slot] = key[u];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <typename K, bool WRITE>
+__global__ void __launch_bounds__(RJ_THREADS, 2) k_rj_join(const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, const K* __restrict__ Sk, const uint32_t* __restrict__ Sr,
+                                                           const RjItem* __restrict__ items, const unsigned long long* __restrict__ n_items_ptr, unsigned long long* tickets,
+                                                           unsigned long long* __restrict__ item_totals,       // count: out (matches per item); write: in (exclusive offsets)
+                                                           int32_t* __restrict__ outR, int32_t* __restrict__ outS,
+                                                           const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows) {
+  extern __shared__ __align__(16) unsigned char rj_raw[];
+  RjSmem<K>& sm = *reinterpret_cast<RjSmem<K>*>(rj_raw);
+  __shared__ TicketQueue tq;
+  __shared__ unsigned long long red[33];
+  __shared__ uint32_t cursor;
+  const long long n_items = (long long)*n_items_ptr;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint64_t pol = policy_evict_first();
+  long long item = ticket_first(tickets, &tq);
+  for (uint32_t it = 0; item < n_items; it++) {
+    const long long pending = ticket_prefetch(tickets);
+    const RjItem w = items[item];
+    unsigned long long cnt = 0;
+    unsigned long long obase = 0;
+    if (WRITE) { obase = item_totals[item]; if (threadIdx.x == 0) cursor = 0; }
+    for (uint32_t r0 = w.r0; r0 < w.r1; r0 += RJ_CAP) {
+      const uint32_t nr = w.r1 - r0 < (uint32_t)RJ_CAP ? w.r1 - r0 : (uint32_t)RJ_CAP;
+      rj_build_round<K>(sm, Rk, Rr, r0, nr, WRITE, pol);
+      constexpr int U = 4;
+      if (!WRITE) {
+        uint32_t c = 0;
+        for (uint32_t j0 = w.s0; j0 < w.s1; j0 += RJ_THREADS * U) {
+          K key[U];
+          #pragma unroll
+          for (int u = 0; u < U; u++) { const uint32_t j = j0 + u * RJ_THREADS + threadIdx.x; key[u] = j < w.s1 ? ld_stream<K>(Sk + j, pol) : K(0); }
+          #pragma unroll
+          for (int u = 0; u < U; u++) {
+            if (j0 + u * RJ_THREADS + threadIdx.x < w.s1) {
+              uint32_t slot = radix_hash<K>(key[u]) & (RJ_SLOTS - 1);
+              while (sm.trow[slot] != ROW_NONE) { c += sm.tkey[slot] == key[u]; slot = (slot + 1) & (RJ_SLOTS - 1); }
+            }
+          }
+        }
+        cnt += c;
+      } else {
+        // warp-synchronous: every warp walks the probe sequences of its 32 tuples in lockstep; the matches of one step are ranked
+        // with a ballot and get a contiguous run of the item's output range from ONE shared-memory atomic
+        for (uint32_t j0 = w.s0 + (threadIdx.x & ~31u); j0 < w.s1; j0 += RJ_THREADS * U) {        // warp-uniform bounds
+          K key[U]; uint32_t srow[U];
+          #pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t j = j0 + u * RJ_THREADS + lane;
+            key[u] = j < w.s1 ? ld_stream<K>(Sk + j, pol) : K(0);
+            srow[u] = j < w.s1 ? ld_stream<uint32_t>(Sr + j, pol) : 0u;
+          }
+          #pragma unroll
+          for (int u = 0; u < U; u++) {
+            if (j0 + u * RJ_THREADS >= w.s1) break;                                               // warp-uniform
+            bool active = j0 + u * RJ_THREADS + lane < w.s1;
+            uint32_t prow = srow[u];
+            if (!carried_rows) prow = probe_payload ? (active ? probe_payload[prow] : 0u) : probe_row_base + prow;   // the copy carries original indices
+            uint32_t slot = radix_hash<K>(key[u]) & (RJ_SLOTS - 1);
+            while (__any_sync(0xffffffffu, active)) {
+              bool hit = false; uint32_t brow = 0;
+              if (active) {
+                brow = sm.trow[slot];
+                if (brow == ROW_NONE) active = false;
+                else { hit = sm.tkey[slot] == key[u]; slot = (slot + 1) & (RJ_SLOTS - 1); }
+              }
+              const unsigned hm = __ballot_sync(0xffffffffu, hit);
+              if (hm) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cursor, (uint32_t)__popc(hm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) {
+                  const unsigned long long pos = obase + base + __popc(hm & lt);
+                  outR[pos] = (int32_t)brow; outS[pos] = (int32_t)prow;
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();                                            // the table is rebuilt by the next round / item
+    }
+    if (!WRITE) {
+      cnt = block_reduce_sum(cnt, red);
+      if (threadIdx.x == 0) item_totals[item] = cnt;
+    }
+    item = ticket_advance(&tq, it, pending);
+  }
+}
+
+template <typename Kern>
+static unsigned rj_grid(Kern kern, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RJ_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (unsigned)(per_sm * sms);
+}
+
+template <typename K, bool WRITE>
+static cudaError_t rj_launch(const RadixArea& r, const RadixScratch& s, unsigned long long* ticket, unsigned long long* item_totals, int32_t* outR, int32_t* outS,
+                             const uint32_t* probe_payload, uint32_t probe_row_base, int carried_rows, uint32_t n_parts, cudaStream_t stream) {
+  auto kern = k_rj_join<K, WRITE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RjSmem<K>));
+  if (e != cudaSuccess) return e;
+  kern<<<rj_grid(kern, sizeof(RjSmem<K>)), RJ_THREADS, sizeof(RjSmem<K>), stream>>>((const K*)r.keys, r.rows, (const K*)s.a.keys, s.a.rows, s.items, s.item_start + n_parts, ticket,
+                                                                                   item_totals, outR, outS, probe_payload, probe_row_base, carried_rows);
+  return cudaGetLastError();
+}
+
+// count: partition the probe relation like the table, make the items, count per item, scan. hdr_host: the table header as read back by
+// the caller. item_totals: u64[radix_max_items(nS) + 1] (the scratch's offsets array); total_out: where the scan leaves the result size.
+cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area,
+                        unsigned long long* item_totals, unsigned long long* scan_block_sums, unsigned long long* ticket, unsigned long long* total_out,
+                        bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+  const int b1 = (int)hdr_host.rj_bits1, b2 = (int)hdr_host.rj_bits2;
+  const uint32_t n_parts = 1u << (b1 + b2);
+  const RadixScratch s = radix_scratch(scratch_area, nS, key_bytes, b1, b2);
+  RadixArea r;
+  r.keys = const_cast<char*>(body) + hdr_host.rj_keys_off; r.rows = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_rows_off);
+  r.offsets = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_offs_off);
+  cudaError_t e = radix_partition2(S, carry_rows ? probe_payload : nullptr, carry_rows ? probe_row_base : 0u, nS, key_bytes, b1, b2, s.a.tmp_keys, s.a.tmp_rows, s.a.keys, s.a.rows,
+                                   s.a.offsets, s.a.ws, s.a.ws_bytes, stream);
+  if (e != cudaSuccess) return e;
+  k_rj_item_counts<<<(n_parts + 255) / 256, 256, 0, stream>>>(r.offsets, s.a.offsets, n_parts, s.item_start);
+  launch_scan(s.item_start, n_parts, s.item_start + n_parts + 1, nullptr, stream);
+  k_rj_items<<<(n_parts + 255) / 256, 256, 0, stream>>>(r.offsets, s.a.offsets, n_parts, s.item_start, s.items);
+  e = cudaMemsetAsync(item_totals, 0, (size_t)(s.max_items + 1) * 8, stream);
+  if (e != cudaSuccess) return e;
+  e = key_bytes == 4 ? rj_launch<int32_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, n_parts, stream)
+                     : rj_launch<int64_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, n_parts, stream);
+  if (e != cudaSuccess) return e;
+  launch_scan(item_totals, s.max_items, scan_block_sums, total_out, stream);
+  return cudaGetLastError();
+}
+
+cudaError_t radix_write(int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area, unsigned long long* item_offsets,
+                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+  const int b1 = (int)hdr_host.rj_bits1, b2 = (int)hdr_host.rj_bits2;
+  const uint32_t n_parts = 1u << (b1 + b2);
+  const RadixScratch s = radix_scratch(scratch_area, nS, key_bytes, b1, b2);
+  RadixArea r;
+  r.keys = const_cast<char*>(body) + hdr_host.rj_keys_off; r.rows = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_rows_off);
+  r.offsets = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_offs_off);
+  return key_bytes == 4 ? rj_launch<int32_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, n_parts, stream)
+                        : rj_launch<int64_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, n_parts, stream);
+}
+
+}  // namespace hj

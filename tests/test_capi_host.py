@@ -19,7 +19,7 @@ def test_header_symbols_exported(lib):
     from mlir_hashjoin_b200 import _lib
     header = (ROOT / "include" / "hashjoin_b200.h").read_text()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    declared = set(re.findall(r"^\s*(?:const\s+char\*|void|int32_t|int64_t)\s+(\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:const\s+char\*|void|int32_t|int64_t|uint32_t)\s+(\w+)\s*\(", header, flags=re.M))
     assert len(declared) >= 50
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
@@ -77,12 +77,15 @@ def test_timer_format(lib, capfd):
 
 def test_workspace_queries(lib):
     assert lib.hjTableBytes(0, 4) >= 256 + 64
-    # room for whichever layout the build picks: inline buckets at load 0.5 (16 / 32 bytes per row) or the grouped layout
-    # for duplicate keys (u32 row ids + 16-byte slots at load <= 0.8: 24 bytes per row); tables beyond L2 reach add a reorder area
+    # room for whichever layout the build picks: inline buckets at load 0.5 (16 / 32 bytes per row), the grouped layout for duplicate
+    # keys (u32 row ids + 16-byte slots at load <= 0.8: 24 bytes per row) or, beyond L2 reach, the radix layout (two copies of
+    # (key, row id) + offsets + partition workspace)
     for n in (1 << 10, 1 << 20):
         assert 24 * n <= lib.hjTableBytes(n, 4) - 256 <= 24 * n + 1024
         assert 32 * n <= lib.hjTableBytes(n, 8) - 256 <= 32 * n + 1024
-    assert lib.hjTableBytes(1 << 24, 4) - 256 >= (24 + 8) * (1 << 24)        # + slice-ordered copy of the build relation (key + index)
+    assert lib.hjTableBytes(1 << 24, 4) - 256 >= 24 * (1 << 24)
+    assert lib.hjTableBytes(1 << 24, 8) - 256 >= 2 * 12 * (1 << 24)
+    assert lib.hjScratchBytes(1 << 24, 8) >= (8 + 2 * 12) * (1 << 24)
     assert lib.hjTableBytes(10, 5) < 0 and lib.hjScratchBytes(-1, 4) < 0
     assert lib.hashJoinTableBytes(1000) == lib.hjTableBytes(1000, 4)
     assert lib.hashJoinScratchBytesI64(1000) == lib.hjScratchBytes(1000, 8)
@@ -115,6 +118,17 @@ def test_argument_validation_of_native_entry_points(lib):
     assert lib.hjJoinFused(p, 10, 4, p, None, 0, p, p, 10, None, 0, None) < 0        # no scratch
     assert lib.hjJoinFused(p, 10, 4, p, p, buf.size, None, None, 10, None, 0, None) < 0   # capacity without result columns
     assert lib.hjTableLayout(None, None) < 0
+    # workspace alignment: buckets are 32-byte vector loads in 64-byte pairs; a table at +16 must be refused, not faulted on
+    base = (p + 255) & ~255
+    assert lib.hjBuild(base, 16, 4, None, 0, base + 16, 2048, None) == -22 and b"64-byte" in lib.hjLastErrorString()
+    assert lib.hjBuildEx(base, 16, 4, None, 0, base + 1024, 2048, 3, None) == -22          # unknown policy bits (before any CUDA call)
+    assert lib.hjCountAsync(base, 16, 4, base + 16, base + 1024, 1 << 30, None) == -22
+    assert lib.hjCountAsync(base, 16, 4, base + 1024, base + 16, 1 << 30, None) == -22
+    assert lib.hjWrite(base, 16, 4, base + 16, base + 1024, base, base, None, 0, None) == -22
+    # row ids are 32-bit and 0xFFFFFFFF is the EMPTY marker: a row base that would reach it is refused
+    assert lib.hjBuild(base, 16, 4, None, 0xFFFFFFF0, base + 1024, 2048, None) == -22
+    assert lib.hjJoinHost(p, 16, p, 1 << 32, 4, None, None, 0) == -22                      # probe rows beyond 32-bit row ids
+    assert lib.hjDefaultPolicy() & 3 in (0, 1, 2)
     assert lib.hjProbePath(None, 10, 4, None) < 0
     assert lib.hjPartitionWorkspaceBytes(1 << 20, 8) > 0
     assert lib.hjLastErrorString()

@@ -388,17 +388,22 @@ def test_mid_size_vs_oracle(lib, cuda, oracle):
     assert torch.unique(bb).numel() == bb.numel()
 
 
+@pytest.mark.parametrize("kb,nR,nS", [(4, 6_000_000, 20_000_003), (8, 4_000_000, 12_000_003)])
 @pytest.mark.parametrize("dups", [False, True])
-def test_big_table_slice_ordered_path(lib, cuda, oracle, dups):
-    """Tables beyond L2 reach (> 48 MB) are built and probed in table-slice order (K5 reorders both relations on the
-    bucket hash). 6M sparse build keys, unique (inline layout) and 3x duplicated (grouped layout), with payload columns,
-    against the OpenMP oracle: count + order-independent digest, plus key equality of every pair."""
+def test_big_table_path(lib, cuda, oracle, layout, dups, kb, nR, nS):
+    """Tables beyond L2 reach (> 48 MB of inline buckets): both relations are radix-partitioned first (K5) and joined partition by
+    partition. Sparse build keys (odd multiplier, no dense range), i32 and i64, unique (inline layout) and 3x duplicated (grouped
+    layout), with payload columns, against the OpenMP oracle: count + order-independent digest, plus key equality of every pair.
+    Also: the same join with the big-table path switched off, and the reference's call sequence (countRows has no probe row ids;
+    hash_join states them at count time through hjCountRows)."""
     import torch
     from mlir_hashjoin_b200 import datagen, join
-    nR, nS = 6_000_000, 20_000_003
+    if layout in ("cache", "lists"):
+        pytest.skip("sparse keys never take the direct-address layout: same code path as auto / hash-lists")
     dom = nR // 3 if dups else nR
-    b = datagen.RelationSpec(nR, 4, datagen.KIND_FK if dups else datagen.KIND_UNIQUE, 7, 0, dom, 0, 0x9E3779B1)
-    p = datagen.RelationSpec(nS, 4, datagen.KIND_UNIFORM, 8, 0, 2 * dom, 0, 0x9E3779B1)
+    mul = 0x9E3779B1 if kb == 4 else datagen.ODD_MUL64
+    b = datagen.RelationSpec(nR, kb, datagen.KIND_FK if dups else datagen.KIND_UNIQUE, 7, 0, dom, 0, mul)
+    p = datagen.RelationSpec(nS, kb, datagen.KIND_UNIFORM, 8, 0, 2 * dom, 0, mul)
     dR, dS = datagen.generate(b), datagen.generate(p)
     pr = torch.arange(nR, dtype=torch.int32, device=cuda) * 3 + 1
     ps = torch.arange(nS, dtype=torch.int32, device=cuda) + 77
@@ -412,14 +417,35 @@ def test_big_table_slice_ordered_path(lib, cuda, oracle, dups):
     a2, b2 = join.hash_join(dR, dS, buildPayload=pr, probePayload=ps)
     lib.hjSetLocality(1)
     assert join.pair_digest(a2, b2) == join.pair_digest(a, bb)
-    # hash_join knows the probe row ids at count time (hjCountRows: the slice-ordered copy carries them). The reference's call
-    # sequence does not (countRows has no such argument): the copy then carries the original index and the write pass gathers.
+    # the reference's call sequence: row ids only at write time (payload column), and none at all (row base)
     table = join.allocateHashTable(nR, None, dR.dtype, cuda)
     join.buildTable(dR, table, pr)
     n = join.countRows(dS, table)
     a3 = torch.empty(n, dtype=torch.int32, device=cuda); b3 = torch.empty(n, dtype=torch.int32, device=cuda)
     join.probeRelation(dS, table, a3, b3, ps)
     assert n == a.numel() and join.pair_digest(a3, b3) == join.pair_digest(a, bb)
+    join.buildTable(dR, table, None, 5)
+    n = join.countRows(dS, table)
+    assert n == oa.size
+    join.probeRelation(dS, table, a3, b3, None, 9)
+    assert join.pair_digest(a3, b3) == oracle.pair_digest(oa + 5, ob + 9)
+
+
+def test_c4_shape_fk_zipf_i64(lib, cuda, oracle, layout):
+    """BASELINE.json config 4 at 1/8 scale: int64 keys, 2^22 build rows with every key exactly 4 times (FK 1:N), 2^24
+    Zipf(1.0)-skewed probe keys -> 2^26 pairs (output-materialisation stress, hot keys). Count + digest vs the oracle."""
+    import torch
+    from mlir_hashjoin_b200 import datagen, join
+    if layout in ("cache", "lists", "hash-lists"):
+        pytest.skip("duplicate sparse keys: same code path as auto / hash")
+    cfg = datagen.shrink(datagen.config("C4"), 1 << 22, 1 << 24)
+    dR, dS = datagen.generate(cfg.build), datagen.generate(cfg.probe)
+    a, bb = join.hash_join(dR, dS)
+    assert a.numel() == 4 << 24
+    oa, ob = oracle.join(dR.cpu().numpy(), dS.cpu().numpy(), threads=0)
+    assert a.numel() == oa.size
+    assert join.pair_digest(a, bb) == oracle.pair_digest(oa, ob)
+    assert bool((dR[a.long()] == dS[bb.long()]).all())
 
 
 @pytest.mark.slow
