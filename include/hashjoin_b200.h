@@ -105,6 +105,9 @@ int32_t hashJoinBuildI64(HJ_MEMREF(int64_t, R), HJ_MEMREF(int8_t, table));
 int64_t hashJoinCountI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch));
 int32_t hashJoinWriteI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEMREF(int8_t, scratch),
                          HJ_MEMREF(int32_t, outR), HJ_MEMREF(int32_t, outS));
+/* late gather: out[k] = column[rowIds[k]] for one i32 payload column (what nested-loop.mlir:165-187 does per matched row) */
+int32_t hashJoinGather(HJ_MEMREF(int32_t, column), HJ_MEMREF(int32_t, rowIds), HJ_MEMREF(int32_t, out));
+int32_t _mlir_ciface_hashJoinGather(HjMemRef1D* column, HjMemRef1D* rowIds, HjMemRef1D* out);
 int32_t _mlir_ciface_hashJoinBuild(HjMemRef1D* R, HjMemRef1D* table);
 int64_t _mlir_ciface_hashJoinCount(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch);
 int32_t _mlir_ciface_hashJoinWrite(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS);
@@ -161,6 +164,33 @@ int64_t hjCountRows(const void* dS, int64_t nS, int32_t keyBytes, const void* dT
  * unique or the table is radix-partitioned (use hjCount + hjWrite). Synchronous. */
 int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
                     int32_t* dOutR, int32_t* dOutS, int64_t capacity, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+/* ---- the operators either side of the path ----
+ * Semi-join (key-only mode): the probe rows that have at least one match, each exactly once, whatever the multiplicity of the build
+ * keys. Same two-phase shape: hjSemiJoinCount returns the size, hjSemiJoinWrite fills dOutS (probe row ids: payload value, else
+ * probeRowBase + j; state the same ones in both calls). Count-only: hjCount alone (no write pass is needed to know the size). */
+int64_t hjSemiJoinCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                        const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+int32_t hjSemiJoinWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch, int32_t* dOutS,
+                        const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream);
+/* Late gather: dOut[k] = dColumn[dRowIds[k] - rowBase] for a payload column of 4- or 8-byte elements; dRowIds is one column of the
+ * pair stream. Asynchronous. (nested-loop.mlir:165-187 copies matched rows inline; projectDescription.md:26 lists it as left out.) */
+int32_t hjGather(const void* dColumn, int32_t elemBytes, const int32_t* dRowIds, int64_t n, uint32_t rowBase, void* dOut, void* stream);
+/* Row materialisation in the reference's layout (nested-loop.mlir:165-187): result row k = the xCols columns of row dPairX[k] of
+ * row-major table X, then columns 1 .. yCols-1 of row dPairY[k] of table Y (the key column is not stored twice). dResult: row-major
+ * i32 [nPairs][xCols + yCols - 1]. hjExtractColumn copies column `col` of a row-major table into a contiguous key column. */
+int32_t hjMaterializeRows(const int32_t* dTableX, int32_t xCols, const int32_t* dTableY, int32_t yCols, const int32_t* dPairX, const int32_t* dPairY,
+                          int64_t nPairs, int32_t* dResult, void* stream);
+int32_t hjExtractColumn(const int32_t* dTable, int64_t rows, int32_t cols, int32_t col, int32_t* dOut, void* stream);
+/* Multi-column keys (projectDescription.md:28): two i32 key columns become one i64 key (a bijection), joined with keyBytes = 8. */
+int32_t hjPackKeys2x32(const int32_t* dA, const int32_t* dB, int64_t n, int64_t* dOut, void* stream);
+/* Selection (Experiments/selection.mlir:34-155): rows with `value OP constant`, count -> scan -> compacted write; output in input
+ * order. dtype: 0 i32, 1 i64, 2 f32, 3 f64 (constant in iconst for integers, fconst for floats; comparisons are ordered: NaN fails).
+ * op: 0 <, 1 <=, 2 >, 3 >=, 4 ==, 5 !=. hjSelectCount is synchronous and returns the size; hjSelectWrite fills dOutValues (same
+ * dtype) and / or dOutRows (rowBase + i), either may be NULL. dScratch: hjSelectScratchBytes(n), 256-byte aligned. */
+int64_t hjSelectScratchBytes(int64_t n);
+int64_t hjSelectCount(const void* dColumn, int64_t n, int32_t dtype, int32_t op, int64_t iconst, double fconst, void* dScratch, int64_t scratchBytes, void* stream);
+int32_t hjSelectWrite(const void* dColumn, int64_t n, int32_t dtype, int32_t op, int64_t iconst, double fconst, const void* dScratch,
+                      void* dOutValues, int32_t* dOutRows, uint32_t rowBase, void* stream);
 /* K5. Radix partition on the key hash into nParts (<= 256) contiguous ranges; dOffsets: u64[nParts+1]. Asynchronous. */
 int64_t hjPartitionWorkspaceBytes(int64_t n, int32_t nParts);
 int32_t hjPartition(const void* dKeys, const uint32_t* dRows, uint32_t rowBase, int64_t n, int32_t keyBytes, int32_t nParts,
@@ -178,11 +208,18 @@ int32_t hjPairDigest(const int32_t* dOutR, const int32_t* dOutS, int64_t n, uint
 /* Seeded device generators, bit-identical to the oracle's (kinds: 0 index, 1 unique, 2 uniform, 3 mixed, 4 fk, 5 zipf). */
 int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64_t seed, int64_t lo, uint64_t domain,
                    uint32_t p16, uint64_t keyMul, int64_t indexBase, uint64_t nTotal, void* stream);
+/* The keys of rows dRowIds[0 .. n) of the relation the same arguments describe (nTotal = its row count): lets a parity guard check
+ * key equality of result pairs whose rows live on other ranks. */
+int32_t hjGenerateAt(void* dOut, const uint32_t* dRowIds, int64_t n, int32_t keyBytes, int32_t kind, uint64_t seed, int64_t lo, uint64_t domain,
+                     uint32_t p16, uint64_t keyMul, uint64_t nTotal, void* stream);
 /* End-to-end convenience with HOST buffers (what the reference's @main does around the kernels, join_v1.mlir:558-615):
  * H2D of both relations, build, count, write, D2H of the pairs. Returns the result size; pairs are copied only when
  * hOutR/hOutS are non-NULL and capacity >= result size. Synchronous. */
 int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes,
                    int32_t* hOutR, int32_t* hOutS, int64_t capacity);
+/* hjJoinHost streams the probe relation through a ring of three device chunks and the pairs through two result slots, so the probe
+ * side may be larger than GPU memory (projectDescription.md:23); the build side and its table must fit. Rows per chunk (default 2^24). */
+void hjSetHostChunkRows(int64_t rows);
 /* 0 forces the hash layout; 1: builds whose key range is at most 4x the row count use a direct-address table (with the match cache);
  * 2 (default): additionally a unique, gap-free key range (dense surrogate keys) is counted by range test alone and looked up once, in
  * the write pass (config 2: 1.84 instead of 1.99 ms). The policy in force at hjBuild decides. */

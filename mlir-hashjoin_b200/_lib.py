@@ -49,6 +49,8 @@ _SIGNATURES = {
     "hashJoinBuildI64": (_i32, _MEMREF * 2),
     "hashJoinCountI64": (_i64, _MEMREF * 3),
     "hashJoinWriteI64": (_i32, _MEMREF * 5),
+    "hashJoinGather": (_i32, _MEMREF * 3),
+    "_mlir_ciface_hashJoinGather": (_i32, [_vp] * 3),
     "_mlir_ciface_hashJoinBuild": (_i32, [_vp] * 2),
     "_mlir_ciface_hashJoinCount": (_i64, [_vp] * 3),
     "_mlir_ciface_hashJoinWrite": (_i32, [_vp] * 5),
@@ -74,6 +76,17 @@ _SIGNATURES = {
     "hjPartitionPush": (_i32, [_vp, _vp, _u32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "hjPairDigest": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "hjGenerate": (_i32, [_vp, _i64, _i32, _i32, _u64, _i64, _u64, _u32, _u64, _i64, _u64, _vp]),
+    "hjSemiJoinCount": (_i64, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _u32, _vp]),
+    "hjSemiJoinWrite": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "hjGather": (_i32, [_vp, _i32, _vp, _i64, _u32, _vp, _vp]),
+    "hjMaterializeRows": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "hjExtractColumn": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "hjPackKeys2x32": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "hjSelectScratchBytes": (_i64, [_i64]),
+    "hjSelectCount": (_i64, [_vp, _i64, _i32, _i32, _i64, C.c_double, _vp, _i64, _vp]),
+    "hjSelectWrite": (_i32, [_vp, _i64, _i32, _i32, _i64, C.c_double, _vp, _vp, _vp, _u32, _vp]),
+    "hjSetHostChunkRows": (None, [_i64]),
+    "hjGenerateAt": (_i32, [_vp, _vp, _i64, _i32, _i32, _u64, _i64, _u64, _u32, _u64, _u64, _vp]),
     "hjJoinHost": (_i64, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64]),
     "hjSetAllowDense": (None, [_i32]),
     "hjSetLocality": (None, [_i32]),

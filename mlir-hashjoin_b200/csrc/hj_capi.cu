@@ -49,7 +49,7 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
-DevBuf g_hR, g_hS, g_hT, g_hSc, g_hOr, g_hOs;
+DevBuf g_hR, g_hS, g_hT, g_hSc, g_hOr[2], g_hOs[2];
 
 std::chrono::high_resolution_clock::time_point g_timer_start;
 uint64_t g_seed_r = 0, g_seed_s = 0;
@@ -172,14 +172,14 @@ int32_t hjBuildEx(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* 
 uint32_t hjDefaultPolicy(void) { return hj::default_policy(); }
 
 static int32_t count_async(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
-                           bool carryRows, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+                           bool carryRows, const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream, bool semi = false) {
   if (!key_ok(keyBytes) || nS < 0 || (nS > 0 && !dS) || !dTable || !dScratch) return fail(HJ_ERR_ARG, "hjCount", "null pointer or bad key width");
   if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjCount", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
   if (carryRows && !dProbePayload && (uint64_t)probeRowBase + (uint64_t)nS > 0x100000000ULL) return fail(HJ_ERR_ARG, "hjCount", "probeRowBase + nS exceeds 2^32");
   if (reinterpret_cast<uintptr_t>(dTable) & 63) return fail(HJ_ERR_ARG, "hjCount", "table workspace must be 64-byte aligned");
   if (reinterpret_cast<uintptr_t>(dScratch) & 255) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace must be 256-byte aligned");
   if (scratchBytes < hj::scratch_bytes(nS, keyBytes)) return fail(HJ_ERR_ARG, "hjCount", "scratch workspace too small (see hjScratchBytes)");
-  cudaError_t e = hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, carryRows, dProbePayload, probeRowBase, S_(stream));
+  cudaError_t e = hj::count_rows_async(dS, nS, keyBytes, dTable, dScratch, carryRows, dProbePayload, probeRowBase, semi, S_(stream));
   if (e == cudaErrorInvalidValue) return fail(HJ_ERR_STATE, "hjCount", "the table workspace holds no table built for this key width (call hjBuild first)");
   if (e != cudaSuccess) return cuda_fail("hjCount", e);
   return HJ_OK;
@@ -235,6 +235,61 @@ int32_t hjWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable
   cudaError_t e = hj::write_pairs(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, dProbePayload, probeRowBase, S_(stream));
   if (e == cudaErrorInvalidValue) return fail(HJ_ERR_STATE, "hjWrite", "the table workspace holds no table built for this key width");
   if (e != cudaSuccess) return cuda_fail("hjWrite", e);
+  return HJ_OK;
+}
+
+// ---- semi-join (key-only mode): the probe rows that have at least one match, each once ------------------------------------
+int64_t hjSemiJoinCount(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, void* dScratch, int64_t scratchBytes,
+                        const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+  int32_t rc = count_async(dS, nS, keyBytes, dTable, dScratch, scratchBytes, true, dProbePayload, probeRowBase, stream, true);
+  if (rc != HJ_OK) return rc;
+  return hjCountResult(dScratch, nS, keyBytes, stream);
+}
+int32_t hjSemiJoinWrite(const void* dS, int64_t nS, int32_t keyBytes, const void* dTable, const void* dScratch, int32_t* dOutS,
+                        const uint32_t* dProbePayload, uint32_t probeRowBase, void* stream) {
+  return hjWrite(dS, nS, keyBytes, dTable, dScratch, nullptr, dOutS, dProbePayload, probeRowBase, stream);
+}
+
+// ---- late gather / row materialisation (nested-loop.mlir:165-187) ------------------------------------------------------------
+int32_t hjGather(const void* dColumn, int32_t elemBytes, const int32_t* dRowIds, int64_t n, uint32_t rowBase, void* dOut, void* stream) {
+  if (n < 0 || (elemBytes != 4 && elemBytes != 8) || (n > 0 && (!dColumn || !dRowIds || !dOut))) return fail(HJ_ERR_ARG, "hjGather", "null pointer or element width not 4 / 8");
+  HJ_CUDA("hjGather", hj::gather_column(dColumn, elemBytes, dRowIds, n, rowBase, dOut, S_(stream)));
+  return HJ_OK;
+}
+int32_t hjMaterializeRows(const int32_t* dTableX, int32_t xCols, const int32_t* dTableY, int32_t yCols, const int32_t* dPairX, const int32_t* dPairY, int64_t nPairs,
+                          int32_t* dResult, void* stream) {
+  if (nPairs < 0 || xCols < 1 || yCols < 1 || (nPairs > 0 && (!dTableX || !dTableY || !dPairX || !dPairY || !dResult))) return fail(HJ_ERR_ARG, "hjMaterializeRows", "bad argument");
+  HJ_CUDA("hjMaterializeRows", hj::materialize_rows(dTableX, xCols, dTableY, yCols, dPairX, dPairY, nPairs, dResult, S_(stream)));
+  return HJ_OK;
+}
+int32_t hjExtractColumn(const int32_t* dTable, int64_t rows, int32_t cols, int32_t col, int32_t* dOut, void* stream) {
+  if (rows < 0 || cols < 1 || col < 0 || col >= cols || (rows > 0 && (!dTable || !dOut))) return fail(HJ_ERR_ARG, "hjExtractColumn", "bad argument");
+  HJ_CUDA("hjExtractColumn", hj::extract_column(dTable, rows, cols, col, dOut, S_(stream)));
+  return HJ_OK;
+}
+int32_t hjPackKeys2x32(const int32_t* dA, const int32_t* dB, int64_t n, int64_t* dOut, void* stream) {
+  if (n < 0 || (n > 0 && (!dA || !dB || !dOut))) return fail(HJ_ERR_ARG, "hjPackKeys2x32", "bad argument");
+  HJ_CUDA("hjPackKeys2x32", hj::pack_keys(dA, dB, n, reinterpret_cast<long long*>(dOut), S_(stream)));
+  return HJ_OK;
+}
+
+// ---- selection (Experiments/selection.mlir:34-155): count -> scan -> write ----------------------------------------------------
+int64_t hjSelectScratchBytes(int64_t n) { return n < 0 ? HJ_ERR_ARG : hj::select_scratch_bytes(n); }
+static bool select_args_ok(const void* col, int64_t n, int32_t dtype, int32_t op, const void* scratch) {
+  return n >= 0 && dtype >= 0 && dtype <= 3 && op >= 0 && op <= 5 && scratch && (n == 0 || col) && (reinterpret_cast<uintptr_t>(scratch) & 255) == 0;
+}
+int64_t hjSelectCount(const void* dColumn, int64_t n, int32_t dtype, int32_t op, int64_t iconst, double fconst, void* dScratch, int64_t scratchBytes, void* stream) {
+  if (!select_args_ok(dColumn, n, dtype, op, dScratch) || scratchBytes < hj::select_scratch_bytes(n)) return fail(HJ_ERR_ARG, "hjSelectCount", "bad argument, or scratch misaligned / too small (see hjSelectScratchBytes)");
+  if (n > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjSelectCount", "more than 2^32-1 rows (row ids are 32-bit)");
+  HJ_CUDA("hjSelectCount", hj::select_count(dColumn, n, dtype, op, iconst, fconst, dScratch, S_(stream)));
+  unsigned long long total = 0;
+  HJ_CUDA("hjSelectCount", hj::readback(&total, hj::select_total_ptr(dScratch, n), 8, S_(stream)));
+  return (int64_t)total;
+}
+int32_t hjSelectWrite(const void* dColumn, int64_t n, int32_t dtype, int32_t op, int64_t iconst, double fconst, const void* dScratch,
+                      void* dOutValues, int32_t* dOutRows, uint32_t rowBase, void* stream) {
+  if (!select_args_ok(dColumn, n, dtype, op, dScratch)) return fail(HJ_ERR_ARG, "hjSelectWrite", "bad argument or misaligned scratch");
+  HJ_CUDA("hjSelectWrite", hj::select_write(dColumn, n, dtype, op, iconst, fconst, dScratch, dOutValues, dOutRows, rowBase, S_(stream)));
   return HJ_OK;
 }
 
@@ -296,66 +351,87 @@ int32_t hjGenerate(void* dOut, int64_t n, int32_t keyBytes, int32_t kind, uint64
                    uint32_t p16, uint64_t keyMul, int64_t indexBase, uint64_t nTotal, void* stream) {
   if (!key_ok(keyBytes) || n < 0 || (n > 0 && !dOut) || kind < 0 || kind > 5) return fail(HJ_ERR_ARG, "hjGenerate", "bad argument");
   if (nTotal == 0) nTotal = (uint64_t)(indexBase + n);
-  HJ_CUDA("hjGenerate", hj::generate_keys_total(dOut, n, keyBytes, kind, seed, lo, domain, p16, keyMul, indexBase, nTotal, S_(stream)));
+  HJ_CUDA("hjGenerate", hj::generate_keys_total(dOut, n, keyBytes, kind, seed, lo, domain, p16, keyMul, indexBase, nTotal, nullptr, S_(stream)));
+  return HJ_OK;
+}
+int32_t hjGenerateAt(void* dOut, const uint32_t* dRowIds, int64_t n, int32_t keyBytes, int32_t kind, uint64_t seed, int64_t lo, uint64_t domain,
+                     uint32_t p16, uint64_t keyMul, uint64_t nTotal, void* stream) {
+  if (!key_ok(keyBytes) || n < 0 || (n > 0 && (!dOut || !dRowIds)) || kind < 0 || kind > 5 || nTotal == 0) return fail(HJ_ERR_ARG, "hjGenerateAt", "bad argument");
+  HJ_CUDA("hjGenerateAt", hj::generate_keys_total(dOut, n, keyBytes, kind, seed, lo, domain, p16, keyMul, 0, nTotal, dRowIds, S_(stream)));
   return HJ_OK;
 }
 
 // Host buffers in, host pairs out. The probe relation moves in chunks so that the three PCIe/compute legs overlap:
-//   stream IN : H2D of probe chunk i+1 ...            (all chunk copies are queued up front, one event each)
-//   stream CMP: count(i) -> 8-byte readback -> write(i) at the running output offset
+//   stream IN : H2D of probe chunks i+1, i+2 into a ring of THREE device slots (the probe relation never sits on the device whole:
+//               it may be larger than GPU memory — projectDescription.md:23 "relations that don't fit on GPU"; the build side must fit)
+//   stream CMP: count(i) -> result-size readback -> write(i) into one of TWO result slots
 //   stream OUT: D2H of the pairs of chunk i           (PCIe is full duplex: runs against the H2D of later chunks)
 // Pairs are appended chunk by chunk (probe_row = chunk base + local row), which is a valid order for a multiset result.
+// Device footprint: build column + table + 3 probe chunks + scratch for one chunk + 2 result slots of the largest chunk result.
+static int64_t g_host_chunk_rows = (int64_t)1 << 24;
+void hjSetHostChunkRows(int64_t rows) { if (rows >= 1024) g_host_chunk_rows = rows; }
+
 int64_t hjJoinHost(const void* hR, int64_t nR, const void* hS, int64_t nS, int32_t keyBytes, int32_t* hOutR, int32_t* hOutS, int64_t capacity) {
   if (!key_ok(keyBytes) || nR < 0 || nS < 0 || (nR > 0 && !hR) || (nS > 0 && !hS)) return fail(HJ_ERR_ARG, "hjJoinHost", "bad argument");
   if (nS > 0xFFFFFFFFLL) return fail(HJ_ERR_ARG, "hjJoinHost", "more than 2^32-1 probe rows (row ids are 32-bit, join_v1.mlir:605)");
   std::lock_guard<std::mutex> lk(g_mu);
-  const int64_t chunk_rows = (int64_t)1 << 24;                        // multiple of the kernel chunk (16 384 / 8 192 rows)
+  const int64_t chunk_rows = g_host_chunk_rows;
   const int64_t nch = (nS + chunk_rows - 1) / chunk_rows;
+  constexpr int RING = 3, OUT_RING = 2;
   const bool want_out = hOutR && hOutS && capacity > 0;
   const int64_t tb = hj::table_bytes(nR, keyBytes), sb = hj::scratch_bytes(std::min(nS, chunk_rows), keyBytes);
+  const int64_t slot_bytes = (std::min(nS, chunk_rows) * keyBytes + 255) / 256 * 256;
   HJ_CUDA("hjJoinHost", g_hR.ensure(std::max<int64_t>(nR * keyBytes, 16)));
-  HJ_CUDA("hjJoinHost", g_hS.ensure(std::max<int64_t>(nS * keyBytes, 16)));
+  HJ_CUDA("hjJoinHost", g_hS.ensure(std::max<int64_t>(slot_bytes * std::min<int64_t>(RING, std::max<int64_t>(nch, 1)), 16)));
   HJ_CUDA("hjJoinHost", g_hT.ensure(tb));
   HJ_CUDA("hjJoinHost", g_hSc.ensure(sb));
-  if (want_out) { HJ_CUDA("hjJoinHost", g_hOr.ensure(capacity * 4)); HJ_CUDA("hjJoinHost", g_hOs.ensure(capacity * 4)); }
   static cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-  static std::vector<cudaEvent_t> ev_in;
-  static cudaEvent_t ev_w = nullptr;
+  static cudaEvent_t ev_in[RING], ev_w = nullptr, ev_out[OUT_RING];
   if (!s_in) {
     HJ_CUDA("hjJoinHost", cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     HJ_CUDA("hjJoinHost", cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
     HJ_CUDA("hjJoinHost", cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     HJ_CUDA("hjJoinHost", cudaEventCreateWithFlags(&ev_w, cudaEventDisableTiming));
+    for (auto& e : ev_in) HJ_CUDA("hjJoinHost", cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_out) HJ_CUDA("hjJoinHost", cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  while ((int64_t)ev_in.size() < nch) { cudaEvent_t e; HJ_CUDA("hjJoinHost", cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev_in.push_back(e); }
-
   const char* hSb = reinterpret_cast<const char*>(hS);
   char* dSb = reinterpret_cast<char*>(g_hS.p);
+  auto issue_h2d = [&](int64_t i) -> cudaError_t {                                     // chunk i -> ring slot i % RING
+    const int64_t off = i * chunk_rows, n = std::min(chunk_rows, nS - off);
+    cudaError_t e = cudaMemcpyAsync(dSb + (i % RING) * slot_bytes, hSb + off * keyBytes, (size_t)n * keyBytes, cudaMemcpyHostToDevice, s_in);
+    return e == cudaSuccess ? cudaEventRecord(ev_in[i % RING], s_in) : e;
+  };
   if (nR) HJ_CUDA("hjJoinHost", cudaMemcpyAsync(g_hR.p, hR, (size_t)nR * keyBytes, cudaMemcpyHostToDevice, s_cmp));   // join_v1.mlir:558-561
   int32_t rc = hjBuild(g_hR.p, nR, keyBytes, nullptr, 0, g_hT.p, tb, s_cmp);
   if (rc != HJ_OK) return rc;
-  for (int64_t i = 0; i < nch; i++) {
-    const int64_t off = i * chunk_rows, n = std::min(chunk_rows, nS - off);
-    HJ_CUDA("hjJoinHost", cudaMemcpyAsync(dSb + off * keyBytes, hSb + off * keyBytes, (size_t)n * keyBytes, cudaMemcpyHostToDevice, s_in));
-    HJ_CUDA("hjJoinHost", cudaEventRecord(ev_in[(size_t)i], s_in));
-  }
+  for (int64_t i = 0; i < std::min<int64_t>(nch, RING - 1); i++) HJ_CUDA("hjJoinHost", issue_h2d(i));
   int64_t total = 0;
   bool overflow = !want_out;
   for (int64_t i = 0; i < nch; i++) {
     const int64_t off = i * chunk_rows, n = std::min(chunk_rows, nS - off);
-    HJ_CUDA("hjJoinHost", cudaStreamWaitEvent(s_cmp, ev_in[(size_t)i], 0));
-    const int64_t c = hjCount(dSb + off * keyBytes, n, keyBytes, g_hT.p, g_hSc.p, sb, s_cmp);                         // :591 (per chunk)
+    const char* dChunk = dSb + (i % RING) * slot_bytes;
+    HJ_CUDA("hjJoinHost", cudaStreamWaitEvent(s_cmp, ev_in[i % RING], 0));
+    const int64_t c = hjCount(dChunk, n, keyBytes, g_hT.p, g_hSc.p, sb, s_cmp);                                       // :591 (per chunk); synchronises s_cmp
     if (c < 0) return c;
+    // s_cmp is idle now, so write(i-1) has finished reading slot (i-1) % RING == (i+2) % RING: refill it
+    if (i + RING - 1 < nch) HJ_CUDA("hjJoinHost", issue_h2d(i + RING - 1));
     if (!overflow && total + c > capacity) overflow = true;
     if (!overflow && c > 0) {                                                                                        // :600-615
-      int32_t* dR = reinterpret_cast<int32_t*>(g_hOr.p) + total;
-      int32_t* dS = reinterpret_cast<int32_t*>(g_hOs.p) + total;
-      rc = hjWrite(dSb + off * keyBytes, n, keyBytes, g_hT.p, g_hSc.p, dR, dS, nullptr, (uint32_t)off, s_cmp);
+      DevBuf& oR = g_hOr[i % OUT_RING]; DevBuf& oS = g_hOs[i % OUT_RING];
+      if (oR.bytes < c * 4 || oS.bytes < c * 4) {                      // growing a slot frees it: its last D2H must be done
+        HJ_CUDA("hjJoinHost", cudaEventSynchronize(ev_out[i % OUT_RING]));
+        HJ_CUDA("hjJoinHost", oR.ensure(c * 4)); HJ_CUDA("hjJoinHost", oS.ensure(c * 4));
+      }
+      HJ_CUDA("hjJoinHost", cudaStreamWaitEvent(s_cmp, ev_out[i % OUT_RING], 0));       // the slot's previous pairs have left the device
+      int32_t* dR = reinterpret_cast<int32_t*>(oR.p); int32_t* dS = reinterpret_cast<int32_t*>(oS.p);
+      rc = hjWrite(dChunk, n, keyBytes, g_hT.p, g_hSc.p, dR, dS, nullptr, (uint32_t)off, s_cmp);
       if (rc != HJ_OK) return rc;
       HJ_CUDA("hjJoinHost", cudaEventRecord(ev_w, s_cmp));
       HJ_CUDA("hjJoinHost", cudaStreamWaitEvent(s_out, ev_w, 0));
       HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutR + total, dR, (size_t)c * 4, cudaMemcpyDeviceToHost, s_out));
       HJ_CUDA("hjJoinHost", cudaMemcpyAsync(hOutS + total, dS, (size_t)c * 4, cudaMemcpyDeviceToHost, s_out));
+      HJ_CUDA("hjJoinHost", cudaEventRecord(ev_out[i % OUT_RING], s_out));
     }
     total += c;
   }
@@ -417,6 +493,15 @@ int32_t hashJoinWriteI64(HJ_MEMREF(int64_t, S), HJ_MEMREF(int8_t, table), HJ_MEM
   (void)SAlloc; (void)tableAlloc; (void)scratchAlloc; (void)outRAlloc; (void)outSAlloc; (void)tableSize; (void)scratchSize;
   const bool ok = MR_ARGS_OK(S) && MR_ARGS_OK(table) && MR_ARGS_OK(scratch) && MR_ARGS_OK(outR) && MR_ARGS_OK(outS);
   return mlir_write(mr_ptr(SAligned, SOff), SSize, ok, 8, mr_ptr(tableAligned, tableOff), mr_ptr(scratchAligned, scratchOff), mr_ptr(outRAligned, outROff), mr_ptr(outSAligned, outSOff));
+}
+
+int32_t hashJoinGather(HJ_MEMREF(int32_t, column), HJ_MEMREF(int32_t, rowIds), HJ_MEMREF(int32_t, out)) {
+  (void)columnAlloc; (void)rowIdsAlloc; (void)outAlloc; (void)columnSize;
+  if (!(MR_ARGS_OK(column) && MR_ARGS_OK(rowIds) && MR_ARGS_OK(out)) || outSize < rowIdsSize) return fail(HJ_ERR_ARG, "hashJoinGather", "non-unit stride memref or short output");
+  int32_t rc = hjGather(mr_ptr(columnAligned, columnOff), 4, mr_ptr(rowIdsAligned, rowIdsOff), rowIdsSize, 0, mr_ptr(outAligned, outOff), nullptr);
+  if (rc != HJ_OK) return rc;
+  cudaError_t e = cudaStreamSynchronize(nullptr);
+  return e == cudaSuccess ? HJ_OK : cuda_fail("hashJoinGather", e);
 }
 
 // =========================================================================================================
@@ -516,7 +601,7 @@ void hashJoinRelease(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_tables) { if (kv.second.table) cudaFree(kv.second.table); if (kv.second.scratch) cudaFree(kv.second.scratch); }
   g_tables.clear();
-  g_hR.release(); g_hS.release(); g_hT.release(); g_hSc.release(); g_hOr.release(); g_hOs.release();
+  g_hR.release(); g_hS.release(); g_hT.release(); g_hSc.release(); for (auto& b : g_hOr) b.release(); for (auto& b : g_hOs) b.release();
 }
 
 // =========================================================================================================
@@ -546,6 +631,7 @@ int64_t _mlir_ciface_hashJoinCount(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D*
 int32_t _mlir_ciface_hashJoinWrite(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS) {
   return hashJoinWrite(MR(int32_t, S), MR(int8_t, table), MR(int8_t, scratch), MR(int32_t, outR), MR(int32_t, outS));
 }
+int32_t _mlir_ciface_hashJoinGather(HjMemRef1D* column, HjMemRef1D* rowIds, HjMemRef1D* out) { return hashJoinGather(MR(int32_t, column), MR(int32_t, rowIds), MR(int32_t, out)); }
 int32_t _mlir_ciface_hashJoinBuildI64(HjMemRef1D* R, HjMemRef1D* table) { return hashJoinBuildI64(MR(int64_t, R), MR(int8_t, table)); }
 int64_t _mlir_ciface_hashJoinCountI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch) { return hashJoinCountI64(MR(int64_t, S), MR(int8_t, table), MR(int8_t, scratch)); }
 int32_t _mlir_ciface_hashJoinWriteI64(HjMemRef1D* S, HjMemRef1D* table, HjMemRef1D* scratch, HjMemRef1D* outR, HjMemRef1D* outS) {

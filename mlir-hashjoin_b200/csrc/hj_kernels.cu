@@ -577,7 +577,7 @@ template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache, uint32_t* __restrict__ run_start,
                                                          unsigned long long* __restrict__ chunk_totals, int64_t nchunks, unsigned long long* tickets,
-                                                         const unsigned long long* __restrict__ sparse_flag) {
+                                                         const unsigned long long* __restrict__ sparse_flag, int semi) {
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
   if (MODE != MODE_GROUP && *sparse_flag) return;                  // selective join: k_count_sparse takes it
@@ -623,7 +623,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S
             // grouped: the slot's payload is (count << 32 | end of the key's row-id range). Count AND run start go to the scratch,
             // so the write pass neither reloads the keys nor probes the table again
             const unsigned long long pay = i0 + e < nS ? group_finish(body, n_pairs, (long long)kv[e], b[e]) : 0ULL;
-            mv[e] = (uint32_t)(pay >> 32); sv[e] = (uint32_t)pay - mv[e]; cnt += mv[e];
+            mv[e] = (uint32_t)(pay >> 32); sv[e] = (uint32_t)pay - mv[e];
+            if (semi && mv[e]) mv[e] = 1;                                       // semi-join: a probe row counts once however many build rows match
+            cnt += mv[e];
           }
         }
         store_vec_u32<KPV>(mcache, i0, pol_s, mv);
@@ -856,7 +858,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write_sparse(const TableHeade
         const uint32_t v = v0 + u * 32 + lane;
         if (v < tot) {
           const uint32_t j = base + e[u].y;                                                // positions are chunk-relative
-          st_stream_u32(outR + o + v, e[u].x, pol_s);
+          if (outR) st_stream_u32(outR + o + v, e[u].x, pol_s);               // outR == nullptr: semi-join, probe rows only
           st_stream_u32(outS + o + v, probe_payload ? probe_payload[j] : probe_row_base + j, pol_s);
         }
       }
@@ -1043,7 +1045,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restri
         if (hit[k]) {
           const unsigned long long dst = o + __popc(mask[k] & lt);
           const uint32_t j = (uint32_t)chunk_base + pos[k];
-          st_stream_u32(outR + dst, m[k], pol_s);
+          if (outR) st_stream_u32(outR + dst, m[k], pol_s);
           st_stream_u32(outS + dst, probe_payload ? probe_payload[j] : probe_row_base + j, pol_s);
         }
         o += __popc(mask[k]);
@@ -1109,7 +1111,7 @@ void launch_scan(unsigned long long* t, int64_t n, unsigned long long* block_sum
 // it finds, under the policy the table was BUILT with. Only the hit-list decision stays on the device (k_sample_hits -> CTR_SPARSE): for
 // the unique layouts the match-cache / range kernel and the hit-list kernel are both queued and one of them exits at once.
 cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch,
-                             bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+                             bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream) {
   ScratchView sv = scratch_view(scratch, nS, key_bytes);
   const TableHeader* hdr = reinterpret_cast<const TableHeader*>(table);
   const char* body = reinterpret_cast<const char*>(table) + HEADER_BYTES;
@@ -1118,9 +1120,10 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
   if (h.magic != HJ_MAGIC || (int)h.key_bytes != key_bytes) return cudaErrorInvalidValue;          // never built, or built for the other key width
   { cudaError_t e = cudaMemsetAsync(sv.counters, 0, SCRATCH_COUNTERS * sizeof(unsigned long long), stream); if (e != cudaSuccess) return e; }
   if (carry_rows) { cudaError_t e = cudaMemsetAsync(sv.counters + CTR_CARRIED, 1, 1, stream); if (e != cudaSuccess) return e; }
+  if (semi) { cudaError_t e = cudaMemsetAsync(sv.counters + CTR_SEMI, 1, 1, stream); if (e != cudaSuccess) return e; }
   unsigned long long* total_out = sv.counters + CTR_TOTAL;
   if (h.mode == MODE_RADIX)
-    return radix_count(S, nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.scan_sums, sv.counters + CTR_TICKET_RADIX, total_out, carry_rows, probe_payload, probe_row_base, stream);
+    return radix_count(S, nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.scan_sums, sv.counters + CTR_TICKET_RADIX, total_out, carry_rows, probe_payload, probe_row_base, semi, stream);
   const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
   const bool tma = (h.policy & POLICY_TMA_COUNT) != 0;
   const int sparse_policy = (tma || h.mode == MODE_GROUP) ? 0 : (int)((h.policy >> POLICY_SPARSE_SHIFT) & 3);
@@ -1132,14 +1135,14 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
   if (sv.nchunks > 0) {
     const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
 #define HJ_LAUNCH_COUNT(K, V) \
-    if (h.mode == MODE_GROUP) k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP, sparse_flag); \
+    if (h.mode == MODE_GROUP) k_count<K, V, MODE_GROUP><<<resident_grid(k_count<K, V, MODE_GROUP>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP, sparse_flag, semi ? 1 : 0); \
     else if (h.mode == MODE_HASH) { \
-      k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_HASH, sparse_flag);  \
+      k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_HASH, sparse_flag, 0);  \
       if (sparse_policy) k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_SPARSE, sparse_flag); \
     } else { \
       if (by_range) k_count_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag); \
       else if (tma && sizeof(K) == 4 && V) k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets); \
-      else k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag); \
+      else k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag, 0); \
       if (sparse_policy) k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_SPARSE, sparse_flag); \
     }
     if (key_bytes == 4) { if (vec) { HJ_LAUNCH_COUNT(int32_t, true) } else { HJ_LAUNCH_COUNT(int32_t, false) } }
@@ -1211,7 +1214,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
         if (m[k] != ROW_NONE) {
           const int64_t j = elem_index<KPV>(tile_base, k);
           const unsigned long long dst = o + __popc(mask[k] & lt);
-          st_stream_u32(outR + dst, m[k], pol_s);
+          if (outR) st_stream_u32(outR + dst, m[k], pol_s);
           st_stream_u32(outS + dst, probe_row(j), pol_s);
         }
         o += __popc(mask[k]);
@@ -1254,7 +1257,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write(const K* __restrict__ S
           owner = owner > 31 ? 31 : owner;
           const uint32_t s0 = __shfl_sync(0xffffffffu, start[k], owner), e0 = __shfl_sync(0xffffffffu, excl, owner), pr = __shfl_sync(0xffffffffu, prow[k], owner);
           if (p < tk) {
-            st_stream_u32(outR + o + p, rows[s0 + (p - e0)], pol_s);
+            if (outR) st_stream_u32(outR + o + p, rows[s0 + (p - e0)], pol_s);
             st_stream_u32(outS + o + p, pr, pol_s);
           }
         }
@@ -1293,7 +1296,7 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
   const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
   if (h.mode == MODE_RADIX) {
     if (ctr[CTR_CARRIED]) { probe_payload = nullptr; probe_row_base = 0; }           // the partitioned copy already holds the probe row ids
-    return radix_write(nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.counters + CTR_TICKET_RADIX_W, outR, outS, ctr[CTR_CARRIED] != 0, probe_payload, probe_row_base, stream);
+    return radix_write(nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.counters + CTR_TICKET_RADIX_W, outR, outS, ctr[CTR_CARRIED] != 0, probe_payload, probe_row_base, ctr[CTR_SEMI] != 0, stream);
   }
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   const bool grouped = h.mode == MODE_GROUP, lists = !grouped && ctr[CTR_SPARSE] != 0, by_range = !grouped && !lists && h.mode == MODE_DENSE && h.all_present;
@@ -1507,12 +1510,12 @@ __device__ __forceinline__ uint64_t zipf_rank(uint64_t r, int log2D, const unsig
 template <typename K>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_generate(K* __restrict__ out, int64_t n, int kind, uint64_t seed, int64_t lo, uint64_t domain, uint32_t p16,
                                                             uint64_t key_mul, int64_t index_base, uint64_t n_total, int hb_domain, int hb_total, int log2D,
-                                                            const ZipfTable zt) {
+                                                            const ZipfTable zt, const uint32_t* __restrict__ at) {
   __shared__ unsigned long long zsm[257];
   for (int t = threadIdx.x; t < 257; t += BLOCK_THREADS) zsm[t] = zt.t[t];
   __syncthreads();
   for (int64_t li = blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x; li < n; li += (int64_t)gridDim.x * BLOCK_THREADS) {
-    const uint64_t i = (uint64_t)(index_base + li);
+    const uint64_t i = at ? (uint64_t)at[li] : (uint64_t)(index_base + li);          // at: the key of row at[li] instead of row index_base + li
     uint64_t v;
     switch (kind) {
       case 0: v = i; break;
@@ -1540,7 +1543,7 @@ static void make_zipf_table(ZipfTable& z) {
 }
 
 cudaError_t generate_keys_total(void* out, int64_t n, int key_bytes, int kind, uint64_t seed, int64_t lo, uint64_t domain,
-                                uint32_t p16, uint64_t key_mul, int64_t index_base, uint64_t n_total, cudaStream_t stream) {
+                                uint32_t p16, uint64_t key_mul, int64_t index_base, uint64_t n_total, const uint32_t* at, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   if (domain == 0) domain = 1;
   ZipfTable zt; make_zipf_table(zt);
@@ -1548,13 +1551,13 @@ cudaError_t generate_keys_total(void* out, int64_t n, int key_bytes, int kind, u
   int64_t blocks = (n + BLOCK_THREADS - 1) / BLOCK_THREADS;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const int hbd = half_bits(domain), hbt = half_bits(n_total ? n_total : 1);
-  if (key_bytes == 4) k_generate<int32_t><<<(unsigned)blocks, BLOCK_THREADS, 0, stream>>>((int32_t*)out, n, kind, seed, lo, domain, p16, key_mul, index_base, n_total, hbd, hbt, log2D, zt);
-  else                k_generate<int64_t><<<(unsigned)blocks, BLOCK_THREADS, 0, stream>>>((int64_t*)out, n, kind, seed, lo, domain, p16, key_mul, index_base, n_total, hbd, hbt, log2D, zt);
+  if (key_bytes == 4) k_generate<int32_t><<<(unsigned)blocks, BLOCK_THREADS, 0, stream>>>((int32_t*)out, n, kind, seed, lo, domain, p16, key_mul, index_base, n_total, hbd, hbt, log2D, zt, at);
+  else                k_generate<int64_t><<<(unsigned)blocks, BLOCK_THREADS, 0, stream>>>((int64_t*)out, n, kind, seed, lo, domain, p16, key_mul, index_base, n_total, hbd, hbt, log2D, zt, at);
   return cudaGetLastError();
 }
 cudaError_t generate_keys(void* out, int64_t n, int key_bytes, int kind, uint64_t seed, int64_t lo, uint64_t domain,
                           uint32_t p16, uint64_t key_mul, int64_t index_base, cudaStream_t stream) {
-  return generate_keys_total(out, n, key_bytes, kind, seed, lo, domain, p16, key_mul, index_base, (uint64_t)(index_base + n), stream);
+  return generate_keys_total(out, n, key_bytes, kind, seed, lo, domain, p16, key_mul, index_base, (uint64_t)(index_base + n), nullptr, stream);
 }
 
 }  // namespace hj

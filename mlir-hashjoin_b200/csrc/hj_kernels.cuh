@@ -39,7 +39,7 @@ bool table_is_big(int64_t n_rows, int key_bytes);
 // first cnt[c] 8-byte entries (matched build row, position of the probe row inside the chunk) of its slice, see k_count_sparse.
 constexpr int SCRATCH_COUNTERS = 16;
 constexpr int CTR_TICKET_HASH = 0, CTR_TICKET_GROUP = 1, CTR_TICKET_GROUP_W = 2, CTR_SPARSE = 3 /* hit-list flag */, CTR_TICKET_SPARSE = 4,
-              CTR_TICKET_RADIX = 5, CTR_CARRIED = 6 /* radix copy carries probe row ids, not indices */, CTR_TOTAL = 7 /* result size */, CTR_TICKET_RADIX_W = 8;
+              CTR_TICKET_RADIX = 5, CTR_CARRIED = 6 /* radix copy carries probe row ids, not indices */, CTR_TOTAL = 7 /* result size */, CTR_TICKET_RADIX_W = 8, CTR_SEMI = 9 /* semi-join: one result row per matching probe row */;
 struct ScratchView {
   uint32_t* mcache;
   uint2* hit_list;
@@ -68,8 +68,8 @@ cudaError_t build_table(const void* R, int64_t nR, int key_bytes, const uint32_t
 // K2+K3: count + scan. The result size lands in counters[CTR_TOTAL]. carry_rows: the probe row ids (payload column or row base) are
 // known now, so the radix layout's partitioned copy carries THEM instead of the original index; write_pairs then needs none.
 cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const void* table, void* scratch,
-                             bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
-// K4: write pairs.
+                             bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
+// K4: write pairs. outR == nullptr: only the probe rows are stored (semi-join).
 cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* table, const void* scratch,
                         int32_t* outR, int32_t* outS, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
 // K3 alone: t[0 .. n) := exclusive prefix, t[n] := total (also *total_out when given)
@@ -103,9 +103,21 @@ int64_t radix_scratch_bytes(int64_t n_probe, int key_bytes);
 cudaError_t radix_build(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base, TableHeader* hdr, char* body, int64_t body_bytes, cudaStream_t stream);
 cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area,
                         unsigned long long* item_totals, unsigned long long* scan_block_sums, unsigned long long* ticket, unsigned long long* total_out,
-                        bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
+                        bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
 cudaError_t radix_write(int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area, unsigned long long* item_offsets,
-                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream);
+                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
+
+// hj_ops.cu: the operators either side of the join
+cudaError_t gather_column(const void* column, int elem_bytes, const int32_t* rows, int64_t n, uint32_t row_base, void* out, cudaStream_t stream);
+cudaError_t materialize_rows(const int32_t* tx, int x_cols, const int32_t* ty, int y_cols, const int32_t* pair_x, const int32_t* pair_y, int64_t n_pairs,
+                             int32_t* result, cudaStream_t stream);
+cudaError_t extract_column(const int32_t* table, int64_t rows, int cols, int col, int32_t* out, cudaStream_t stream);
+cudaError_t pack_keys(const int32_t* a, const int32_t* b, int64_t n, long long* out, cudaStream_t stream);
+int64_t select_scratch_bytes(int64_t n);
+unsigned long long* select_total_ptr(void* scratch, int64_t n);
+cudaError_t select_count(const void* col, int64_t n, int dtype, int op, long long iconst, double fconst, void* scratch, cudaStream_t stream);
+cudaError_t select_write(const void* col, int64_t n, int dtype, int op, long long iconst, double fconst, const void* scratch, void* out_values, int32_t* out_rows, uint32_t row_base,
+                         cudaStream_t stream);
 
 // K6: verification helpers — order-independent digest of a pair stream: out[0] += sum(mix64(pair)), out[1] ^= xor.
 cudaError_t pair_digest(const int32_t* outR, const int32_t* outS, int64_t n, unsigned long long* out2, cudaStream_t stream);
@@ -114,6 +126,6 @@ cudaError_t pair_digest(const int32_t* outR, const int32_t* outS, int64_t n, uns
 cudaError_t generate_keys(void* out, int64_t n, int key_bytes, int kind, uint64_t seed, int64_t lo, uint64_t domain,
                           uint32_t p16, uint64_t key_mul, int64_t index_base, cudaStream_t stream);
 cudaError_t generate_keys_total(void* out, int64_t n, int key_bytes, int kind, uint64_t seed, int64_t lo, uint64_t domain,
-                                uint32_t p16, uint64_t key_mul, int64_t index_base, uint64_t n_total, cudaStream_t stream);
+                                uint32_t p16, uint64_t key_mul, int64_t index_base, uint64_t n_total, const uint32_t* at, cudaStream_t stream);
 
 }  // namespace hj

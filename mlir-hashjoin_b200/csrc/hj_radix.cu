@@ -5,13 +5,15 @@
 //   build   both passes of K5 (hj_partition.cu) split the build relation into 2^(b1+b2) partitions of <= ~4 096 (key, row id) tuples on
 //           the top bits of radix_hash(key); the partitioned copy + its offsets ARE the table (no clear, no global atomics);
 //   count   the probe relation is partitioned the same way; a work item = (partition, <= 16 384 probe tuples of it). A CTA takes items
-//           by ticket, builds the partition's table in SHARED memory (8 192 slots, one ATOMS.CAS per tuple on the row word — EMPTY is
-//           the row id 0xFFFFFFFF, so every key value stays legal), streams its probe tuples through it and writes the item's match
-//           count; K3 (the same scan as the other layouts) turns item counts into offsets and the total;
+//           by ticket, builds the partition's table in SHARED memory — 4 096 buckets in CSR form: one ATOMS.ADD per tuple ranks it inside
+//           its bucket, a block scan turns bucket counts into starts, the tuples land bucket-sorted; no sentinel, so every key value
+//           stays legal, and no probe-sequence clustering, so duplicate keys cost exactly their multiplicity — streams its probe
+//           tuples through it and writes the item's match count; K3 (the same scan as the other layouts) turns item counts into
+//           offsets and the total;
 //   write   the same items again: the table is rebuilt with row ids, every warp ranks the matches of its 32 probe tuples with a ballot,
 //           claims a run of the item's output range with one shared-memory atomic and stores the pairs (order is free: shared.cpp:168-171).
-// Duplicate build keys need nothing special (equal keys sit in one probe sequence and every occupied slot of it is compared); a partition
-// larger than the table (heavy skew) is joined in rounds of RJ_CAP build tuples; a hot probe key only makes more items.
+// Duplicate build keys need nothing special (equal keys share a bucket and every entry of it is compared); a partition larger than the
+// table (heavy skew) is joined in rounds of RJ_CAP build tuples; a hot probe key only makes more items.
 #include <algorithm>
 #include <cstdio>
 #include "hj_common.cuh"
@@ -20,8 +22,9 @@
 namespace hj {
 
 constexpr int RJ_THREADS = 512;
-constexpr int RJ_SLOTS = 8192;          // shared-memory table slots
-constexpr int RJ_CAP = 5632;            // build tuples per round (load factor <= 0.69)
+constexpr int RJ_BUCKETS = 4096;        // shared-memory table: buckets (CSR starts) ...
+constexpr int RJ_CAP = 4864;            // ... over at most this many build tuples per round: 72 KB (i64) / 53 KB (i32) per CTA, 3 / 4 CTAs per SM
+constexpr int RJ_R_ITEMS = (RJ_CAP + RJ_THREADS - 1) / RJ_THREADS;
 constexpr int RJ_TARGET = 4096;         // partitions are sized so that the AVERAGE build partition is at most this (sigma = 64 for uniform hashes)
 constexpr int RJ_ITEM_ROWS = 16384;     // probe tuples per work item
 constexpr int RJ_MAX_BITS = 16;         // two passes of <= 8 bits
@@ -112,43 +115,60 @@ __global__ void __launch_bounds__(256) k_rj_items(const uint32_t* __restrict__ o
 // ---------------------------------------------------------------------------------------------------------
 // the join kernel: WRITE = false counts the matches of every item, WRITE = true emits them at the item's offset
 // ---------------------------------------------------------------------------------------------------------
-template <typename K> struct RjSmem { K tkey[RJ_SLOTS]; uint32_t trow[RJ_SLOTS]; };
+template <typename K> struct RjSmem { K ckey[RJ_CAP]; uint32_t crow[RJ_CAP]; uint32_t start[RJ_BUCKETS + 1]; };
 
 template <typename K>
-__device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, uint32_t r0, uint32_t nr, bool with_rows, uint64_t pol) {
+__device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, uint32_t r0, uint32_t nr, bool with_rows,
+                                               uint64_t pol, uint32_t* scan_sm) {
+  constexpr int PER = RJ_BUCKETS / RJ_THREADS;                       // bucket counters per thread in the scan
   #pragma unroll
-  for (int i = 0; i < RJ_SLOTS / (RJ_THREADS * 4); i++) reinterpret_cast<uint4*>(sm.trow)[i * RJ_THREADS + threadIdx.x] = make_uint4(ROW_NONE, ROW_NONE, ROW_NONE, ROW_NONE);
+  for (int i = 0; i < PER; i++) sm.start[i * RJ_THREADS + threadIdx.x] = 0;
   __syncthreads();
-  for (uint32_t i0 = 0; i0 < nr; i0 += RJ_THREADS * 4) {
-    K key[4]; uint32_t row[4];
-    #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const uint32_t i = i0 + u * RJ_THREADS + threadIdx.x;
-      key[u] = i < nr ? ld_stream<K>(Rk + r0 + i, pol) : K(0);
-      row[u] = (with_rows && i < nr) ? ld_stream<uint32_t>(Rr + r0 + i, pol) : 0u;           // counting needs no row ids: any value but EMPTY marks the slot
+  uint32_t br[RJ_R_ITEMS];                                           // bucket << 16 | rank inside the bucket
+  #pragma unroll
+  for (int u = 0; u < RJ_R_ITEMS; u++) {
+    const uint32_t i = u * RJ_THREADS + threadIdx.x;
+    br[u] = 0;
+    if (i < nr) {
+      const uint32_t b = radix_hash<K>(ld_stream<K>(Rk + r0 + i, pol)) & (RJ_BUCKETS - 1);
+      br[u] = (b << 16) | atomicAdd(&sm.start[b], 1u);
     }
+  }
+  __syncthreads();
+  {                                                                   // counts -> exclusive starts: thread t owns buckets [t * PER, (t + 1) * PER)
+    uint32_t v[PER], sum = 0;
     #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (i0 + u * RJ_THREADS + threadIdx.x < nr) {
-        uint32_t slot = radix_hash<K>(key[u]) & (RJ_SLOTS - 1);
-        while (atomicCAS(&sm.trow[slot], ROW_NONE, row[u]) != ROW_NONE) slot = (slot + 1) & (RJ_SLOTS - 1);   // nr <= RJ_CAP < RJ_SLOTS: there is a free slot
-        sm.tkey[slot] = key[u];
-      }
+    for (int i = 0; i < PER; i++) { v[i] = sm.start[threadIdx.x * PER + i]; sum += v[i]; }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, scan_sm, &total);
+    #pragma unroll
+    for (int i = 0; i < PER; i++) { sm.start[threadIdx.x * PER + i] = run; run += v[i]; }
+    if (threadIdx.x == 0) sm.start[RJ_BUCKETS] = total;
+  }
+  __syncthreads();
+  #pragma unroll
+  for (int u = 0; u < RJ_R_ITEMS; u++) {
+    const uint32_t i = u * RJ_THREADS + threadIdx.x;
+    if (i < nr) {                                                     // second look at the tuple: an L1 / L2 hit (the partition was read a moment ago)
+      const uint32_t pos = sm.start[br[u] >> 16] + (br[u] & 0xFFFFu);
+      sm.ckey[pos] = Rk[r0 + i];
+      sm.crow[pos] = with_rows ? Rr[r0 + i] : 0u;                     // counting needs no row ids
     }
   }
   __syncthreads();
 }
 
 template <typename K, bool WRITE>
-__global__ void __launch_bounds__(RJ_THREADS, 2) k_rj_join(const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, const K* __restrict__ Sk, const uint32_t* __restrict__ Sr,
+__global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, const K* __restrict__ Sk, const uint32_t* __restrict__ Sr,
                                                            const RjItem* __restrict__ items, const unsigned long long* __restrict__ n_items_ptr, unsigned long long* tickets,
                                                            unsigned long long* __restrict__ item_totals,       // count: out (matches per item); write: in (exclusive offsets)
                                                            int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                           const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows) {
+                                                           const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows, int semi) {
   extern __shared__ __align__(16) unsigned char rj_raw[];
   RjSmem<K>& sm = *reinterpret_cast<RjSmem<K>*>(rj_raw);
   __shared__ TicketQueue tq;
   __shared__ unsigned long long red[33];
+  __shared__ uint32_t scan_sm[33];
   __shared__ uint32_t cursor;
   const long long n_items = (long long)*n_items_ptr;
   const int lane = threadIdx.x & 31;
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(RJ_THREADS, 2) k_rj_join(const K* __restrict__
     if (WRITE) { obase = item_totals[item]; if (threadIdx.x == 0) cursor = 0; }
     for (uint32_t r0 = w.r0; r0 < w.r1; r0 += RJ_CAP) {
       const uint32_t nr = w.r1 - r0 < (uint32_t)RJ_CAP ? w.r1 - r0 : (uint32_t)RJ_CAP;
-      rj_build_round<K>(sm, Rk, Rr, r0, nr, WRITE, pol);
+      rj_build_round<K>(sm, Rk, Rr, r0, nr, WRITE, pol, scan_sm);
       constexpr int U = 4;
       if (!WRITE) {
         uint32_t c = 0;
@@ -174,8 +194,10 @@ __global__ void __launch_bounds__(RJ_THREADS, 2) k_rj_join(const K* __restrict__
           #pragma unroll
           for (int u = 0; u < U; u++) {
             if (j0 + u * RJ_THREADS + threadIdx.x < w.s1) {
-              uint32_t slot = radix_hash<K>(key[u]) & (RJ_SLOTS - 1);
-              while (sm.trow[slot] != ROW_NONE) { c += sm.tkey[slot] == key[u]; slot = (slot + 1) & (RJ_SLOTS - 1); }
+              const uint32_t b = radix_hash<K>(key[u]) & (RJ_BUCKETS - 1);
+              uint32_t m = 0;
+              for (uint32_t p = sm.start[b], p1 = sm.start[b + 1]; p < p1; p++) m += sm.ckey[p] == key[u];
+              c += semi ? (m != 0) : m;                                                            // semi-join: a probe tuple counts once
             }
           }
         }
@@ -197,14 +219,12 @@ __global__ void __launch_bounds__(RJ_THREADS, 2) k_rj_join(const K* __restrict__
             bool active = j0 + u * RJ_THREADS + lane < w.s1;
             uint32_t prow = srow[u];
             if (!carried_rows) prow = probe_payload ? (active ? probe_payload[prow] : 0u) : probe_row_base + prow;   // the copy carries original indices
-            uint32_t slot = radix_hash<K>(key[u]) & (RJ_SLOTS - 1);
-            while (__any_sync(0xffffffffu, active)) {
+            const uint32_t b = radix_hash<K>(key[u]) & (RJ_BUCKETS - 1);
+            uint32_t p = active ? sm.start[b] : 0u;
+            const uint32_t p1 = active ? sm.start[b + 1] : 0u;
+            while (__any_sync(0xffffffffu, p < p1)) {
               bool hit = false; uint32_t brow = 0;
-              if (active) {
-                brow = sm.trow[slot];
-                if (brow == ROW_NONE) active = false;
-                else { hit = sm.tkey[slot] == key[u]; slot = (slot + 1) & (RJ_SLOTS - 1); }
-              }
+              if (p < p1) { hit = sm.ckey[p] == key[u]; brow = sm.crow[p]; p = (semi && hit) ? p1 : p + 1; }
               const unsigned hm = __ballot_sync(0xffffffffu, hit);
               if (hm) {
                 uint32_t base = 0;
@@ -212,7 +232,8 @@ __global__ void __launch_bounds__(RJ_THREADS, 2) k_rj_join(const K* __restrict__
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (hit) {
                   const unsigned long long pos = obase + base + __popc(hm & lt);
-                  outR[pos] = (int32_t)brow; outS[pos] = (int32_t)prow;
+                  if (outR) outR[pos] = (int32_t)brow;
+                  outS[pos] = (int32_t)prow;
                 }
               }
             }
@@ -240,12 +261,12 @@ static unsigned rj_grid(Kern kern, size_t smem) {
 
 template <typename K, bool WRITE>
 static cudaError_t rj_launch(const RadixArea& r, const RadixScratch& s, unsigned long long* ticket, unsigned long long* item_totals, int32_t* outR, int32_t* outS,
-                             const uint32_t* probe_payload, uint32_t probe_row_base, int carried_rows, uint32_t n_parts, cudaStream_t stream) {
+                             const uint32_t* probe_payload, uint32_t probe_row_base, int carried_rows, int semi, uint32_t n_parts, cudaStream_t stream) {
   auto kern = k_rj_join<K, WRITE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RjSmem<K>));
   if (e != cudaSuccess) return e;
   kern<<<rj_grid(kern, sizeof(RjSmem<K>)), RJ_THREADS, sizeof(RjSmem<K>), stream>>>((const K*)r.keys, r.rows, (const K*)s.a.keys, s.a.rows, s.items, s.item_start + n_parts, ticket,
-                                                                                   item_totals, outR, outS, probe_payload, probe_row_base, carried_rows);
+                                                                                   item_totals, outR, outS, probe_payload, probe_row_base, carried_rows, semi);
   return cudaGetLastError();
 }
 
@@ -253,7 +274,7 @@ static cudaError_t rj_launch(const RadixArea& r, const RadixScratch& s, unsigned
 // the caller. item_totals: u64[radix_max_items(nS) + 1] (the scratch's offsets array); total_out: where the scan leaves the result size.
 cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area,
                         unsigned long long* item_totals, unsigned long long* scan_block_sums, unsigned long long* ticket, unsigned long long* total_out,
-                        bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+                        bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream) {
   const int b1 = (int)hdr_host.rj_bits1, b2 = (int)hdr_host.rj_bits2;
   const uint32_t n_parts = 1u << (b1 + b2);
   const RadixScratch s = radix_scratch(scratch_area, nS, key_bytes, b1, b2);
@@ -268,23 +289,23 @@ cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHea
   k_rj_items<<<(n_parts + 255) / 256, 256, 0, stream>>>(r.offsets, s.a.offsets, n_parts, s.item_start, s.items);
   e = cudaMemsetAsync(item_totals, 0, (size_t)(s.max_items + 1) * 8, stream);
   if (e != cudaSuccess) return e;
-  e = key_bytes == 4 ? rj_launch<int32_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, n_parts, stream)
-                     : rj_launch<int64_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, n_parts, stream);
+  e = key_bytes == 4 ? rj_launch<int32_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, semi ? 1 : 0, n_parts, stream)
+                     : rj_launch<int64_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, semi ? 1 : 0, n_parts, stream);
   if (e != cudaSuccess) return e;
   launch_scan(item_totals, s.max_items, scan_block_sums, total_out, stream);
   return cudaGetLastError();
 }
 
 cudaError_t radix_write(int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area, unsigned long long* item_offsets,
-                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, cudaStream_t stream) {
+                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream) {
   const int b1 = (int)hdr_host.rj_bits1, b2 = (int)hdr_host.rj_bits2;
   const uint32_t n_parts = 1u << (b1 + b2);
   const RadixScratch s = radix_scratch(scratch_area, nS, key_bytes, b1, b2);
   RadixArea r;
   r.keys = const_cast<char*>(body) + hdr_host.rj_keys_off; r.rows = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_rows_off);
   r.offsets = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_offs_off);
-  return key_bytes == 4 ? rj_launch<int32_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, n_parts, stream)
-                        : rj_launch<int64_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, n_parts, stream);
+  return key_bytes == 4 ? rj_launch<int32_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, semi ? 1 : 0, n_parts, stream)
+                        : rj_launch<int64_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, semi ? 1 : 0, n_parts, stream);
 }
 
 }  // namespace hj

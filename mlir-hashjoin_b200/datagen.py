@@ -50,6 +50,15 @@ def generate(spec: RelationSpec, device="cuda", index_base: int = 0, n_local: in
     return out
 
 
+def generate_at(spec: RelationSpec, row_ids: torch.Tensor) -> torch.Tensor:
+    """Keys of the rows ``row_ids`` (int32 patterns of u32 row ids) of the relation ``spec`` describes (hjGenerateAt)."""
+    out = torch.empty(row_ids.numel(), dtype=spec.dtype, device=row_ids.device)
+    rc = _lib.load().hjGenerateAt(out.data_ptr(), row_ids.data_ptr(), row_ids.numel(), spec.key_bytes, spec.kind, spec.seed, spec.lo, spec.domain, spec.p16,
+                                  spec.key_mul, spec.n, torch.cuda.current_stream().cuda_stream)
+    _lib.check_status(rc, "hjGenerateAt")
+    return out
+
+
 def config(name: str, scale_log2: int = 0) -> JoinConfig:
     """The five BASELINE.json configs. ``scale_log2`` < 0 shrinks both relations by 2^k."""
     s = scale_log2
@@ -63,6 +72,18 @@ def config(name: str, scale_log2: int = 0) -> JoinConfig:
         nR, nS = sh(1 << 24), sh(1 << 28)
         return JoinConfig("C2", RelationSpec(nR, 4, KIND_UNIQUE, 42, 0, nR), RelationSpec(nS, 4, KIND_UNIFORM, 43, 0, nR), nS,
                           "HBM-resident table, every probe key hits exactly one build row")
+    if name == "C2S":      # config 2 with sparse keys: the same permutation spread over int32 by an odd multiplier -> no dense range to ride
+        nR, nS = sh(1 << 24), sh(1 << 28)
+        return JoinConfig("C2S", RelationSpec(nR, 4, KIND_UNIQUE, 42, 0, nR, 0, 0x9E3779B1), RelationSpec(nS, 4, KIND_UNIFORM, 43, 0, nR, 0, 0x9E3779B1), nS,
+                          "config 2's sizes and match pattern, keys multiplied by an odd constant mod 2^32 (a bijection): only the hash-table paths apply")
+    if name == "REF10M":   # join-performances.md:3-6 / :16-19
+        n = sh(10_000_000)
+        return JoinConfig("REF10M", RelationSpec(n, 4, KIND_UNIFORM, 50, 1, 100_000), RelationSpec(n, 4, KIND_UNIFORM, 51, 1, 100_000), None,
+                          "the reference's published shape 1: 10M x 10M rows, keys uniform in [1, 100k], ~1e9 result pairs")
+    if name == "REF100M":  # join-performances.md:8-11 / :21-24
+        n = sh(100_000_000)
+        return JoinConfig("REF100M", RelationSpec(n, 4, KIND_UNIFORM, 52, 1, 1_000_000_000), RelationSpec(n, 4, KIND_UNIFORM, 53, 1, 1_000_000_000), None,
+                          "the reference's published shape 2: 100M x 100M rows, keys uniform in [1, 1e9], ~1e7 result pairs")
     if name == "C3":       # 1M x 1B i32, 10 % selectivity, L2-resident table
         nR, nS = sh(1 << 20), sh(1 << 30)
         return JoinConfig("C3", RelationSpec(nR, 4, KIND_UNIQUE, 44, 0, nR), RelationSpec(nS, 4, KIND_MIXED, 45, 0, nR, 6554), None,

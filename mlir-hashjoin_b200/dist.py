@@ -95,37 +95,56 @@ class PeerExchange:
         """Stream-ordered barrier across the ranks (signal pads in peer memory)."""
         self.hk.barrier()
 
-    def push(self, keys: torch.Tensor, row_base: int) -> int:
-        """Partition ``keys`` (row ids row_base + i) by owner rank and store them into the owners' buffers. Returns the
-        number of tuples this rank will have received once every rank's push has completed (call barrier())."""
+    def count(self, keys: torch.Tensor):
+        """Pass 1 of the fused exchange: tuples of ``keys`` per owner rank (device, int64[world]) and the workspace that keeps the
+        per-block count matrix for push()."""
         lib = _lib.load()
-        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        stream = torch.cuda.current_stream().cuda_stream
+        world = dist.get_world_size(self.group)
         kb, n = keys.element_size(), keys.numel()
         counts = torch.empty(world, dtype=torch.int64, device=keys.device)
         ws = torch.empty(lib.hjPartitionWorkspaceBytes(n, world), dtype=torch.uint8, device=keys.device)
-        _lib.check_status(lib.hjPartitionCount(keys.data_ptr(), n, kb, world, counts.data_ptr(), ws.data_ptr(), ws.numel(), stream), "hjPartitionCount")
-        matrix = torch.empty(world * world, dtype=torch.int64, device=keys.device)
-        dist.all_gather_into_tensor(matrix, counts, group=self.group)
-        matrix = matrix.view(world, world)                          # matrix[src][dst]
-        cursors = matrix[:rank].sum(0).contiguous()                 # first element of my region in every destination
-        received = int(matrix[:, rank].sum().item())
-        if int(matrix.sum(0).max().item()) > self.capacity:
-            raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
-        rc = lib.hjPartitionPush(keys.data_ptr(), None, row_base & 0xFFFFFFFF, n, kb, world, self.key_ptrs.data_ptr(), self.row_ptrs.data_ptr(),
-                                 cursors.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check_status(lib.hjPartitionCount(keys.data_ptr(), n, kb, world, counts.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "hjPartitionCount")
+        return counts, ws
+
+    def push(self, keys: torch.Tensor, row_base: int, cursors: torch.Tensor, ws: torch.Tensor) -> None:
+        """Pass 2: store every (key, row_base + i) into its owner's buffer, starting at ``cursors[owner]`` (device, int64[world]: the
+        tuples the lower ranks send to that owner). Follows count() on the same keys and workspace; call barrier() afterwards."""
+        lib = _lib.load()
+        world = dist.get_world_size(self.group)
+        rc = lib.hjPartitionPush(keys.data_ptr(), None, row_base & 0xFFFFFFFF, keys.numel(), keys.element_size(), world, self.key_ptrs.data_ptr(), self.row_ptrs.data_ptr(),
+                                 cursors.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         _lib.check_status(rc, "hjPartitionPush")
-        return received
+
+
+def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
+                   build_x: PeerExchange, probe_x: PeerExchange) -> tuple[int, int]:
+    """Both relations through the fused partition + exchange with ONE collective (the all-gather of both count rows) and ONE host
+    readback (the count matrices, needed to size the local join). Returns the tuples this rank receives (build, probe); they are all
+    there after the closing barrier. Raises HashJoinError — on every rank alike — when an owner would receive more than its buffer
+    holds (skew beyond the slack): nothing has been stored then, and radix_join() (NCCL all-to-all, exact sizes) is the fallback."""
+    group = build_x.group
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    build_x.barrier()                                               # nobody is still reading last step's buffers
+    cb, wsb = build_x.count(build_shard)
+    cp, wsp = probe_x.count(probe_shard)
+    matrix = torch.empty(world, 2 * world, dtype=torch.int64, device=build_shard.device)
+    dist.all_gather_into_tensor(matrix.view(-1), torch.cat([cb, cp]), group=group)      # matrix[src] = [build counts per dst | probe counts per dst]
+    host = matrix.cpu()                                             # the step's one host sync
+    mb, mp = host[:, :world], host[:, world:]
+    if int(mb.sum(0).max()) > build_x.capacity or int(mp.sum(0).max()) > probe_x.capacity:
+        raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
+    cursors = torch.cat([mb[:rank].sum(0), mp[:rank].sum(0)]).to(build_shard.device, non_blocking=True)   # first element of my region in every owner's buffer
+    build_x.push(build_shard, build_row_base, cursors[:world], wsb)
+    probe_x.push(probe_shard, probe_row_base, cursors[world:], wsp)
+    build_x.barrier()                                               # every rank's stores have landed
+    return int(mb[:, rank].sum()), int(mp[:, rank].sum())
 
 
 def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
                      build_x: PeerExchange, probe_x: PeerExchange, exchanged=None):
     """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink).
     ``exchanged`` (optional callable) runs once every rank's tuples have landed, before the local join (bench.py marks a phase there)."""
-    build_x.barrier()                                               # nobody is still reading last step's buffers
-    nb = build_x.push(build_shard, build_row_base)
-    npr = probe_x.push(probe_shard, probe_row_base)
-    build_x.barrier()                                               # every rank's stores have landed
+    nb, npr = exchange_fused(build_shard, build_row_base, probe_shard, probe_row_base, build_x, probe_x)
     if exchanged is not None:
         exchanged()
     return join.hash_join(build_x.keys[:nb], probe_x.keys[:npr], buildPayload=build_x.rows[:nb], probePayload=probe_x.rows[:npr])

@@ -200,6 +200,83 @@ def join_host(hostBuildRelation: torch.Tensor, hostProbeRelation: torch.Tensor, 
     return outR[:got], outS[:got], got
 
 
+# ---- the operators either side of the path --------------------------------------------------------------
+def semi_join(probeRelation_: torch.Tensor, table: HashTable, probePayload: torch.Tensor | None = None, probeRowBase: int = 0) -> torch.Tensor:
+    """Key-only mode: the row ids of the probe rows with at least one match in ``table``, each once (hjSemiJoinCount + hjSemiJoinWrite)."""
+    _require_cuda(probeRelation_, "probeRelation")
+    if not table.built:
+        raise _lib.HashJoinError("semi_join on a table that was never built")
+    lib = _lib.load()
+    scratch = _scratch_for(table, probeRelation_)
+    n = _lib.check_status(lib.hjSemiJoinCount(_ptr(probeRelation_), probeRelation_.numel(), table.key_bytes, _ptr(table.storage), _ptr(scratch), scratch.numel(),
+                                              _ptr(probePayload), probeRowBase & 0xFFFFFFFF, _stream_ptr()), "hjSemiJoinCount")
+    outS = torch.empty(n, dtype=torch.int32, device=probeRelation_.device)
+    if n:
+        _lib.check_status(lib.hjSemiJoinWrite(_ptr(probeRelation_), probeRelation_.numel(), table.key_bytes, _ptr(table.storage), _ptr(scratch), _ptr(outS),
+                                              _ptr(probePayload), probeRowBase & 0xFFFFFFFF, _stream_ptr()), "hjSemiJoinWrite")
+    return outS
+
+
+def gather(column: torch.Tensor, rowIds: torch.Tensor, rowBase: int = 0) -> torch.Tensor:
+    """Late materialisation of one payload column: out[k] = column[rowIds[k] - rowBase] (hjGather; 4- or 8-byte elements)."""
+    _require_cuda(column, "column"); _require_cuda(rowIds, "rowIds")
+    if rowIds.dtype != torch.int32 or column.element_size() not in (4, 8):
+        raise _lib.HashJoinError("gather takes int32 row ids and a column of 4- or 8-byte elements")
+    out = torch.empty(rowIds.numel(), dtype=column.dtype, device=column.device)
+    rc = _lib.load().hjGather(_ptr(column), column.element_size(), _ptr(rowIds), rowIds.numel(), rowBase & 0xFFFFFFFF, _ptr(out), _stream_ptr())
+    _lib.check_status(rc, "hjGather")
+    return out
+
+
+def nested_loop_join(table1: torch.Tensor, table2: torch.Tensor) -> torch.Tensor:
+    """What nested-loop.mlir:203-283 computes — the equi-join of two row-major int32 tables on column 0, result rows = all columns of
+    the larger table's row followed by the other table's non-key columns (:165-187) — as hash join + row materialisation on the GPU
+    (hjExtractColumn, hjBuild / hjCount / hjWrite, hjMaterializeRows). The larger table is the outer (x) side like the reference (:252-262)."""
+    for t in (table1, table2):
+        _require_cuda(t, "table")
+        if t.dtype != torch.int32 or t.dim() != 2:
+            raise _lib.HashJoinError("nested_loop_join takes 2-D int32 tables (memref<?x?xi32>)")
+    lib = _lib.load()
+    x, y = (table2, table1) if table1.shape[0] < table2.shape[0] else (table1, table2)      # :252: the smaller table is the inner loop
+    kx = torch.empty(x.shape[0], dtype=torch.int32, device=x.device); ky = torch.empty(y.shape[0], dtype=torch.int32, device=y.device)
+    _lib.check_status(lib.hjExtractColumn(_ptr(x), x.shape[0], x.shape[1], 0, _ptr(kx), _stream_ptr()), "hjExtractColumn")
+    _lib.check_status(lib.hjExtractColumn(_ptr(y), y.shape[0], y.shape[1], 0, _ptr(ky), _stream_ptr()), "hjExtractColumn")
+    py, px = hash_join(ky, kx)                                                               # build on the smaller table y, probe with x
+    out = torch.empty((px.numel(), x.shape[1] + y.shape[1] - 1), dtype=torch.int32, device=x.device)
+    rc = lib.hjMaterializeRows(_ptr(x), x.shape[1], _ptr(y), y.shape[1], _ptr(px), _ptr(py), px.numel(), _ptr(out), _stream_ptr())
+    _lib.check_status(rc, "hjMaterializeRows")
+    return out
+
+
+def pack_keys(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Two int32 key columns -> one int64 key column (hjPackKeys2x32): a two-column equi-join becomes an i64-key join."""
+    _require_cuda(a, "a"); _require_cuda(b, "b")
+    if a.dtype != torch.int32 or b.dtype != torch.int32 or a.numel() != b.numel():
+        raise _lib.HashJoinError("pack_keys takes two int32 columns of equal length")
+    out = torch.empty(a.numel(), dtype=torch.int64, device=a.device)
+    _lib.check_status(_lib.load().hjPackKeys2x32(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream_ptr()), "hjPackKeys2x32")
+    return out
+
+
+_SELECT_DTYPES = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
+SELECT_OPS = {"<": 0, "<=": 1, ">": 2, ">=": 3, "==": 4, "!=": 5}
+
+
+def selection(column: torch.Tensor, op: str, constant, rowBase: int = 0):
+    """Experiments/selection.mlir:34-155 (`d_arrayA[i] < 80.0` there): (values, row ids) of the rows with ``value op constant``, in input
+    order; count -> scan -> write through hjSelectCount / hjSelectWrite."""
+    _require_cuda(column, "column")
+    lib = _lib.load()
+    dt = _SELECT_DTYPES[column.dtype]
+    ic, fc = (int(constant), 0.0) if dt < 2 else (0, float(constant))
+    n = column.numel()
+    scratch = torch.empty(lib.hjSelectScratchBytes(n), dtype=torch.uint8, device=column.device)
+    cnt = _lib.check_status(lib.hjSelectCount(_ptr(column), n, dt, SELECT_OPS[op], ic, fc, _ptr(scratch), scratch.numel(), _stream_ptr()), "hjSelectCount")
+    vals = torch.empty(cnt, dtype=column.dtype, device=column.device); rows = torch.empty(cnt, dtype=torch.int32, device=column.device)
+    _lib.check_status(lib.hjSelectWrite(_ptr(column), n, dt, SELECT_OPS[op], ic, fc, _ptr(scratch), _ptr(vals), _ptr(rows), rowBase & 0xFFFFFFFF, _stream_ptr()), "hjSelectWrite")
+    return vals, rows
+
+
 def pair_digest(outR: torch.Tensor, outS: torch.Tensor) -> tuple[int, int]:
     """Order-independent (sum, xor) digest of a device pair stream (K6)."""
     out = (C.c_uint64 * 2)()

@@ -57,6 +57,11 @@ class Oracle:
             "oracle_v1_join_i32": (_i64, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, C.c_int]),
             "oracle_v1_join_i64": (_i64, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, C.c_int]),
             "oracle_nested_join_i32": (_i64, [_vp, _i64, _vp, _i64, _vp, _vp, _i64]),
+            "oracle_nested_join_rows_i32": (_i64, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64]),
+            "oracle_select_i32": (_i64, [_vp, _i64, _i32, _i32, _vp, _vp, _i64]),
+            "oracle_select_i64": (_i64, [_vp, _i64, _i32, _i64, _vp, _vp, _i64]),
+            "oracle_select_f32": (_i64, [_vp, _i64, _i32, C.c_float, _vp, _vp, _i64]),
+            "oracle_select_f64": (_i64, [_vp, _i64, _i32, C.c_double, _vp, _vp, _i64]),
             "oracle_init_index": (None, [_vp, _i64]),
             "oracle_pair_digest": (None, [_vp, _vp, _i64, _vp, _vp]),
             "oracle_gen_i32": (None, [_vp, _i64, C.c_int, _u64, _i64, _u64, _u32, _u64]),
@@ -116,6 +121,25 @@ class Oracle:
         outR = np.empty(n, dtype=np.int32); outS = np.empty(n, dtype=np.int32)
         self.lib.oracle_nested_join_i32(_p(R), R.size, _p(S), S.size, _p(outR), _p(outS), n)
         return outR, outS
+
+    def nested_join_rows(self, tx, ty):
+        """nested-loop.mlir:78-188 with row materialisation (:165-187): (n, x_cols + y_cols - 1) int32 array, x-major order."""
+        tx = np.ascontiguousarray(tx, dtype=np.int32); ty = np.ascontiguousarray(ty, dtype=np.int32)
+        args = (_p(tx), tx.shape[0], tx.shape[1], _p(ty), ty.shape[0], ty.shape[1])
+        n = int(self.lib.oracle_nested_join_rows_i32(*args, None, 0))
+        out = np.empty((n, tx.shape[1] + ty.shape[1] - 1), dtype=np.int32)
+        self.lib.oracle_nested_join_rows_i32(*args, _p(out), n)
+        return out
+
+    def select(self, col, op: int, c):
+        """Experiments/selection.mlir:34-155: (values, row ids) of the rows with `value OP c`, input order."""
+        col = np.ascontiguousarray(col)
+        fn = {np.dtype(np.int32): self.lib.oracle_select_i32, np.dtype(np.int64): self.lib.oracle_select_i64,
+              np.dtype(np.float32): self.lib.oracle_select_f32, np.dtype(np.float64): self.lib.oracle_select_f64}[col.dtype]
+        n = int(fn(_p(col), col.size, op, c, None, None, 0))
+        vals = np.empty(n, dtype=col.dtype); rows = np.empty(n, dtype=np.int32)
+        fn(_p(col), col.size, op, c, _p(vals), _p(rows), n)
+        return vals, rows
 
     def pair_digest(self, outR, outS) -> tuple[int, int]:
         outR = np.ascontiguousarray(outR, dtype=np.int32); outS = np.ascontiguousarray(outS, dtype=np.int32)

@@ -17,6 +17,8 @@
  *   oracle_v1_probe     <- join_v1.mlir:436-521              second chain walk, outR[w]=(i32)row, outS[w]=tid, w++
  *   oracle_v1_join      <- join_v1.mlir:525-649              the @main sequence init -> build -> count -> probe
  *   oracle_nested_join  <- nested-loop.mlir:78-188           O(n*m) compare, count -> scan -> write skeleton
+ *   oracle_nested_join_rows <- nested-loop.mlir:165-187      the same loops, materialising the joined rows
+ *   oracle_select_*     <- Experiments/selection.mlir:34-155 predicate -> count -> scan -> compacted write
  *   oracle_init_index   <- shared_stuff/shared.cpp:35-41     a[i] = i
  *
  * Parity pinning: the reference's own check() compiles here (oracle/Makefile -> oracle/_ref/shared.so) and
@@ -209,6 +211,46 @@ API int64_t oracle_nested_join_i32(const int32_t* R, int64_t nR, const int32_t* 
       }
   return total;
 }
+
+/* nested-loop.mlir:165-187 — the same loops with ROW MATERIALISATION: result row = all x_cols columns of table x's row i, then
+ * columns 1 .. y_cols-1 of table y's row j (the key, column 0, is not stored twice: the inner loop starts at j = 1, :181).
+ * Tables and result are row-major i32 (memref<?x?xi32>, :7-24). Returns the number of result rows; fills at most `capacity`. */
+API int64_t oracle_nested_join_rows_i32(const int32_t* tx, int64_t x_rows, int32_t x_cols, const int32_t* ty, int64_t y_rows, int32_t y_cols,
+                                        int32_t* result, int64_t capacity) {
+  const int64_t out_cols = (int64_t)x_cols + y_cols - 1;
+  int64_t total = 0;
+  for (int64_t i = 0; i < x_rows; i++)                                           /* thread = row of table x, :95-110 */
+    for (int64_t j = 0; j < y_rows; j++)                                         /* :160 */
+      if (tx[i * x_cols] == ty[j * y_cols]) {                                    /* :161-163: keys are column 0 */
+        if (result && total < capacity) {
+          for (int32_t c = 0; c < x_cols; c++) result[total * out_cols + c] = tx[i * x_cols + c];                    /* :170-173 */
+          for (int32_t c = 1; c < y_cols; c++) result[total * out_cols + x_cols - 1 + c] = ty[j * y_cols + c];       /* :179-184 */
+        }
+        total++;
+      }
+  return total;
+}
+
+/* Experiments/selection.mlir:34-155 — predicate, count, scan, compacted write (f32 `olt` there: ordered less-than, :62; the
+ * other comparisons and types are the same loop). op: 0 <, 1 <=, 2 >, 3 >=, 4 ==, 5 !=. Output in input order (what one block of
+ * the reference produces, :140-152; across blocks the reference's order depends on which atomic lands first, :118). */
+#define DEFINE_SELECT(NAME, T)                                                                                   \
+  API int64_t NAME(const T* col, int64_t n, int32_t op, T c, T* out_values, int32_t* out_rows, int64_t capacity) { \
+    int64_t total = 0;                                                                                           \
+    for (int64_t i = 0; i < n; i++) {                                                                            \
+      const T v = col[i];                                                                                        \
+      const int keep = op == 0 ? v < c : op == 1 ? v <= c : op == 2 ? v > c : op == 3 ? v >= c : op == 4 ? v == c : v != c; \
+      if (keep) {                                                                                                \
+        if (total < capacity) { if (out_values) out_values[total] = v; if (out_rows) out_rows[total] = (int32_t)i; } \
+        total++;                                                                                                 \
+      }                                                                                                          \
+    }                                                                                                            \
+    return total;                                                                                                \
+  }
+DEFINE_SELECT(oracle_select_i32, int32_t)
+DEFINE_SELECT(oracle_select_i64, int64_t)
+DEFINE_SELECT(oracle_select_f32, float)
+DEFINE_SELECT(oracle_select_f64, double)
 
 API void oracle_init_index(int32_t* a, int64_t n) { for (int64_t i = 0; i < n; i++) a[i] = (int32_t)i; } /* shared.cpp:35-41 */
 

@@ -96,3 +96,32 @@ def test_generators(oracle):
     assert zc[0] > 5 * zc[50] > 0                                              # heavy head, long tail
     m32 = oracle.generate(1000, 4, 1, 5, 0, 1000, 0, 0x9E3779B1)
     assert len(set(m32.tolist())) == 1000                                      # odd multiplier keeps uniqueness
+
+
+def test_nested_loop_rows_kat(oracle):
+    """nested-loop.mlir:208-212: tables val = i + j (20 x 3, 20 x 2) join on column 0 -> 20 rows [i, i+1, i+2, i+1] (:165-187)."""
+    t1 = (np.arange(20)[:, None] + np.arange(3)[None, :]).astype(np.int32)
+    t2 = (np.arange(20)[:, None] + np.arange(2)[None, :]).astype(np.int32)
+    want = np.stack([np.arange(20), np.arange(20) + 1, np.arange(20) + 2, np.arange(20) + 1], axis=1).astype(np.int32)
+    assert np.array_equal(oracle.nested_join_rows(t1, t2), want)
+    # the pair form and the row form agree: rows are the gathered pairs
+    oa, ob = oracle.nested_join(t1[:, 0], t2[:, 0])
+    assert np.array_equal(np.concatenate([t1[oa], t2[ob][:, 1:]], axis=1), oracle.nested_join_rows(t1, t2))
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 30, (200, 3)).astype(np.int32); b = rng.integers(0, 30, (150, 4)).astype(np.int32)
+    oa, ob = oracle.nested_join(a[:, 0], b[:, 0])
+    assert np.array_equal(np.concatenate([a[oa], b[ob][:, 1:]], axis=1), oracle.nested_join_rows(a, b))
+
+
+def test_selection_oracle_against_numpy(oracle):
+    """Experiments/selection.mlir:52,62: value < 80.0 (ordered: NaN fails); the restatement equals numpy's boolean indexing."""
+    rng = np.random.default_rng(6)
+    col = (rng.random(10_000) * 160).astype(np.float32); col[::31] = np.nan
+    v, r = oracle.select(col, 0, 80.0)
+    with np.errstate(invalid="ignore"):
+        keep = col < np.float32(80.0)
+    assert np.array_equal(v, col[keep]) and np.array_equal(r, np.nonzero(keep)[0])
+    x = rng.integers(-9, 9, 5000).astype(np.int64)
+    for op, f in enumerate((np.less, np.less_equal, np.greater, np.greater_equal, np.equal, np.not_equal)):
+        v, r = oracle.select(x, op, 2)
+        assert np.array_equal(v, x[f(x, 2)]) and np.array_equal(r, np.nonzero(f(x, 2))[0])

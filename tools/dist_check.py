@@ -25,6 +25,9 @@ def main():
     for name, b, p in (
         ("i32 unique x uniform", datagen.RelationSpec(200_003, 4, datagen.KIND_UNIQUE, 42, 0, 300_000), datagen.RelationSpec(1_000_003, 4, datagen.KIND_UNIFORM, 43, 0, 400_000)),
         ("i64 fk x zipf", datagen.RelationSpec(1 << 16, 8, datagen.KIND_FK, 46, 0, 1 << 14, 0, datagen.ODD_MUL64), datagen.RelationSpec(300_001, 8, datagen.KIND_ZIPF, 47, 0, 1 << 14, 0, datagen.ODD_MUL64)),
+        # local joins beyond L2 reach on every rank: the radix layout behind both multi-GPU plans
+        ("i64 unique big", datagen.RelationSpec(4_000_003 * world, 8, datagen.KIND_UNIQUE, 48, 0, 4_000_003 * world, 0, datagen.ODD_MUL64),
+         datagen.RelationSpec(6_000_001 * world, 8, datagen.KIND_UNIFORM, 49, 0, 6_000_000 * world, 0, datagen.ODD_MUL64)),
     ):
         R = o.generate(b.n, b.key_bytes, b.kind, b.seed, b.lo, b.domain, b.p16, b.key_mul)
         S = o.generate(p.n, p.key_bytes, p.kind, p.seed, p.lo, p.domain, p.p16, p.key_mul)
@@ -43,7 +46,20 @@ def main():
         a3, b3 = hjdist.radix_join_fused(dRs, blo, dS, plo, bx, px)
         a3, b3 = a3.clone(), b3.clone()
         a4, b4 = hjdist.radix_join_fused(dRs, blo, dS, plo, bx, px)      # buffers are reusable step after step
-        for plan, (a, bb) in (("broadcast", (a1, b1)), ("radix", (a2, b2)), ("radix-fused", (a3, b3)), ("radix-fused#2", (a4, b4))):
+        # receive buffers too small for the key distribution: every rank raises alike, nothing was stored, and the NCCL all-to-all
+        # plan (exact sizes) gives the oracle's result
+        from mlir_hashjoin_b200._lib import HashJoinError
+        tiny_b = hjdist.PeerExchange(max(16, b.n // (4 * world)), b.dtype, dev); tiny_p = hjdist.PeerExchange(max(16, p.n // (4 * world)), p.dtype, dev)
+        try:
+            hjdist.radix_join_fused(dRs, blo, dS, plo, tiny_b, tiny_p)
+            overflow_raised = False
+        except HashJoinError:
+            overflow_raised = True
+        a5, b5 = hjdist.radix_join(dRs, blo, dS, plo)
+        if rank == 0:
+            print(f"{name:22s} overflow   world={world} raised={overflow_raised} parity={'OK' if overflow_raised else 'FAIL'}", flush=True)
+            ok = ok and overflow_raised
+        for plan, (a, bb) in (("broadcast", (a1, b1)), ("radix", (a2, b2)), ("radix-fused", (a3, b3)), ("radix-fused#2", (a4, b4)), ("radix-after-overflow", (a5, b5))):
             n = torch.tensor([a.numel()], device=dev)
             sizes = [torch.zeros_like(n) for _ in range(world)]
             dist.all_gather(sizes, n)
