@@ -123,6 +123,12 @@ __device__ __forceinline__ uint32_t ld_keep_u32(const uint32_t* p, uint64_t pol)
   return r;
 }
 
+// bucket of the radix join's shared-memory table: a multiplicative hash is enough there (the keys of one partition are already a
+// pseudo-random subset, picked by radix_hash) and costs 2-4 instructions where mix64 costs ~20 (ncu: k_rj_join ran 55-70 % issue-bound)
+template <typename K> __device__ __forceinline__ uint32_t bucket_hash(K key);
+template <> __device__ __forceinline__ uint32_t bucket_hash<int32_t>(int32_t key) { return (uint32_t)key * 0x9E3779B1u; }
+template <> __device__ __forceinline__ uint32_t bucket_hash<int64_t>(int64_t key) { return (uint32_t)key * 0x9E3779B1u + (uint32_t)((uint64_t)key >> 32) * 0x85EBCA77u; }
+
 // scalar streaming loads (coalesced per warp at any alignment: the partition kernels read segments that start anywhere)
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p, uint64_t pol);
 template <> __device__ __forceinline__ int32_t ld_stream<int32_t>(const int32_t* p, uint64_t pol) {

@@ -1123,7 +1123,8 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
   if (semi) { cudaError_t e = cudaMemsetAsync(sv.counters + CTR_SEMI, 1, 1, stream); if (e != cudaSuccess) return e; }
   unsigned long long* total_out = sv.counters + CTR_TOTAL;
   if (h.mode == MODE_RADIX)
-    return radix_count(S, nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.scan_sums, sv.counters + CTR_TICKET_RADIX, total_out, carry_rows, probe_payload, probe_row_base, semi, stream);
+    return radix_count(S, nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.scan_sums, sv.counters + CTR_TICKET_RADIX, total_out, sv.mcache, sv.counters + CTR_RADIX_MULTI,
+                       carry_rows, probe_payload, probe_row_base, semi, stream);
   const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
   const bool tma = (h.policy & POLICY_TMA_COUNT) != 0;
   const int sparse_policy = (tma || h.mode == MODE_GROUP) ? 0 : (int)((h.policy >> POLICY_SPARSE_SHIFT) & 3);
@@ -1292,11 +1293,13 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
   if (ctr[CTR_TOTAL] == 0) return cudaSuccess;                      // nothing to emit (join_v1.mlir:600-601 skips the probe too)
   { cudaError_t e = cudaMemsetAsync(sv.counters + CTR_TICKET_GROUP_W, 0, 8, stream);                 // the write pass may be repeated after one count
     if (e == cudaSuccess) e = cudaMemsetAsync(sv.counters + CTR_TICKET_RADIX_W, 0, 8, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sv.counters + CTR_TICKET_RADIX_E, 0, 8, stream);
     if (e != cudaSuccess) return e; }
   const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
   if (h.mode == MODE_RADIX) {
     if (ctr[CTR_CARRIED]) { probe_payload = nullptr; probe_row_base = 0; }           // the partitioned copy already holds the probe row ids
-    return radix_write(nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.counters + CTR_TICKET_RADIX_W, outR, outS, ctr[CTR_CARRIED] != 0, probe_payload, probe_row_base, ctr[CTR_SEMI] != 0, stream);
+    return radix_write(nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.counters + CTR_TICKET_RADIX_W, sv.counters + CTR_TICKET_RADIX_E, sv.mcache, sv.counters + CTR_RADIX_MULTI,
+                       outR, outS, ctr[CTR_CARRIED] != 0, probe_payload, probe_row_base, ctr[CTR_SEMI] != 0, stream);
   }
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   const bool grouped = h.mode == MODE_GROUP, lists = !grouped && ctr[CTR_SPARSE] != 0, by_range = !grouped && !lists && h.mode == MODE_DENSE && h.all_present;
@@ -1342,26 +1345,37 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
-  __shared__ long long ticket;
-  __shared__ uint32_t wt[WARPS];
+  __shared__ TicketQueue tq;
+  __shared__ uint32_t wt[2][WARPS];
   __shared__ unsigned long long base_sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t n_pairs = hdr->n_pairs;
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
+  // gap-free unique key range: a probe key matches iff it is in range, so a tile's match count — all the look-back needs — is known
+  // from the range test alone and the look-back runs while the lookups are still in flight
+  const bool by_range = MODE == MODE_DENSE && hdr->all_present;
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
 
-  for (long long tile = next_ticket(tickets, &ticket); tile < ntiles; tile = next_ticket(tickets, &ticket)) {
+  long long tile = ticket_first(tickets, &tq);
+  for (uint32_t it = 0; tile < ntiles; it++) {
+    const long long pending = ticket_prefetch(tickets);
     const int64_t tile_base = tile * TILE;
     K key[KPT];
     #pragma unroll
     for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
     uint32_t m[KPT];
+    bool hit[KPT];
     if constexpr (MODE == MODE_DENSE) {
       #pragma unroll
       for (int k = 0; k < KPT; k++) {
         const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
-        m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
+        hit[k] = off < drange && elem_index<KPV>(tile_base, k) < nS;
+        m[k] = hit[k] ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
+      }
+      if (!by_range) {
+        #pragma unroll
+        for (int k = 0; k < KPT; k++) hit[k] = m[k] != ROW_NONE;
       }
     } else {
       #pragma unroll
@@ -1373,18 +1387,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
         for (int e = 0; e < KPV; e++) {
           const int k = v * KPV + e;
           m[k] = elem_index<KPV>(tile_base, k) < nS ? finish_probe_unique<K>(body, n_pairs, key[k], b[e]) : ROW_NONE;
+          hit[k] = m[k] != ROW_NONE;
         }
       }
     }
     unsigned mask[KPT];
     uint32_t wtot = 0;
     #pragma unroll
-    for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, m[k] != ROW_NONE); wtot += __popc(mask[k]); }
-    if (lane == 0) wt[warp] = wtot;
+    for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, hit[k]); wtot += __popc(mask[k]); }
+    if (lane == 0) wt[it & 1][warp] = wtot;
     __syncthreads();
     uint32_t wbase = 0, ttot = 0;
     #pragma unroll
-    for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[w]; wbase += w < warp ? x : 0u; ttot += x; }
+    for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[it & 1][w]; wbase += w < warp ? x : 0u; ttot += x; }
 
     // decoupled look-back, one warp: publish this tile's aggregate, then sum the tiles before it until an inclusive prefix shows up
     if (warp == 0) {
@@ -1414,7 +1429,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
     const unsigned lt = (1u << lane) - 1u;
     #pragma unroll
     for (int k = 0; k < KPT; k++) {
-      if (m[k] != ROW_NONE) {
+      if (hit[k]) {
         const unsigned long long dst = o + __popc(mask[k] & lt);
         if (dst < capacity) {
           const int64_t j = elem_index<KPV>(tile_base, k);
@@ -1424,6 +1439,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
       }
       o += __popc(mask[k]);
     }
+    tile = ticket_advance(&tq, it, pending);          // its barrier also orders this tile's read of base_sm before the next tile's write
   }
 }
 

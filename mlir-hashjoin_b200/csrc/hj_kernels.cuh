@@ -39,7 +39,8 @@ bool table_is_big(int64_t n_rows, int key_bytes);
 // first cnt[c] 8-byte entries (matched build row, position of the probe row inside the chunk) of its slice, see k_count_sparse.
 constexpr int SCRATCH_COUNTERS = 16;
 constexpr int CTR_TICKET_HASH = 0, CTR_TICKET_GROUP = 1, CTR_TICKET_GROUP_W = 2, CTR_SPARSE = 3 /* hit-list flag */, CTR_TICKET_SPARSE = 4,
-              CTR_TICKET_RADIX = 5, CTR_CARRIED = 6 /* radix copy carries probe row ids, not indices */, CTR_TOTAL = 7 /* result size */, CTR_TICKET_RADIX_W = 8, CTR_SEMI = 9 /* semi-join: one result row per matching probe row */;
+              CTR_TICKET_RADIX = 5, CTR_CARRIED = 6 /* radix copy carries probe row ids, not indices */, CTR_TOTAL = 7 /* result size */, CTR_TICKET_RADIX_W = 8, CTR_SEMI = 9 /* semi-join: one result row per matching probe row */,
+              CTR_TICKET_RADIX_E = 10, CTR_RADIX_MULTI = 11 /* radix items the match cache cannot describe */;
 struct ScratchView {
   uint32_t* mcache;
   uint2* hit_list;
@@ -103,9 +104,10 @@ int64_t radix_scratch_bytes(int64_t n_probe, int key_bytes);
 cudaError_t radix_build(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base, TableHeader* hdr, char* body, int64_t body_bytes, cudaStream_t stream);
 cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area,
                         unsigned long long* item_totals, unsigned long long* scan_block_sums, unsigned long long* ticket, unsigned long long* total_out,
-                        bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
+                        uint32_t* mcache, unsigned long long* n_multi, bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
 cudaError_t radix_write(int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area, unsigned long long* item_offsets,
-                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
+                        unsigned long long* ticket, unsigned long long* ticket_emit, const uint32_t* mcache, unsigned long long* n_multi,
+                        int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream);
 
 // hj_ops.cu: the operators either side of the join
 cudaError_t gather_column(const void* column, int elem_bytes, const int32_t* rows, int64_t n, uint32_t row_base, void* out, cudaStream_t stream);

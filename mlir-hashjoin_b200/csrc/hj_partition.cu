@@ -30,6 +30,7 @@ constexpr int RP_BLOCK_TILES = 8;
 constexpr int RP_BLOCK = RP_TILE * RP_BLOCK_TILES;        // 32 768 tuples per block
 constexpr int RP_MAX_FAN = 256;
 constexpr int SEL_OWNER = 0, SEL_RADIX = 1;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 struct RpBlock { uint32_t begin, end, seg, pad; };
 struct DigitArgs { uint32_t fan, shift, mask; };
@@ -164,7 +165,7 @@ struct RpSmem {
 };
 
 template <typename K, int SEL, bool PUSH>
-__global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
+__global__ void __launch_bounds__(RP_THREADS, 3) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
                                                               const RpBlock* __restrict__ blocks, const uint32_t* __restrict__ n_blocks, DigitArgs da,
                                                               K* __restrict__ out_keys, uint32_t* __restrict__ out_rows,
                                                               K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
@@ -181,13 +182,16 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(const K* __restric
     if (PUSH && threadIdx.x < fan) { sm.kptr[threadIdx.x] = dst_keys[threadIdx.x]; sm.rptr[threadIdx.x] = dst_rows[threadIdx.x]; }
   }
   const uint64_t pol = policy_evict_first();
-  K key[RP_ITEMS]; uint32_t row[RP_ITEMS];
+  K key[RP_ITEMS];
+  // Keys travel in registers from one tile's output loop to the next tile's rank phase; row ids are only pulled into L2 here and read
+  // in the stage phase (an L2 hit): holding them too costs 8 more registers per thread and with them the third CTA per SM
+  // (ncu, 2 CTAs: 50 % warps active, long-scoreboard + barrier stalls of 12-14 warps per issue slot, DRAM at 37-43 %).
   auto load_tile = [&](uint32_t base) {                      // element e of this thread sits at base + e * RP_THREADS + tid: every load instruction is one
     #pragma unroll                                           // contiguous run per warp whatever the alignment of `base` (segments start anywhere)
     for (int e = 0; e < RP_ITEMS; e++) {
       const uint32_t i = base + e * RP_THREADS + threadIdx.x;
       key[e] = i < blk.end ? ld_stream<K>(keys + i, pol) : K(0);
-      row[e] = rows ? (i < blk.end ? ld_stream<uint32_t>(rows + i, pol) : 0u) : row_base + i;
+      if (rows && i < blk.end && (threadIdx.x & 7) == 0) prefetch_l2(rows + i);      // one request per 32-byte sector
     }
   };
   load_tile(blk.begin);
@@ -218,15 +222,23 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(const K* __restric
     }
     __syncthreads();
     #pragma unroll
-    for (int e = 0; e < RP_ITEMS; e++) {
+    for (int e = 0; e < RP_ITEMS; e++) {                     // keys first: their registers are free again before the row ids arrive
       if (pr[e] != 0xFFFFFFFFu) {
         const uint32_t d = pr[e] >> 16, pos = sm.lbase[d] + (pr[e] & 0xFFFFu);
-        sm.skeys[pos] = key[e]; sm.srows[pos] = row[e]; sm.sdig[pos] = (unsigned char)d;
+        sm.skeys[pos] = key[e]; sm.sdig[pos] = (unsigned char)d;
+        pr[e] = pos;
+      }
+    }
+    #pragma unroll
+    for (int e = 0; e < RP_ITEMS; e++) {
+      if (pr[e] != 0xFFFFFFFFu) {
+        const uint32_t i = base + e * RP_THREADS + threadIdx.x;
+        sm.srows[pr[e]] = rows ? ld_stream<uint32_t>(rows + i, pol) : row_base + i;      // an L2 hit (prefetched with the keys)
       }
     }
     __syncthreads();
     if (base + RP_TILE < blk.end) load_tile(base + RP_TILE);  // in flight while this tile's runs are written
-    #pragma unroll 4
+    #pragma unroll 2
     for (uint32_t i = threadIdx.x; i < count; i += RP_THREADS) {   // digit-sorted: consecutive i -> consecutive destination addresses
       const K k = sm.skeys[i];
       const uint32_t r = sm.srows[i], d = sm.sdig[i];

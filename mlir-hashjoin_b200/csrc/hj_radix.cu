@@ -58,9 +58,9 @@ int64_t radix_table_bytes(int64_t n_build, int key_bytes) {
   return radix_area_bytes(n_build, key_bytes, b1, b2);
 }
 // probe side: the partition count is the TABLE's, unknown when the scratch is sized: room for the most partitions there can be
-struct RadixScratch { RadixArea a; unsigned long long* item_start; RjItem* items; int64_t max_items; };
+struct RadixScratch { RadixArea a; unsigned long long* item_start; RjItem* items; unsigned char* item_multi; int64_t max_items; };
 static int64_t radix_items_bytes(int64_t n_probe) {
-  return r256((((int64_t)1 << RJ_MAX_BITS) + 1 + 264) * 8) + r256(radix_max_items(n_probe) * (int64_t)sizeof(RjItem));
+  return r256((((int64_t)1 << RJ_MAX_BITS) + 1 + 264) * 8) + r256(radix_max_items(n_probe) * (int64_t)sizeof(RjItem)) + r256(radix_max_items(n_probe));
 }
 int64_t radix_scratch_bytes(int64_t n_probe, int key_bytes) { return radix_area_bytes(n_probe, key_bytes, 8, 8) + radix_items_bytes(n_probe); }
 static RadixScratch radix_scratch(char* base, int64_t n_probe, int key_bytes, int bits1, int bits2) {
@@ -68,6 +68,7 @@ static RadixScratch radix_scratch(char* base, int64_t n_probe, int key_bytes, in
   s.max_items = radix_max_items(n_probe);
   s.item_start = reinterpret_cast<unsigned long long*>(base);
   s.items = reinterpret_cast<RjItem*>(base + r256((((int64_t)1 << RJ_MAX_BITS) + 1 + 264) * 8));
+  s.item_multi = reinterpret_cast<unsigned char*>(s.items) + r256(s.max_items * (int64_t)sizeof(RjItem));
   s.a = radix_area(base + radix_items_bytes(n_probe), n_probe, key_bytes, bits1, bits2);
   return s;
 }
@@ -115,14 +116,18 @@ __global__ void __launch_bounds__(256) k_rj_items(const uint32_t* __restrict__ o
 // ---------------------------------------------------------------------------------------------------------
 // the join kernel: WRITE = false counts the matches of every item, WRITE = true emits them at the item's offset
 // ---------------------------------------------------------------------------------------------------------
-template <typename K> struct RjSmem { K ckey[RJ_CAP]; uint32_t crow[RJ_CAP]; uint32_t start[RJ_BUCKETS + 1]; };
+// start[] is read 8 consecutive buckets per thread in the scan: one pad word per 32 keeps those accesses (and everyone else's) conflict-free
+__device__ __forceinline__ uint32_t spad(uint32_t b) { return b + (b >> 5); }
+constexpr int RJ_START_WORDS = RJ_BUCKETS + RJ_BUCKETS / 32 + 2;
+constexpr int RJ_BUCKET_SHIFT = 32 - 12;                 // bucket = top 12 bits of bucket_hash
+static_assert(RJ_BUCKETS == 1 << 12, "bucket shift");
+template <typename K> struct RjSmem { K ckey[RJ_CAP]; uint32_t crow[RJ_CAP]; uint32_t start[RJ_START_WORDS]; };
 
 template <typename K>
 __device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, uint32_t r0, uint32_t nr, bool with_rows,
                                                uint64_t pol, uint32_t* scan_sm) {
   constexpr int PER = RJ_BUCKETS / RJ_THREADS;                       // bucket counters per thread in the scan
-  #pragma unroll
-  for (int i = 0; i < PER; i++) sm.start[i * RJ_THREADS + threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < RJ_START_WORDS; i += RJ_THREADS) sm.start[i] = 0;
   __syncthreads();
   uint32_t br[RJ_R_ITEMS];                                           // bucket << 16 | rank inside the bucket
   #pragma unroll
@@ -130,29 +135,29 @@ __device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restric
     const uint32_t i = u * RJ_THREADS + threadIdx.x;
     br[u] = 0;
     if (i < nr) {
-      const uint32_t b = radix_hash<K>(ld_stream<K>(Rk + r0 + i, pol)) & (RJ_BUCKETS - 1);
-      br[u] = (b << 16) | atomicAdd(&sm.start[b], 1u);
+      const uint32_t b = bucket_hash<K>(Rk[r0 + i]) >> RJ_BUCKET_SHIFT;            // default cache policy: the second look below must hit L2
+      br[u] = (b << 16) | atomicAdd(&sm.start[spad(b)], 1u);
     }
   }
   __syncthreads();
   {                                                                   // counts -> exclusive starts: thread t owns buckets [t * PER, (t + 1) * PER)
     uint32_t v[PER], sum = 0;
     #pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] = sm.start[threadIdx.x * PER + i]; sum += v[i]; }
+    for (int i = 0; i < PER; i++) { v[i] = sm.start[spad(threadIdx.x * PER + i)]; sum += v[i]; }
     uint32_t total;
     uint32_t run = block_exclusive_scan(sum, scan_sm, &total);
     #pragma unroll
-    for (int i = 0; i < PER; i++) { sm.start[threadIdx.x * PER + i] = run; run += v[i]; }
-    if (threadIdx.x == 0) sm.start[RJ_BUCKETS] = total;
+    for (int i = 0; i < PER; i++) { sm.start[spad(threadIdx.x * PER + i)] = run; run += v[i]; }
+    if (threadIdx.x == 0) sm.start[spad(RJ_BUCKETS)] = total;
   }
   __syncthreads();
   #pragma unroll
   for (int u = 0; u < RJ_R_ITEMS; u++) {
     const uint32_t i = u * RJ_THREADS + threadIdx.x;
     if (i < nr) {                                                     // second look at the tuple: an L1 / L2 hit (the partition was read a moment ago)
-      const uint32_t pos = sm.start[br[u] >> 16] + (br[u] & 0xFFFFu);
-      sm.ckey[pos] = Rk[r0 + i];
-      sm.crow[pos] = with_rows ? Rr[r0 + i] : 0u;                     // counting needs no row ids
+      const uint32_t pos = sm.start[spad(br[u] >> 16)] + (br[u] & 0xFFFFu);
+      sm.ckey[pos] = ld_stream<K>(Rk + r0 + i, pol);
+      sm.crow[pos] = with_rows ? ld_stream<uint32_t>(Rr + r0 + i, pol) : i;   // counting keeps the tuple's position instead: it goes into the match cache
     }
   }
   __syncthreads();
@@ -163,23 +168,32 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
                                                            const RjItem* __restrict__ items, const unsigned long long* __restrict__ n_items_ptr, unsigned long long* tickets,
                                                            unsigned long long* __restrict__ item_totals,       // count: out (matches per item); write: in (exclusive offsets)
                                                            int32_t* __restrict__ outR, int32_t* __restrict__ outS,
-                                                           const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows, int semi) {
+                                                           const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows, int semi,
+                                                           uint32_t* __restrict__ mcache,                       // count: out, per partitioned probe tuple: matched build position | NONE
+                                                           unsigned char* __restrict__ item_multi,              // count: out / write: in — items the match cache cannot describe
+                                                           unsigned long long* __restrict__ n_multi) {
   extern __shared__ __align__(16) unsigned char rj_raw[];
   RjSmem<K>& sm = *reinterpret_cast<RjSmem<K>*>(rj_raw);
   __shared__ TicketQueue tq;
-  __shared__ unsigned long long red[33];
+  __shared__ unsigned long long acc_cnt[2];                        // the item's match count and multi flag, double-buffered over the items
+  __shared__ uint32_t acc_multi[2];
   __shared__ uint32_t scan_sm[33];
   __shared__ uint32_t cursor;
+  if (threadIdx.x < 2) { acc_cnt[threadIdx.x] = 0; acc_multi[threadIdx.x] = 0; }
   const long long n_items = (long long)*n_items_ptr;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const uint64_t pol = policy_evict_first();
+  if (WRITE && *n_multi == 0) return;                             // every item was described by the match cache: k_rj_emit writes them all
   long long item = ticket_first(tickets, &tq);
   for (uint32_t it = 0; item < n_items; it++) {
     const long long pending = ticket_prefetch(tickets);
+    if (WRITE && !item_multi[item]) { item = ticket_advance(&tq, it, pending); continue; }      // uniform: k_rj_emit has this item
     const RjItem w = items[item];
     unsigned long long cnt = 0;
     unsigned long long obase = 0;
+    const bool one_round = w.r1 - w.r0 <= (uint32_t)RJ_CAP;
+    bool multi = !one_round && !semi;                               // a key may match in several rounds: no single cache entry can say so
     if (WRITE) { obase = item_totals[item]; if (threadIdx.x == 0) cursor = 0; }
     for (uint32_t r0 = w.r0; r0 < w.r1; r0 += RJ_CAP) {
       const uint32_t nr = w.r1 - r0 < (uint32_t)RJ_CAP ? w.r1 - r0 : (uint32_t)RJ_CAP;
@@ -193,11 +207,22 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
           for (int u = 0; u < U; u++) { const uint32_t j = j0 + u * RJ_THREADS + threadIdx.x; key[u] = j < w.s1 ? ld_stream<K>(Sk + j, pol) : K(0); }
           #pragma unroll
           for (int u = 0; u < U; u++) {
-            if (j0 + u * RJ_THREADS + threadIdx.x < w.s1) {
-              const uint32_t b = radix_hash<K>(key[u]) & (RJ_BUCKETS - 1);
-              uint32_t m = 0;
-              for (uint32_t p = sm.start[b], p1 = sm.start[b + 1]; p < p1; p++) m += sm.ckey[p] == key[u];
-              c += semi ? (m != 0) : m;                                                            // semi-join: a probe tuple counts once
+            const uint32_t j = j0 + u * RJ_THREADS + threadIdx.x;
+            if (j < w.s1) {
+              const uint32_t b = bucket_hash<K>(key[u]) >> RJ_BUCKET_SHIFT;
+              uint32_t m = 0, first = ROW_NONE;
+              for (uint32_t p = sm.start[spad(b)], p1 = sm.start[spad(b + 1)]; p < p1; p++) {
+                if (sm.ckey[p] == key[u]) { if (!m) first = sm.crow[p]; m++; }
+              }
+              // match cache: the matched build tuple's position in the partitioned build copy (or NONE); with it the write pass of
+              // this item is a pure stream (k_rj_emit) — valid while every probe tuple of the item has at most one match
+              if (!semi) {
+                c += m; multi |= m > 1;
+                if (one_round) mcache[j] = m ? r0 + first : ROW_NONE;
+              } else {                                                                             // semi-join: a probe tuple counts once, in the first round that matches it
+                const uint32_t prev = r0 == w.r0 ? ROW_NONE : mcache[j];                          // this thread's own entry of an earlier round
+                if (prev == ROW_NONE) { c += m != 0; if (m || r0 == w.r0) mcache[j] = m ? r0 + first : ROW_NONE; }
+              }
             }
           }
         }
@@ -219,9 +244,9 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
             bool active = j0 + u * RJ_THREADS + lane < w.s1;
             uint32_t prow = srow[u];
             if (!carried_rows) prow = probe_payload ? (active ? probe_payload[prow] : 0u) : probe_row_base + prow;   // the copy carries original indices
-            const uint32_t b = radix_hash<K>(key[u]) & (RJ_BUCKETS - 1);
-            uint32_t p = active ? sm.start[b] : 0u;
-            const uint32_t p1 = active ? sm.start[b + 1] : 0u;
+            const uint32_t b = bucket_hash<K>(key[u]) >> RJ_BUCKET_SHIFT;
+            uint32_t p = active ? sm.start[spad(b)] : 0u;
+            const uint32_t p1 = active ? sm.start[spad(b + 1)] : 0u;
             while (__any_sync(0xffffffffu, p < p1)) {
               bool hit = false; uint32_t brow = 0;
               if (p < p1) { hit = sm.ckey[p] == key[u]; brow = sm.crow[p]; p = (semi && hit) ? p1 : p + 1; }
@@ -242,10 +267,74 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
       }
       __syncthreads();                                            // the table is rebuilt by the next round / item
     }
-    if (!WRITE) {
-      cnt = block_reduce_sum(cnt, red);
-      if (threadIdx.x == 0) item_totals[item] = cnt;
+    const long long done = item;
+    if (!WRITE) {                                                   // one shared-memory atomic per warp; the barrier of ticket_advance closes the item
+      cnt = warp_reduce_sum(cnt);
+      const unsigned wm = __ballot_sync(0xffffffffu, multi);
+      if (lane == 0) { atomicAdd(&acc_cnt[it & 1], cnt); if (wm) acc_multi[it & 1] = 1; }
     }
+    item = ticket_advance(&tq, it, pending);
+    if (!WRITE && threadIdx.x == 0) {
+      item_totals[done] = acc_cnt[it & 1];
+      if (acc_multi[it & 1]) { item_multi[done] = 1; atomicAdd(n_multi, 1ULL); }
+      acc_cnt[it & 1] = 0; acc_multi[it & 1] = 0;                   // used again two items from now, several barriers away
+    }
+  }
+}
+
+// Write pass of the items the match cache describes (every probe tuple has at most one match: unique build keys, or a semi-join): no
+// table, no keys — each warp streams 32 cache words and probe row ids, ranks the hits with a ballot, claims its run of the item's output
+// range with one shared-memory atomic and gathers the build row ids (the partition's 16 KB of row ids stay in L1 / L2 while its items run).
+__global__ void __launch_bounds__(RJ_THREADS) k_rj_emit(const uint32_t* __restrict__ Rr, const uint32_t* __restrict__ Sr, const uint32_t* __restrict__ mcache,
+                                                        const RjItem* __restrict__ items, const unsigned char* __restrict__ item_multi,
+                                                        const unsigned long long* __restrict__ n_items_ptr, unsigned long long* tickets,
+                                                        const unsigned long long* __restrict__ item_offsets, int32_t* __restrict__ outR, int32_t* __restrict__ outS,
+                                                        const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows) {
+  __shared__ TicketQueue tq;
+  __shared__ uint32_t cursor[2];
+  const long long n_items = (long long)*n_items_ptr;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint64_t pol = policy_evict_first();
+  constexpr int U = 4;
+  if (threadIdx.x < 2) cursor[threadIdx.x] = 0;
+  long long item = ticket_first(tickets, &tq);
+  for (uint32_t it = 0; item < n_items; it++) {
+    const long long pending = ticket_prefetch(tickets);
+    if (!item_multi[item]) {                                        // uniform
+      const RjItem w = items[item];
+      const unsigned long long obase = item_offsets[item];
+      uint32_t* cur = &cursor[it & 1];                              // double-buffered: the other one is reset for the next item below
+      for (uint32_t j0 = w.s0 + (threadIdx.x & ~31u); j0 < w.s1; j0 += RJ_THREADS * U) {         // warp-uniform bounds
+        uint32_t mc[U], srow[U], brow[U];
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t j = j0 + u * RJ_THREADS + lane;
+          mc[u] = j < w.s1 ? ld_stream<uint32_t>(mcache + j, pol) : ROW_NONE;
+          srow[u] = j < w.s1 ? ld_stream<uint32_t>(Sr + j, pol) : 0u;
+        }
+        #pragma unroll
+        for (int u = 0; u < U; u++) brow[u] = (outR && mc[u] != ROW_NONE) ? Rr[mc[u]] : 0u;
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+          const bool hit = mc[u] != ROW_NONE;
+          const unsigned hm = __ballot_sync(0xffffffffu, hit);
+          if (hm) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cur, (uint32_t)__popc(hm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+              uint32_t prow = srow[u];
+              if (!carried_rows) prow = probe_payload ? probe_payload[prow] : probe_row_base + prow;
+              const unsigned long long pos = obase + base + __popc(hm & lt);
+              if (outR) outR[pos] = (int32_t)brow[u];
+              outS[pos] = (int32_t)prow;
+            }
+          }
+        }
+      }
+    }
+    if (threadIdx.x == 0) cursor[(it + 1) & 1] = 0;                  // nobody touches it during this item; ticket_advance's barrier publishes the reset
     item = ticket_advance(&tq, it, pending);
   }
 }
@@ -261,12 +350,13 @@ static unsigned rj_grid(Kern kern, size_t smem) {
 
 template <typename K, bool WRITE>
 static cudaError_t rj_launch(const RadixArea& r, const RadixScratch& s, unsigned long long* ticket, unsigned long long* item_totals, int32_t* outR, int32_t* outS,
-                             const uint32_t* probe_payload, uint32_t probe_row_base, int carried_rows, int semi, uint32_t n_parts, cudaStream_t stream) {
+                             const uint32_t* probe_payload, uint32_t probe_row_base, int carried_rows, int semi, uint32_t n_parts, uint32_t* mcache, unsigned long long* n_multi,
+                             cudaStream_t stream) {
   auto kern = k_rj_join<K, WRITE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RjSmem<K>));
   if (e != cudaSuccess) return e;
   kern<<<rj_grid(kern, sizeof(RjSmem<K>)), RJ_THREADS, sizeof(RjSmem<K>), stream>>>((const K*)r.keys, r.rows, (const K*)s.a.keys, s.a.rows, s.items, s.item_start + n_parts, ticket,
-                                                                                   item_totals, outR, outS, probe_payload, probe_row_base, carried_rows, semi);
+                                                                                   item_totals, outR, outS, probe_payload, probe_row_base, carried_rows, semi, mcache, s.item_multi, n_multi);
   return cudaGetLastError();
 }
 
@@ -274,6 +364,7 @@ static cudaError_t rj_launch(const RadixArea& r, const RadixScratch& s, unsigned
 // the caller. item_totals: u64[radix_max_items(nS) + 1] (the scratch's offsets array); total_out: where the scan leaves the result size.
 cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area,
                         unsigned long long* item_totals, unsigned long long* scan_block_sums, unsigned long long* ticket, unsigned long long* total_out,
+                        uint32_t* mcache, unsigned long long* n_multi,
                         bool carry_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream) {
   const int b1 = (int)hdr_host.rj_bits1, b2 = (int)hdr_host.rj_bits2;
   const uint32_t n_parts = 1u << (b1 + b2);
@@ -288,24 +379,29 @@ cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHea
   launch_scan(s.item_start, n_parts, s.item_start + n_parts + 1, nullptr, stream);
   k_rj_items<<<(n_parts + 255) / 256, 256, 0, stream>>>(r.offsets, s.a.offsets, n_parts, s.item_start, s.items);
   e = cudaMemsetAsync(item_totals, 0, (size_t)(s.max_items + 1) * 8, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s.item_multi, 0, (size_t)s.max_items, stream);
   if (e != cudaSuccess) return e;
-  e = key_bytes == 4 ? rj_launch<int32_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, semi ? 1 : 0, n_parts, stream)
-                     : rj_launch<int64_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, semi ? 1 : 0, n_parts, stream);
+  e = key_bytes == 4 ? rj_launch<int32_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, semi ? 1 : 0, n_parts, mcache, n_multi, stream)
+                     : rj_launch<int64_t, false>(r, s, ticket, item_totals, nullptr, nullptr, nullptr, 0, 1, semi ? 1 : 0, n_parts, mcache, n_multi, stream);
   if (e != cudaSuccess) return e;
   launch_scan(item_totals, s.max_items, scan_block_sums, total_out, stream);
   return cudaGetLastError();
 }
 
 cudaError_t radix_write(int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area, unsigned long long* item_offsets,
-                        unsigned long long* ticket, int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream) {
+                        unsigned long long* ticket, unsigned long long* ticket_emit, const uint32_t* mcache, unsigned long long* n_multi,
+                        int32_t* outR, int32_t* outS, bool carried_rows, const uint32_t* probe_payload, uint32_t probe_row_base, bool semi, cudaStream_t stream) {
   const int b1 = (int)hdr_host.rj_bits1, b2 = (int)hdr_host.rj_bits2;
   const uint32_t n_parts = 1u << (b1 + b2);
   const RadixScratch s = radix_scratch(scratch_area, nS, key_bytes, b1, b2);
   RadixArea r;
   r.keys = const_cast<char*>(body) + hdr_host.rj_keys_off; r.rows = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_rows_off);
   r.offsets = reinterpret_cast<uint32_t*>(const_cast<char*>(body) + hdr_host.rj_offs_off);
-  return key_bytes == 4 ? rj_launch<int32_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, semi ? 1 : 0, n_parts, stream)
-                        : rj_launch<int64_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, semi ? 1 : 0, n_parts, stream);
+  k_rj_emit<<<148 * 4, RJ_THREADS, 0, stream>>>(r.rows, s.a.rows, mcache, s.items, s.item_multi, s.item_start + n_parts, ticket_emit, item_offsets, outR, outS,
+                                               probe_payload, probe_row_base, carried_rows ? 1 : 0);
+  // the items the cache cannot describe (a probe tuple with several matches, partitions joined in rounds): the join again; exits at once when there are none
+  return key_bytes == 4 ? rj_launch<int32_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, semi ? 1 : 0, n_parts, const_cast<uint32_t*>(mcache), n_multi, stream)
+                        : rj_launch<int64_t, true>(r, s, ticket, item_offsets, outR, outS, probe_payload, probe_row_base, carried_rows ? 1 : 0, semi ? 1 : 0, n_parts, const_cast<uint32_t*>(mcache), n_multi, stream);
 }
 
 }  // namespace hj
