@@ -63,7 +63,14 @@ template <typename K> struct KeyTraits;
 // 32-bit hash of the radix join: the TOP bits pick the partition (two passes of <= 8 bits), the LOW bits the slot of the shared-memory table
 template <typename K> __host__ __device__ __forceinline__ uint32_t radix_hash(K key);
 template <> __host__ __device__ __forceinline__ uint32_t radix_hash<int32_t>(int32_t key) { return mix32((uint32_t)key + 0x68E31DA4u); }
-template <> __host__ __device__ __forceinline__ uint32_t radix_hash<int64_t>(int64_t key) { const uint64_t h = mix64((uint64_t)key + 0x2545F4914F6CDD1DULL); return (uint32_t)(h >> 32) ^ (uint32_t)h; }
+// i64: one 64-bit multiply folded to 32 bits, one 32-bit multiply-xorshift round (8 instructions; splitmix64 costs 22, and the partition
+// kernels hash every tuple four times: ncu showed k_rp_scatter at 2.8 warp instructions per tuple, 31 % issue-bound at 37 % of DRAM)
+template <> __host__ __device__ __forceinline__ uint32_t radix_hash<int64_t>(int64_t key) {
+  const uint64_t z = (uint64_t)key * 0x9E3779B97F4A7C15ULL;
+  uint32_t h = (uint32_t)(z >> 32) ^ (uint32_t)z;
+  h *= 0x85EBCA6Bu; h ^= h >> 15; h *= 0xC2B2AE35u;
+  return h;
+}
 
 template <> struct KeyTraits<int32_t> {
   static constexpr int SLOTS = 4;             // slots per 32-byte bucket

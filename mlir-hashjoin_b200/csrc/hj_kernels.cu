@@ -1324,6 +1324,8 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
 // tiles before it (tiles are taken by ticket, so every tile a CTA waits for is already running) and streams its pairs
 // straight into the result columns: no match cache, no second pass over the probe relation. The reference's call sequence
 // (countRows -> allocate -> probeRelation, join_v1.mlir:591,604-605) cannot use it; hjJoinFused can.
+// (Measured and rejected in round 2: publishing a tile's aggregate from the range test alone, before its lookups return, with the next
+// ticket fetched ahead: config 2 2.44 -> 3.68 ms.)
 // =========================================================================================================
 constexpr unsigned long long LB_AGG = 1ULL << 62, LB_INCL = 2ULL << 62, LB_MASK = (1ULL << 62) - 1;
 
@@ -1345,37 +1347,26 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
   using T = KeyTraits<K>;
   if (hdr->mode != MODE) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
-  __shared__ TicketQueue tq;
-  __shared__ uint32_t wt[2][WARPS];
+  __shared__ long long ticket;
+  __shared__ uint32_t wt[WARPS];
   __shared__ unsigned long long base_sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t n_pairs = hdr->n_pairs;
   const long long kmin = hdr->kmin;
   const unsigned long long drange = hdr->dense_range;
-  // gap-free unique key range: a probe key matches iff it is in range, so a tile's match count — all the look-back needs — is known
-  // from the range test alone and the look-back runs while the lookups are still in flight
-  const bool by_range = MODE == MODE_DENSE && hdr->all_present;
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
 
-  long long tile = ticket_first(tickets, &tq);
-  for (uint32_t it = 0; tile < ntiles; it++) {
-    const long long pending = ticket_prefetch(tickets);
+  for (long long tile = next_ticket(tickets, &ticket); tile < ntiles; tile = next_ticket(tickets, &ticket)) {
     const int64_t tile_base = tile * TILE;
     K key[KPT];
     #pragma unroll
     for (int v = 0; v < VECS_PER_THREAD; v++) load_vec_keys<K, VEC>(S, nS, tile_base + ((int64_t)v * BLOCK_THREADS + threadIdx.x) * KPV, pol_s, &key[v * KPV]);
     uint32_t m[KPT];
-    bool hit[KPT];
     if constexpr (MODE == MODE_DENSE) {
       #pragma unroll
       for (int k = 0; k < KPT; k++) {
         const unsigned long long off = (unsigned long long)((long long)key[k] - kmin);
-        hit[k] = off < drange && elem_index<KPV>(tile_base, k) < nS;
-        m[k] = hit[k] ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
-      }
-      if (!by_range) {
-        #pragma unroll
-        for (int k = 0; k < KPT; k++) hit[k] = m[k] != ROW_NONE;
+        m[k] = (off < drange && elem_index<KPV>(tile_base, k) < nS) ? ld_keep_u32(reinterpret_cast<const uint32_t*>(body) + off, pol_t) : ROW_NONE;
       }
     } else {
       #pragma unroll
@@ -1387,19 +1378,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
         for (int e = 0; e < KPV; e++) {
           const int k = v * KPV + e;
           m[k] = elem_index<KPV>(tile_base, k) < nS ? finish_probe_unique<K>(body, n_pairs, key[k], b[e]) : ROW_NONE;
-          hit[k] = m[k] != ROW_NONE;
         }
       }
     }
     unsigned mask[KPT];
     uint32_t wtot = 0;
     #pragma unroll
-    for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, hit[k]); wtot += __popc(mask[k]); }
-    if (lane == 0) wt[it & 1][warp] = wtot;
+    for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, m[k] != ROW_NONE); wtot += __popc(mask[k]); }
+    if (lane == 0) wt[warp] = wtot;
     __syncthreads();
     uint32_t wbase = 0, ttot = 0;
     #pragma unroll
-    for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[it & 1][w]; wbase += w < warp ? x : 0u; ttot += x; }
+    for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[w]; wbase += w < warp ? x : 0u; ttot += x; }
 
     // decoupled look-back, one warp: publish this tile's aggregate, then sum the tiles before it until an inclusive prefix shows up
     if (warp == 0) {
@@ -1429,7 +1419,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
     const unsigned lt = (1u << lane) - 1u;
     #pragma unroll
     for (int k = 0; k < KPT; k++) {
-      if (hit[k]) {
+      if (m[k] != ROW_NONE) {
         const unsigned long long dst = o + __popc(mask[k] & lt);
         if (dst < capacity) {
           const int64_t j = elem_index<KPV>(tile_base, k);
@@ -1439,7 +1429,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_join_fused(const K* __restric
       }
       o += __popc(mask[k]);
     }
-    tile = ticket_advance(&tq, it, pending);          // its barrier also orders this tile's read of base_sm before the next tile's write
   }
 }
 

@@ -7,7 +7,7 @@
 //   * hjPartitionCount + hjPartitionPush: the same pass with the exchange fused in — every run is stored straight into the
 //     receive buffer of the rank that owns it, through peer-mapped pointers (NVLink).
 //
-// One pass = three launches over BLOCKS of 32 768 tuples (a block never straddles two segments of the previous pass):
+// One pass = three launches over BLOCKS of 8 192 .. 131 072 tuples (a block never straddles two segments of the previous pass):
 //   k_rp_hist     per block: digit counts in shared memory -> mat[block][digit]; totals[segment][digit] by one atomic per (block, digit)
 //   k_rp_scan     per (segment, 32 digits): first destination of every (block, digit) = segment base + exclusive scan of the digit
 //                 totals + prefix over the segment's blocks   (coalesced 128-byte rows, two looks at the matrix)
@@ -18,6 +18,7 @@
 // Indices are 32-bit (relations hold < 2^32 rows, join_v1.mlir:604-605: row ids are i32).
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 #include "hj_common.cuh"
 #include "hj_kernels.cuh"
 
@@ -26,8 +27,12 @@ namespace hj {
 constexpr int RP_THREADS = 512;
 constexpr int RP_ITEMS = 8;
 constexpr int RP_TILE = RP_THREADS * RP_ITEMS;            // 4 096 tuples
-constexpr int RP_BLOCK_TILES = 8;
-constexpr int RP_BLOCK = RP_TILE * RP_BLOCK_TILES;        // 32 768 tuples per block
+// tuples per block: 2 .. 32 tiles, chosen so that a pass has about 2 000 blocks (148 SMs x 2 CTAs x ~7 waves): a block pays one cursor
+// load and one un-overlapped first tile, so bigger is better until the tail of the grid shows
+static inline uint32_t rp_block_tuples(int64_t n) {
+  const int64_t tiles = (n + RP_TILE - 1) / RP_TILE;
+  return (uint32_t)(std::min<int64_t>(32, std::max<int64_t>(2, tiles / 2000)) * RP_TILE);
+}
 constexpr int RP_MAX_FAN = 256;
 constexpr int SEL_OWNER = 0, SEL_RADIX = 1;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
@@ -42,10 +47,10 @@ __device__ __forceinline__ uint32_t rp_digit(K key, const DigitArgs& da) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// block descriptors: segment s = [seg_off[s], seg_off[s+1]) is cut into blocks of RP_BLOCK tuples. One CTA.
+// block descriptors: segment s = [seg_off[s], seg_off[s+1]) is cut into blocks of RP_BLOCK tuples (rp_block_tuples). One CTA.
 // seg_off == nullptr: a single segment [0, n).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rp_blocks(const uint32_t* __restrict__ seg_off, uint32_t nseg, uint32_t n, RpBlock* __restrict__ blocks,
+__global__ void __launch_bounds__(256) k_rp_blocks(const uint32_t* __restrict__ seg_off, uint32_t nseg, uint32_t n, uint32_t RP_BLOCK, RpBlock* __restrict__ blocks,
                                                    uint32_t* __restrict__ blk_start, uint32_t* __restrict__ n_blocks) {
   __shared__ uint32_t sm[33];
   __shared__ uint32_t first_sm[RP_MAX_FAN + 1], lo_sm[RP_MAX_FAN], hi_sm[RP_MAX_FAN];
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(256) k_rp_blocks(const uint32_t* __restrict__ 
     while (z - a > 1) { const uint32_t m = (a + z) >> 1; if (first_sm[m] <= b) a = m; else z = m; }
     const uint32_t j = b - first_sm[a];
     const uint32_t begin = lo_sm[a] + j * RP_BLOCK;
-    const uint32_t end = hi_sm[a] - begin < (uint32_t)RP_BLOCK ? hi_sm[a] : begin + RP_BLOCK;
+    const uint32_t end = hi_sm[a] - begin < RP_BLOCK ? hi_sm[a] : begin + RP_BLOCK;
     blocks[b] = RpBlock{begin, end, a, 0u};
   }
 }
@@ -165,7 +170,7 @@ struct RpSmem {
 };
 
 template <typename K, int SEL, bool PUSH>
-__global__ void __launch_bounds__(RP_THREADS, 3) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
+__global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
                                                               const RpBlock* __restrict__ blocks, const uint32_t* __restrict__ n_blocks, DigitArgs da,
                                                               K* __restrict__ out_keys, uint32_t* __restrict__ out_rows,
                                                               K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
@@ -182,27 +187,33 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rp_scatter(const K* __restric
     if (PUSH && threadIdx.x < fan) { sm.kptr[threadIdx.x] = dst_keys[threadIdx.x]; sm.rptr[threadIdx.x] = dst_rows[threadIdx.x]; }
   }
   const uint64_t pol = policy_evict_first();
-  K key[RP_ITEMS];
-  // Keys travel in registers from one tile's output loop to the next tile's rank phase; row ids are only pulled into L2 here and read
-  // in the stage phase (an L2 hit): holding them too costs 8 more registers per thread and with them the third CTA per SM
-  // (ncu, 2 CTAs: 50 % warps active, long-scoreboard + barrier stalls of 12-14 warps per issue slot, DRAM at 37-43 %).
-  auto load_tile = [&](uint32_t base) {                      // element e of this thread sits at base + e * RP_THREADS + tid: every load instruction is one
-    #pragma unroll                                           // contiguous run per warp whatever the alignment of `base` (segments start anywhere)
+  K key[RP_ITEMS]; uint32_t row[RP_ITEMS];
+  // Tile t+1 is loaded into registers right before tile t's output loop and tile t+2 is pulled into L2 at the same time, so the register
+  // loads are L2 hits. Full tiles (all but the last of a block) run a copy of the code without per-element bounds tests.
+  // (Measured and rejected: keys only in registers, row ids re-read in the stage phase, 40 registers for a third CTA per SM — 2^28 i64
+  // tuples per pass 2.13 -> 3.23 ms: the spills and the exposed row loads cost more than the occupancy gains.)
+  auto load_tile = [&](uint32_t base, auto full_tag) {       // element e of this thread sits at base + e * RP_THREADS + tid: every load instruction is one
+    constexpr bool FULL = decltype(full_tag)::value;         // contiguous run per warp whatever the alignment of `base` (segments start anywhere)
+    #pragma unroll
     for (int e = 0; e < RP_ITEMS; e++) {
       const uint32_t i = base + e * RP_THREADS + threadIdx.x;
-      key[e] = i < blk.end ? ld_stream<K>(keys + i, pol) : K(0);
-      if (rows && i < blk.end && (threadIdx.x & 7) == 0) prefetch_l2(rows + i);      // one request per 32-byte sector
+      key[e] = (FULL || i < blk.end) ? ld_stream<K>(keys + i, pol) : K(0);
+      row[e] = rows ? ((FULL || i < blk.end) ? ld_stream<uint32_t>(rows + i, pol) : 0u) : row_base + i;
     }
+    const uint32_t ahead = base + RP_TILE + threadIdx.x * (32 / sizeof(K));          // one prefetch per 32-byte sector of the tile after
+    if (threadIdx.x < RP_TILE * sizeof(K) / 32 && ahead < blk.end) prefetch_l2(keys + ahead);
+    if (rows && threadIdx.x < RP_TILE * 4 / 32 && base + RP_TILE + threadIdx.x * 8 < blk.end) prefetch_l2(rows + base + RP_TILE + threadIdx.x * 8);
   };
-  load_tile(blk.begin);
-  __syncthreads();
-  for (uint32_t base = blk.begin; base < blk.end; base += RP_TILE) {
-    const uint32_t count = blk.end - base < (uint32_t)RP_TILE ? blk.end - base : (uint32_t)RP_TILE;
+  auto load_next = [&](uint32_t base) {
+    if (base + RP_TILE <= blk.end) load_tile(base, std::true_type{}); else load_tile(base, std::false_type{});
+  };
+  auto tile_body = [&](uint32_t base, uint32_t count, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
     uint32_t pr[RP_ITEMS];                                   // digit << 16 | rank inside the digit
     #pragma unroll
     for (int e = 0; e < RP_ITEMS; e++) {
       pr[e] = 0xFFFFFFFFu;
-      if (e * RP_THREADS + threadIdx.x < count) {
+      if (FULL || e * RP_THREADS + threadIdx.x < count) {
         const uint32_t d = rp_digit<K, SEL>(key[e], da);
         pr[e] = (d << 16) | atomicAdd(&sm.cnt[d], 1u);
       }
@@ -222,32 +233,33 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rp_scatter(const K* __restric
     }
     __syncthreads();
     #pragma unroll
-    for (int e = 0; e < RP_ITEMS; e++) {                     // keys first: their registers are free again before the row ids arrive
-      if (pr[e] != 0xFFFFFFFFu) {
-        const uint32_t d = pr[e] >> 16, pos = sm.lbase[d] + (pr[e] & 0xFFFFu);
-        sm.skeys[pos] = key[e]; sm.sdig[pos] = (unsigned char)d;
-        pr[e] = pos;
-      }
-    }
-    #pragma unroll
     for (int e = 0; e < RP_ITEMS; e++) {
-      if (pr[e] != 0xFFFFFFFFu) {
-        const uint32_t i = base + e * RP_THREADS + threadIdx.x;
-        sm.srows[pr[e]] = rows ? ld_stream<uint32_t>(rows + i, pol) : row_base + i;      // an L2 hit (prefetched with the keys)
+      if (FULL || pr[e] != 0xFFFFFFFFu) {
+        const uint32_t d = pr[e] >> 16, pos = sm.lbase[d] + (pr[e] & 0xFFFFu);
+        sm.skeys[pos] = key[e]; sm.srows[pos] = row[e]; sm.sdig[pos] = (unsigned char)d;
       }
     }
     __syncthreads();
-    if (base + RP_TILE < blk.end) load_tile(base + RP_TILE);  // in flight while this tile's runs are written
+    if (base + RP_TILE < blk.end) load_next(base + RP_TILE);  // in flight while this tile's runs are written
     #pragma unroll 2
-    for (uint32_t i = threadIdx.x; i < count; i += RP_THREADS) {   // digit-sorted: consecutive i -> consecutive destination addresses
-      const K k = sm.skeys[i];
-      const uint32_t r = sm.srows[i], d = sm.sdig[i];
-      const uint32_t idx = sm.delta[d] + i;
-      if (PUSH) { sm.kptr[d][idx] = k; sm.rptr[d][idx] = r; }
-      else { out_keys[idx] = k; out_rows[idx] = r; }
+    for (int it = 0; it < RP_ITEMS; it++) {                   // digit-sorted: consecutive i -> consecutive destination addresses
+      const uint32_t i = it * RP_THREADS + threadIdx.x;
+      if (FULL || i < count) {
+        const K k = sm.skeys[i];
+        const uint32_t r = sm.srows[i], d = sm.sdig[i];
+        const uint32_t idx = sm.delta[d] + i;
+        if (PUSH) { sm.kptr[d][idx] = k; sm.rptr[d][idx] = r; }
+        else { out_keys[idx] = k; out_rows[idx] = r; }
+      }
     }
     // the next tile's rank phase only touches cnt (reset above); its scan and stage phases come after barriers every thread reaches
     // only once it has left this output loop
+  };
+  load_next(blk.begin);
+  __syncthreads();
+  for (uint32_t base = blk.begin; base < blk.end; base += RP_TILE) {
+    if (blk.end - base >= (uint32_t)RP_TILE) tile_body(base, (uint32_t)RP_TILE, std::true_type{});
+    else tile_body(base, blk.end - base, std::false_type{});
   }
 }
 
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rp_scatter(const K* __restric
 // host side
 // ---------------------------------------------------------------------------------------------------------
 static inline int64_t r256(int64_t x) { return (x + 255) / 256 * 256; }
-static inline int64_t rp_max_blocks(int64_t n, int nseg) { return (n + RP_BLOCK - 1) / RP_BLOCK + nseg + 1; }
+static inline int64_t rp_max_blocks(int64_t n, int nseg) { const int64_t b = rp_block_tuples(n); return (n + b - 1) / b + nseg + 1; }
 
 // workspace of one pass: [n_blocks u32 (256 B)] [blk_start u32 x (nseg + 1)] [totals u32 x nseg x fan] [blocks] [mat u32 x blocks x fan]
 struct RpWorkspace { uint32_t* n_blocks; uint32_t* blk_start; uint32_t* totals; RpBlock* blocks; uint32_t* mat; int64_t max_blocks; };
@@ -290,7 +302,7 @@ template <typename K, int SEL>
 static cudaError_t rp_hist(const void* keys, int64_t n, const uint32_t* seg_off, int nseg, DigitArgs da, const RpWorkspace& w, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(w.totals, 0, (size_t)nseg * da.fan * 4, stream);
   if (e != cudaSuccess) return e;
-  k_rp_blocks<<<1, 256, 0, stream>>>(seg_off, (uint32_t)nseg, (uint32_t)n, w.blocks, w.blk_start, w.n_blocks);
+  k_rp_blocks<<<1, 256, 0, stream>>>(seg_off, (uint32_t)nseg, (uint32_t)n, rp_block_tuples(n), w.blocks, w.blk_start, w.n_blocks);
   k_rp_hist<K, SEL><<<(unsigned)w.max_blocks, RP_THREADS, 0, stream>>>((const K*)keys, w.blocks, w.n_blocks, da, w.mat, w.totals);
   return cudaGetLastError();
 }

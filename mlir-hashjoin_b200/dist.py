@@ -141,16 +141,16 @@ def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: 
 
 
 def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
-                     build_x: PeerExchange, probe_x: PeerExchange, exchanged=None):
+                     build_x: PeerExchange, probe_x: PeerExchange, exchanged=None, table: join.HashTable | None = None):
     """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink).
     ``exchanged`` (optional callable) runs once every rank's tuples have landed, before the local join (bench.py marks a phase there)."""
     nb, npr = exchange_fused(build_shard, build_row_base, probe_shard, probe_row_base, build_x, probe_x)
     if exchanged is not None:
         exchanged()
-    return join.hash_join(build_x.keys[:nb], probe_x.keys[:npr], buildPayload=build_x.rows[:nb], probePayload=probe_x.rows[:npr])
+    return join.hash_join(build_x.keys[:nb], probe_x.keys[:npr], table=table, buildPayload=build_x.rows[:nb], probePayload=probe_x.rows[:npr])
 
 
-def radix_join(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int, group=None):
+def radix_join(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int, group=None, table: join.HashTable | None = None):
     """Radix-partitioned join of range-sharded relations. Returns this rank's (build_row, probe_row) pairs, global row ids."""
     world = dist.get_world_size(group)
     bk, br, bo = partition(build_shard, build_row_base, world)
@@ -158,4 +158,4 @@ def radix_join(build_shard: torch.Tensor, build_row_base: int, probe_shard: torc
     bplan, pplan = exchange_plan(bo, group), exchange_plan(po, group)
     my_bk, my_br = exchange(bk, bplan, group), exchange(br, bplan, group)
     my_pk, my_pr = exchange(pk, pplan, group), exchange(pr, pplan, group)
-    return join.hash_join(my_bk, my_pk, buildPayload=my_br, probePayload=my_pr)
+    return join.hash_join(my_bk, my_pk, table=table, buildPayload=my_br, probePayload=my_pr)
