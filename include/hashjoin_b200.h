@@ -240,6 +240,8 @@ void hjSetDenseWaves(int32_t k);
 /* 1 (default): builds of >= 2^18 rows look at 16 x 4 096 sampled rows for duplicate keys first and go straight to the grouped layout
  * when they find some (the inline, unique-key build is otherwise attempted and aborted); 0: always attempt the inline layout. */
 void hjSetDupSample(int32_t on);
+/* Experiment switch: CTA shape of the radix-partition scatter kernel: 512 threads / 4 096-tuple tiles (default) or 256 / 2 048. */
+void hjSetPartitionThreads(int32_t threads);
 /* Layout the last hjBuild gave this table (diagnostic; one header readback): 0 = bucketised hash (unique keys), 1 = direct-address,
  * 2 = grouped (duplicate keys), 3 = radix-partitioned (beyond L2 reach); + 0x100 when the direct-address table is gap-free and unique, i.e. the count pass runs by range test. */
 int32_t hjTableLayout(const void* dTable, void* stream);

@@ -81,6 +81,7 @@ void hjSetTmaCount(int32_t on) { hj::set_tma_count(on); }
 void hjSetSparse(int32_t policy) { hj::set_sparse(policy); }
 void hjSetDenseWaves(int32_t k) { hj::set_dense_waves(k); }
 void hjSetDupSample(int32_t on) { hj::set_dup_sample(on); }
+void hjSetPartitionThreads(int32_t t) { hj::set_partition_threads(t); }
 
 // =========================================================================================================
 // A. legacy helper symbols

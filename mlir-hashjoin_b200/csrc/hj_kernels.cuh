@@ -60,6 +60,7 @@ void set_sparse(int policy);
 void set_dup_sample(int on);
 void set_dense_waves(int k);    // experiment: grid of the direct-address probe kernels
 void set_tma_count(int on);
+void set_partition_threads(int t);   // experiment: CTA shape of the partition scatter kernel (256 | 512)
 
 cudaError_t readback(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t stream);   // <= 1 KB through the calling thread's pinned block; synchronises
 

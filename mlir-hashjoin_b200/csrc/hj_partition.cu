@@ -156,35 +156,37 @@ __global__ void __launch_bounds__(RPSCAN_THREADS) k_rp_scan(uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 of 2: scatter
 // ---------------------------------------------------------------------------------------------------------
-template <typename K, bool PUSH>
+template <typename K, bool PUSH, int THREADS>
 struct RpSmem {
-  K skeys[RP_TILE];
-  uint32_t srows[RP_TILE];
+  static constexpr int TILE = THREADS * RP_ITEMS;
+  K skeys[TILE];
+  uint32_t srows[TILE];
   uint32_t cnt[RP_MAX_FAN];                   // tuples of each digit in the tile (rank counter), zero between tiles
   uint32_t lbase[RP_MAX_FAN];                 // first staged position of each digit
   uint32_t delta[RP_MAX_FAN];                 // destination index of staged position i of digit d: delta[d] + i (mod 2^32)
   uint32_t gcur[RP_MAX_FAN];                  // running destination cursor of each digit for this block
   K* kptr[PUSH ? RP_MAX_FAN : 1];             // per-digit destination buffers: only the push into peers' receive buffers has more than one
   uint32_t* rptr[PUSH ? RP_MAX_FAN : 1];
-  unsigned char sdig[RP_TILE];
+  unsigned char sdig[TILE];
 };
 
-template <typename K, int SEL, bool PUSH>
-__global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
+template <typename K, int SEL, bool PUSH, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
                                                               const RpBlock* __restrict__ blocks, const uint32_t* __restrict__ n_blocks, DigitArgs da,
                                                               K* __restrict__ out_keys, uint32_t* __restrict__ out_rows,
                                                               K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
                                                               const uint32_t* __restrict__ mat) {
   extern __shared__ __align__(16) unsigned char rp_raw[];
-  RpSmem<K, PUSH>& sm = *reinterpret_cast<RpSmem<K, PUSH>*>(rp_raw);
+  RpSmem<K, PUSH, THREADS>& sm = *reinterpret_cast<RpSmem<K, PUSH, THREADS>*>(rp_raw);
+  constexpr int RP_THREADS = THREADS, RP_TILE = THREADS * RP_ITEMS;             // shadow the file-scope geometry (that of k_rp_hist)
   const uint32_t b = blockIdx.x;
   if (b >= *n_blocks) return;
   const RpBlock blk = blocks[b];
   const uint32_t fan = da.fan;
-  if (threadIdx.x < RP_MAX_FAN) {
-    sm.cnt[threadIdx.x] = 0;
-    sm.gcur[threadIdx.x] = threadIdx.x < fan ? mat[(size_t)b * fan + threadIdx.x] : 0u;
-    if (PUSH && threadIdx.x < fan) { sm.kptr[threadIdx.x] = dst_keys[threadIdx.x]; sm.rptr[threadIdx.x] = dst_rows[threadIdx.x]; }
+  for (uint32_t d = threadIdx.x; d < RP_MAX_FAN; d += THREADS) {
+    sm.cnt[d] = 0;
+    sm.gcur[d] = d < fan ? mat[(size_t)b * fan + d] : 0u;
+    if (PUSH && d < fan) { sm.kptr[d] = dst_keys[d]; sm.rptr[d] = dst_rows[d]; }
   }
   const uint64_t pol = policy_evict_first();
   K key[RP_ITEMS]; uint32_t row[RP_ITEMS];
@@ -200,9 +202,13 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(const K* __restric
       key[e] = (FULL || i < blk.end) ? ld_stream<K>(keys + i, pol) : K(0);
       row[e] = rows ? ((FULL || i < blk.end) ? ld_stream<uint32_t>(rows + i, pol) : 0u) : row_base + i;
     }
-    const uint32_t ahead = base + RP_TILE + threadIdx.x * (32 / sizeof(K));          // one prefetch per 32-byte sector of the tile after
-    if (threadIdx.x < RP_TILE * sizeof(K) / 32 && ahead < blk.end) prefetch_l2(keys + ahead);
-    if (rows && threadIdx.x < RP_TILE * 4 / 32 && base + RP_TILE + threadIdx.x * 8 < blk.end) prefetch_l2(rows + base + RP_TILE + threadIdx.x * 8);
+    constexpr int KEYS_PER_SECTOR = 32 / sizeof(K), KEY_SECTORS = RP_TILE / KEYS_PER_SECTOR;   // the tile after: one prefetch per 32-byte sector
+    #pragma unroll
+    for (int q = 0; q < KEY_SECTORS / RP_THREADS; q++) {
+      const uint32_t ahead = base + RP_TILE + (q * RP_THREADS + threadIdx.x) * KEYS_PER_SECTOR;
+      if (ahead < blk.end) prefetch_l2(keys + ahead);
+    }
+    if (rows && base + RP_TILE + threadIdx.x * 8 < blk.end) prefetch_l2(rows + base + RP_TILE + threadIdx.x * 8);
   };
   auto load_next = [&](uint32_t base) {
     if (base + RP_TILE <= blk.end) load_tile(base, std::true_type{}); else load_tile(base, std::false_type{});
@@ -287,15 +293,25 @@ static RpWorkspace rp_workspace(void* ws, int64_t n, int nseg, int fan) {
   return w;
 }
 
+template <typename K, int SEL, bool PUSH, int THREADS>
+static cudaError_t rp_launch_scatter_t(const void* keys, const uint32_t* rows, uint32_t row_base, const RpWorkspace& w, DigitArgs da, void* out_keys, uint32_t* out_rows,
+                                       void* const* dst_keys, uint32_t* const* dst_rows, cudaStream_t stream) {
+  auto kern = k_rp_scatter<K, SEL, PUSH, THREADS>;
+  using Smem = RpSmem<K, PUSH, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));     // cheap, per device: no cached flag
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)w.max_blocks, THREADS, sizeof(Smem), stream>>>((const K*)keys, rows, row_base, w.blocks, w.n_blocks, da, (K*)out_keys, out_rows,
+                                                                (K* const*)dst_keys, dst_rows, w.mat);
+  return cudaGetLastError();
+}
+// CTA shape of the scatter kernel: 512 threads (4 096-tuple tiles, 2 CTAs per SM) or 256 threads (2 048-tuple tiles, 4 CTAs per SM)
+static int g_rp_threads = 0;
+void set_partition_threads(int t) { g_rp_threads = t; }
 template <typename K, int SEL, bool PUSH>
 static cudaError_t rp_launch_scatter(const void* keys, const uint32_t* rows, uint32_t row_base, const RpWorkspace& w, DigitArgs da, void* out_keys, uint32_t* out_rows,
                                      void* const* dst_keys, uint32_t* const* dst_rows, cudaStream_t stream) {
-  auto kern = k_rp_scatter<K, SEL, PUSH>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RpSmem<K, PUSH>));     // cheap, per device: no cached flag
-  if (e != cudaSuccess) return e;
-  kern<<<(unsigned)w.max_blocks, RP_THREADS, sizeof(RpSmem<K, PUSH>), stream>>>((const K*)keys, rows, row_base, w.blocks, w.n_blocks, da, (K*)out_keys, out_rows,
-                                                                              (K* const*)dst_keys, dst_rows, w.mat);
-  return cudaGetLastError();
+  if (g_rp_threads == 256) return rp_launch_scatter_t<K, SEL, PUSH, 256>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
+  return rp_launch_scatter_t<K, SEL, PUSH, 512>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
 }
 
 template <typename K, int SEL>

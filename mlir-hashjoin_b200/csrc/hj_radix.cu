@@ -6,7 +6,7 @@
 //           the top bits of radix_hash(key); the partitioned copy + its offsets ARE the table (no clear, no global atomics);
 //   count   the probe relation is partitioned the same way; a work item = (partition, <= 16 384 probe tuples of it). A CTA takes items
 //           by ticket, builds the partition's table in SHARED memory — 4 096 buckets in CSR form: one ATOMS.ADD per tuple ranks it inside
-//           its bucket, a block scan turns bucket counts into starts, the tuples land bucket-sorted; no sentinel, so every key value
+//           its bucket, a block scan turns bucket counts into a directory (first entry, entries), the tuples land bucket-sorted; no sentinel, so every key value
 //           stays legal, and no probe-sequence clustering, so duplicate keys cost exactly their multiplicity — streams its probe
 //           tuples through it and writes the item's match count; K3 (the same scan as the other layouts) turns item counts into
 //           offsets and the total;
@@ -116,18 +116,19 @@ __global__ void __launch_bounds__(256) k_rj_items(const uint32_t* __restrict__ o
 // ---------------------------------------------------------------------------------------------------------
 // the join kernel: WRITE = false counts the matches of every item, WRITE = true emits them at the item's offset
 // ---------------------------------------------------------------------------------------------------------
-// start[] is read 8 consecutive buckets per thread in the scan: one pad word per 32 keeps those accesses (and everyone else's) conflict-free
+// bucket directory: one word per bucket, first entry << 16 | entries (both < 2^13), so a probe needs ONE shared-memory load to know its
+// candidates. The scan reads 8 consecutive buckets per thread: one pad word per 32 keeps those accesses (and everyone else's) conflict-free.
 __device__ __forceinline__ uint32_t spad(uint32_t b) { return b + (b >> 5); }
-constexpr int RJ_START_WORDS = RJ_BUCKETS + RJ_BUCKETS / 32 + 2;
+constexpr int RJ_DIR_WORDS = RJ_BUCKETS + RJ_BUCKETS / 32 + 1;
 constexpr int RJ_BUCKET_SHIFT = 32 - 12;                 // bucket = top 12 bits of bucket_hash
-static_assert(RJ_BUCKETS == 1 << 12, "bucket shift");
-template <typename K> struct RjSmem { K ckey[RJ_CAP]; uint32_t crow[RJ_CAP]; uint32_t start[RJ_START_WORDS]; };
+static_assert(RJ_BUCKETS == 1 << 12 && RJ_CAP < (1 << 13), "bucket shift / directory packing");
+template <typename K> struct RjSmem { K ckey[RJ_CAP]; uint32_t crow[RJ_CAP]; uint32_t dir[RJ_DIR_WORDS]; };
 
 template <typename K>
 __device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restrict__ Rk, const uint32_t* __restrict__ Rr, uint32_t r0, uint32_t nr, bool with_rows,
                                                uint64_t pol, uint32_t* scan_sm) {
-  constexpr int PER = RJ_BUCKETS / RJ_THREADS;                       // bucket counters per thread in the scan
-  for (int i = threadIdx.x; i < RJ_START_WORDS; i += RJ_THREADS) sm.start[i] = 0;
+  constexpr int PER = RJ_BUCKETS / RJ_THREADS;                       // directory words per thread in the scan
+  for (int i = threadIdx.x; i < RJ_DIR_WORDS; i += RJ_THREADS) sm.dir[i] = 0;
   __syncthreads();
   uint32_t br[RJ_R_ITEMS];                                           // bucket << 16 | rank inside the bucket
   #pragma unroll
@@ -136,26 +137,25 @@ __device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restric
     br[u] = 0;
     if (i < nr) {
       const uint32_t b = bucket_hash<K>(Rk[r0 + i]) >> RJ_BUCKET_SHIFT;            // default cache policy: the second look below must hit L2
-      br[u] = (b << 16) | atomicAdd(&sm.start[spad(b)], 1u);
+      br[u] = (b << 16) | atomicAdd(&sm.dir[spad(b)], 1u);                         // the count sits in the low half: the returned value is the rank
     }
   }
   __syncthreads();
-  {                                                                   // counts -> exclusive starts: thread t owns buckets [t * PER, (t + 1) * PER)
+  {                                                                   // counts -> first << 16 | count: thread t owns buckets [t * PER, (t + 1) * PER)
     uint32_t v[PER], sum = 0;
     #pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] = sm.start[spad(threadIdx.x * PER + i)]; sum += v[i]; }
+    for (int i = 0; i < PER; i++) { v[i] = sm.dir[spad(threadIdx.x * PER + i)]; sum += v[i]; }
     uint32_t total;
     uint32_t run = block_exclusive_scan(sum, scan_sm, &total);
     #pragma unroll
-    for (int i = 0; i < PER; i++) { sm.start[spad(threadIdx.x * PER + i)] = run; run += v[i]; }
-    if (threadIdx.x == 0) sm.start[spad(RJ_BUCKETS)] = total;
+    for (int i = 0; i < PER; i++) { sm.dir[spad(threadIdx.x * PER + i)] = (run << 16) | v[i]; run += v[i]; }
   }
   __syncthreads();
   #pragma unroll
   for (int u = 0; u < RJ_R_ITEMS; u++) {
     const uint32_t i = u * RJ_THREADS + threadIdx.x;
     if (i < nr) {                                                     // second look at the tuple: an L1 / L2 hit (the partition was read a moment ago)
-      const uint32_t pos = sm.start[spad(br[u] >> 16)] + (br[u] & 0xFFFFu);
+      const uint32_t pos = (sm.dir[spad(br[u] >> 16)] >> 16) + (br[u] & 0xFFFFu);
       sm.ckey[pos] = ld_stream<K>(Rk + r0 + i, pol);
       sm.crow[pos] = with_rows ? ld_stream<uint32_t>(Rr + r0 + i, pol) : i;   // counting keeps the tuple's position instead: it goes into the match cache
     }
@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
             if (j < w.s1) {
               const uint32_t b = bucket_hash<K>(key[u]) >> RJ_BUCKET_SHIFT;
               uint32_t m = 0, first = ROW_NONE;
-              for (uint32_t p = sm.start[spad(b)], p1 = sm.start[spad(b + 1)]; p < p1; p++) {
+              const uint32_t de = sm.dir[spad(b)];
+              for (uint32_t p = de >> 16, p1 = (de >> 16) + (de & 0xFFFFu); p < p1; p++) {
                 if (sm.ckey[p] == key[u]) { if (!m) first = sm.crow[p]; m++; }
               }
               // match cache: the matched build tuple's position in the partitioned build copy (or NONE); with it the write pass of
@@ -245,8 +246,9 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
             uint32_t prow = srow[u];
             if (!carried_rows) prow = probe_payload ? (active ? probe_payload[prow] : 0u) : probe_row_base + prow;   // the copy carries original indices
             const uint32_t b = bucket_hash<K>(key[u]) >> RJ_BUCKET_SHIFT;
-            uint32_t p = active ? sm.start[spad(b)] : 0u;
-            const uint32_t p1 = active ? sm.start[spad(b + 1)] : 0u;
+            const uint32_t de = active ? sm.dir[spad(b)] : 0u;
+            uint32_t p = de >> 16;
+            const uint32_t p1 = (de >> 16) + (de & 0xFFFFu);
             while (__any_sync(0xffffffffu, p < p1)) {
               bool hit = false; uint32_t brow = 0;
               if (p < p1) { hit = sm.ckey[p] == key[u]; brow = sm.crow[p]; p = (semi && hit) ? p1 : p + 1; }
