@@ -218,7 +218,7 @@ def main() -> None:
                     help="auto = library default (direct-address table for dense key ranges, counted by range test when gap-free and unique); "
                          "cache = direct-address table with the match cache only; hash = never the direct-address layout")
     ap.add_argument("--sparse", type=int, default=1, choices=[0, 1, 2], help="hit lists for selective joins (0 never, 1 sampled on the device, 2 always)")
-    ap.add_argument("--partition-threads", type=int, default=0, choices=[0, 256, 512], help="experiment: CTA shape of the partition scatter kernel")
+    ap.add_argument("--partition-threads", type=int, default=0, choices=[0, 256, 512, 1024], help="experiment: CTA shape of the partition scatter kernel")
     ap.add_argument("--no-radix", action="store_true", help="tables beyond L2 reach: one hash table in global memory instead of the radix join")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

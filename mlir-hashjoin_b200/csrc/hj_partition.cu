@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(RPSCAN_THREADS) k_rp_scan(uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 of 2: scatter
 // ---------------------------------------------------------------------------------------------------------
-template <typename K, bool PUSH, int THREADS>
+template <typename K, bool PUSH, int THREADS, int ITEMS>
 struct RpSmem {
-  static constexpr int TILE = THREADS * RP_ITEMS;
+  static constexpr int TILE = THREADS * ITEMS;
   K skeys[TILE];
   uint32_t srows[TILE];
   uint32_t cnt[RP_MAX_FAN];                   // tuples of each digit in the tile (rank counter), zero between tiles
@@ -170,15 +170,15 @@ struct RpSmem {
   unsigned char sdig[TILE];
 };
 
-template <typename K, int SEL, bool PUSH, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
+template <typename K, int SEL, bool PUSH, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 1024 / THREADS) k_rp_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
                                                               const RpBlock* __restrict__ blocks, const uint32_t* __restrict__ n_blocks, DigitArgs da,
                                                               K* __restrict__ out_keys, uint32_t* __restrict__ out_rows,
                                                               K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
                                                               const uint32_t* __restrict__ mat) {
   extern __shared__ __align__(16) unsigned char rp_raw[];
-  RpSmem<K, PUSH, THREADS>& sm = *reinterpret_cast<RpSmem<K, PUSH, THREADS>*>(rp_raw);
-  constexpr int RP_THREADS = THREADS, RP_TILE = THREADS * RP_ITEMS;             // shadow the file-scope geometry (that of k_rp_hist)
+  RpSmem<K, PUSH, THREADS, ITEMS>& sm = *reinterpret_cast<RpSmem<K, PUSH, THREADS, ITEMS>*>(rp_raw);
+  constexpr int RP_THREADS = THREADS, RP_ITEMS = ITEMS, RP_TILE = THREADS * ITEMS;   // shadow the file-scope geometry (that of k_rp_hist)
   const uint32_t b = blockIdx.x;
   if (b >= *n_blocks) return;
   const RpBlock blk = blocks[b];
@@ -293,24 +293,33 @@ static RpWorkspace rp_workspace(void* ws, int64_t n, int nseg, int fan) {
   return w;
 }
 
-template <typename K, int SEL, bool PUSH, int THREADS>
+template <typename K, int SEL, bool PUSH, int THREADS, int ITEMS = 8>
 static cudaError_t rp_launch_scatter_t(const void* keys, const uint32_t* rows, uint32_t row_base, const RpWorkspace& w, DigitArgs da, void* out_keys, uint32_t* out_rows,
                                        void* const* dst_keys, uint32_t* const* dst_rows, cudaStream_t stream) {
-  auto kern = k_rp_scatter<K, SEL, PUSH, THREADS>;
-  using Smem = RpSmem<K, PUSH, THREADS>;
+  auto kern = k_rp_scatter<K, SEL, PUSH, THREADS, ITEMS>;
+  using Smem = RpSmem<K, PUSH, THREADS, ITEMS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));     // cheap, per device: no cached flag
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)w.max_blocks, THREADS, sizeof(Smem), stream>>>((const K*)keys, rows, row_base, w.blocks, w.n_blocks, da, (K*)out_keys, out_rows,
                                                                 (K* const*)dst_keys, dst_rows, w.mat);
   return cudaGetLastError();
 }
-// CTA shape of the scatter kernel: 512 threads (4 096-tuple tiles, 2 CTAs per SM) or 256 threads (2 048-tuple tiles, 4 CTAs per SM)
+// CTA shape of the scatter kernel. What decides is the RUN LENGTH (tile / fan): a run is written as one contiguous piece at an arbitrary
+// alignment, and the shorter it is, the more partial 32-byte sectors reach L2 and DRAM. Measured on 2^28 i64 tuples, fan 256 (ncu, per pass):
+//   256 threads, 2 048-tuple tiles,  8-tuple runs, 4 CTAs / SM: 3.33 ms, DRAM 3.6 GB read + 4.5 GB written (5.3 GB algorithmic)
+//   512 threads, 4 096-tuple tiles, 16-tuple runs, 2 CTAs / SM: 2.13 ms, DRAM 2.8 + 3.7 GB
+//  1024 threads, 8 192-tuple tiles, 32-tuple runs, 1 CTA  / SM: ~1.8 ms (bench: 2^28 x 2^28 i64 join 14.6 -> 12.6 ms)
+// With fan <= 128 the 512-thread shape already has 32-tuple runs and its two CTAs per SM overlap each other's barriers (config 2 with
+// sparse keys, fan 64: 5.09 ms vs 5.22 ms with 1024 threads). 16 tuples per thread instead of 8 (longer runs at the same CTA shape) spills:
+// 112 bytes of stack per thread for i32 keys, 184 for i64, at the 64 registers two 512-thread CTAs leave. 0 = choose by fan.
 static int g_rp_threads = 0;
 void set_partition_threads(int t) { g_rp_threads = t; }
 template <typename K, int SEL, bool PUSH>
 static cudaError_t rp_launch_scatter(const void* keys, const uint32_t* rows, uint32_t row_base, const RpWorkspace& w, DigitArgs da, void* out_keys, uint32_t* out_rows,
                                      void* const* dst_keys, uint32_t* const* dst_rows, cudaStream_t stream) {
-  if (g_rp_threads == 256) return rp_launch_scatter_t<K, SEL, PUSH, 256>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
+  const int threads = g_rp_threads ? g_rp_threads : (da.fan > 128 ? 1024 : 512);
+  if (threads == 1024) return rp_launch_scatter_t<K, SEL, PUSH, 1024>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
+  if (threads == 256) return rp_launch_scatter_t<K, SEL, PUSH, 256>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
   return rp_launch_scatter_t<K, SEL, PUSH, 512>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
 }
 
