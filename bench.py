@@ -219,6 +219,7 @@ def main() -> None:
                          "cache = direct-address table with the match cache only; hash = never the direct-address layout")
     ap.add_argument("--sparse", type=int, default=1, choices=[0, 1, 2], help="hit lists for selective joins (0 never, 1 sampled on the device, 2 always)")
     ap.add_argument("--partition-threads", type=int, default=0, choices=[0, 256, 512, 1024], help="experiment: CTA shape of the partition scatter kernel")
+    ap.add_argument("--no-sliced", action="store_true", help="tables of 48 MB .. 1 GB of buckets: radix layout instead of one slice-ordered hash table")
     ap.add_argument("--no-radix", action="store_true", help="tables beyond L2 reach: one hash table in global memory instead of the radix join")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -273,6 +274,7 @@ def main() -> None:
     DENSE_POLICY = {"hash": 0, "cache": 1, "auto": 2}
     lib.hjSetSparse(args.sparse)
     lib.hjSetLocality(0 if args.no_radix else 1)
+    lib.hjSetSliced(0 if args.no_sliced else 1)
     if args.partition_threads:
         lib.hjSetPartitionThreads(args.partition_threads)
 
@@ -435,7 +437,7 @@ def main() -> None:
                                                      "radix": "radix partition, " + ("exchange fused into the partition kernel (NVLink peer stores)" if args.exchange == "fused" else "NCCL all-to-all")}[plan]),
                "ms_per_step": ms, "wall_ms_per_step": wall_ms, "value": (nR_job + nS_job) / (ms / 1e3), "unit": UNIT, "phases_ms": phases,
                "build_rows": nR_job, "probe_rows": nS_job, "result_pairs": tot_out, "pairs_per_s": tot_out / (ms / 1e3), "parity": parity,
-               "table_layout_chosen": LAYOUT_NAMES.get(layout_code & 0xFF, "?") + (", count by range test" if layout_code & 0x100 and not hit_lists else "") + (", hit lists" if hit_lists else ""),
+               "table_layout_chosen": LAYOUT_NAMES.get(layout_code & 0xFF, "?") + (", slice-ordered" if layout_code & 0x200 else "") + (", count by range test" if layout_code & 0x100 and not hit_lists else "") + (", hit lists" if hit_lists else ""),
                "steps": steps, "clocks": clocks}
         # ---- roofline: algorithmic bytes over the event-timed phases -----------------------------------------------
         if plan == "radix":

@@ -125,7 +125,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
                 void* dTable, int64_t tableBytes, void* stream);
 /* hjBuild with the table's policy stated per call instead of taken from the process defaults (hjSet*). The policy is stored in the
  * table header; every later hjCount / hjWrite on that table follows it, so tables built under different policies coexist.
- * policy = HJ_POLICY_DEFAULT or an OR of: HJ_POLICY_DENSE_* (one of), HJ_POLICY_RADIX, HJ_POLICY_LISTS_* (one of), HJ_POLICY_DUP_SAMPLE. */
+ * policy = HJ_POLICY_DEFAULT or an OR of: HJ_POLICY_DENSE_* (one of), HJ_POLICY_RADIX, HJ_POLICY_LISTS_* (one of), HJ_POLICY_DUP_SAMPLE, HJ_POLICY_NO_SLICES. */
 #define HJ_POLICY_DEFAULT 0xFFFFFFFFu
 #define HJ_POLICY_DENSE_OFF 0u          /* never the direct-address layout */
 #define HJ_POLICY_DENSE_CACHE 1u        /* direct-address layout for dense key ranges, lookups in the count pass (match cache) */
@@ -135,6 +135,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
 #define HJ_POLICY_LISTS_SAMPLED (1u << 3) /* hit lists for selective joins, decided on the device from a probe-key sample (default) */
 #define HJ_POLICY_LISTS_ALWAYS (2u << 3)
 #define HJ_POLICY_DUP_SAMPLE (1u << 5)  /* sample the build keys for duplicates before attempting a unique-key layout (default on) */
+#define HJ_POLICY_NO_SLICES (1u << 7)   /* never the slice-ordered inline layout: every table beyond L2 reach takes the radix layout (default off) */
 #define HJ_POLICY_TMA_COUNT (1u << 6)   /* experimental: TMA-staged streams in the direct-address count kernel (slower; default off) */
 int32_t hjBuildEx(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase,
                   void* dTable, int64_t tableBytes, uint32_t policy, void* stream);
@@ -224,8 +225,9 @@ void hjSetHostChunkRows(int64_t rows);
  * 2 (default): additionally a unique, gap-free key range (dense surrogate keys) is counted by range test alone and looked up once, in
  * the write pass (config 2: 1.84 instead of 1.99 ms). The policy in force at hjBuild decides. */
 void hjSetAllowDense(int32_t on);
-/* 1 (default): build relations whose hash table would not stay in L2 (> 48 MB of buckets) are joined by radix partitioning (two
- * passes, <= 65 536 partitions) and shared-memory tables; 0 builds one hash table in global memory and probes in input order. */
+/* 1 (default): build relations whose hash table would not stay in L2 (> 48 MB of buckets) are partitioned first: up to 1 GB of buckets
+ * (and unique keys) once, on the bucket hash, so that one global table is built and probed slice by slice; beyond that (or with
+ * duplicate keys) twice, into <= 65 536 partitions joined in shared memory. 0 builds one hash table and probes in input order. */
 void hjSetLocality(int32_t on);
 /* 1: the direct-address count kernel moves its two streams with TMA bulk copies (cp.async.bulk, per-warp mbarriers); 0 (default): LDG/STG.
  * Experimental: measured 3.7x slower on config 2 (profiles/README.md). */
@@ -240,10 +242,14 @@ void hjSetDenseWaves(int32_t k);
 /* 1 (default): builds of >= 2^18 rows look at 16 x 4 096 sampled rows for duplicate keys first and go straight to the grouped layout
  * when they find some (the inline, unique-key build is otherwise attempted and aborted); 0: always attempt the inline layout. */
 void hjSetDupSample(int32_t on);
+/* 1 (default): tables of 48 MB .. 1 GB of buckets with unique keys are built and probed as one hash table in table-slice order;
+ * 0: they take the radix layout like the bigger ones (HJ_POLICY_NO_SLICES). */
+void hjSetSliced(int32_t on);
 /* Experiment switch: CTA shape of the radix-partition scatter kernel: 512 threads / 4 096-tuple tiles (default) or 256 / 2 048. */
 void hjSetPartitionThreads(int32_t threads);
 /* Layout the last hjBuild gave this table (diagnostic; one header readback): 0 = bucketised hash (unique keys), 1 = direct-address,
- * 2 = grouped (duplicate keys), 3 = radix-partitioned (beyond L2 reach); + 0x100 when the direct-address table is gap-free and unique, i.e. the count pass runs by range test. */
+ * 2 = grouped (duplicate keys), 3 = radix-partitioned (beyond 1 GB of buckets, or duplicate keys beyond L2 reach); + 0x200 when layout 0 / 2
+ * was built in table-slice order (48 MB .. 1 GB of buckets: both relations are partitioned once on the bucket hash); + 0x100 when the direct-address table is gap-free and unique, i.e. the count pass runs by range test. */
 int32_t hjTableLayout(const void* dTable, void* stream);
 /* Which probe path the last hjCount on this scratch took: 0 = match cache, 1 = hit lists (diagnostic; one 8-byte readback). */
 int32_t hjProbePath(const void* dScratch, int64_t nS, int32_t keyBytes, void* stream);

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "hjSetDenseWaves": (None, [_i32]),
     "hjSetDupSample": (None, [_i32]),
     "hjSetPartitionThreads": (None, [_i32]),
+    "hjSetSliced": (None, [_i32]),
     "hjProbePath": (_i32, [_vp, _i64, _i32, _vp]),
     "hjTableLayout": (_i32, [_vp, _vp]),
     "hjLastErrorString": (C.c_char_p, []),

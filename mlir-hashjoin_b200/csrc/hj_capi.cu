@@ -82,6 +82,7 @@ void hjSetSparse(int32_t policy) { hj::set_sparse(policy); }
 void hjSetDenseWaves(int32_t k) { hj::set_dense_waves(k); }
 void hjSetDupSample(int32_t on) { hj::set_dup_sample(on); }
 void hjSetPartitionThreads(int32_t t) { hj::set_partition_threads(t); }
+void hjSetSliced(int32_t on) { hj::set_sliced(on); }
 
 // =========================================================================================================
 // A. legacy helper symbols
@@ -167,7 +168,7 @@ int32_t hjBuild(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dP
 }
 int32_t hjBuildEx(const void* dR, int64_t nR, int32_t keyBytes, const uint32_t* dPayload, uint32_t rowBase, void* dTable, int64_t tableBytes, uint32_t policy, void* stream) {
   if (policy == HJ_POLICY_DEFAULT) policy = hj::default_policy();
-  else if ((policy & 3u) == 3u || ((policy >> 3) & 3u) == 3u || (policy >> 7)) return fail(HJ_ERR_ARG, "hjBuildEx", "unknown policy bits");
+  else if ((policy & 3u) == 3u || ((policy >> 3) & 3u) == 3u || (policy >> 8)) return fail(HJ_ERR_ARG, "hjBuildEx", "unknown policy bits");
   return build_checked("hjBuildEx", dR, nR, keyBytes, dPayload, rowBase, dTable, tableBytes, policy, stream);
 }
 uint32_t hjDefaultPolicy(void) { return hj::default_policy(); }
@@ -307,7 +308,7 @@ int64_t hjJoinFused(const void* dS, int64_t nS, int32_t keyBytes, const void* dT
   HJ_CUDA("hjJoinFused", hj::join_fused_async(dS, nS, keyBytes, dTable, dScratch, dOutR, dOutS, capacity, dProbePayload, probeRowBase, S_(stream)));
   uint32_t mode = 0;
   HJ_CUDA("hjJoinFused", hj::read_table_mode(dTable, &mode, nullptr, S_(stream)));
-  if (mode >= 2) return fail(HJ_ERR_STATE, "hjJoinFused", "grouped (duplicate build keys) or radix (beyond L2 reach) table: use hjCount + hjWrite");
+  if ((mode & 0xFF) >= 2) return fail(HJ_ERR_STATE, "hjJoinFused", "grouped (duplicate build keys) or radix (beyond L2 reach) table: use hjCount + hjWrite");
   return hjCountResult(dScratch, nS, keyBytes, stream);
 }
 

@@ -43,7 +43,7 @@ struct TableHeader {
   unsigned long long work[4];     // ticket counters of the bounded-grid build kernels (hash, group count, group fill)
   uint32_t policy;                // hjBuildEx flags in force for this table (HJ_POLICY_*): the probe passes follow the TABLE, not a process global
   uint32_t rj_bits1, rj_bits2;    // radix layout: 2^(bits1 + bits2) partitions of the build relation, partition id = top bits of radix_hash(key)
-  uint32_t pad0;
+  uint32_t slice_bits;            // inline layout built in table-slice order: the probe relation is partitioned into 2^slice_bits slices first (0 = no)
   unsigned long long rj_keys_off, rj_rows_off, rj_offs_off;   // radix layout: byte offsets (inside the body) of the partitioned keys, row ids, u32 offsets[parts + 1]
 };
 static_assert(sizeof(TableHeader) <= HEADER_BYTES, "header too large");
@@ -81,6 +81,7 @@ template <> struct KeyTraits<int32_t> {
     pair = ((uint64_t)h * n_pairs) >> 32;     // n_pairs <= 2^32
     half = h & 1u;
   }
+  __device__ __forceinline__ static uint32_t home_hash32(int32_t key) { return mix32((uint32_t)key); }   // pair index is monotone in this: its top bits name a table slice
   __device__ __forceinline__ static uint32_t part_hash(int32_t key) { return mix32((uint32_t)key ^ 0x9E3779B9u); }
 };
 
@@ -92,6 +93,7 @@ template <> struct KeyTraits<int64_t> {
     pair = __umul64hi(h, n_pairs);
     half = (uint32_t)h & 1u;
   }
+  __device__ __forceinline__ static uint32_t home_hash32(int64_t key) { return (uint32_t)(mix64((uint64_t)key) >> 32); }
   __device__ __forceinline__ static uint32_t part_hash(int64_t key) { return (uint32_t)(mix64((uint64_t)key ^ 0x9E3779B97F4A7C15ULL) >> 32); }
 };
 

@@ -45,8 +45,22 @@ static int64_t table_part_bytes(int64_t n_rows, int key_bytes) {
 // by partition (K7, hj_radix.cu). The workspace still holds room for the bucketised layouts (policy bit HJ_POLICY_RADIX off).
 constexpr int64_t LOCALITY_MIN_BYTES = (int64_t)48 << 20;
 bool table_is_big(int64_t n_rows, int key_bytes) { return preferred_pairs(n_rows, key_bytes) * 64 > LOCALITY_MIN_BYTES; }
+// Between "fits L2" and "too big to slice": an inline table of at most 1 GB is still built and probed as ONE hash table in global memory,
+// but in TABLE-SLICE order — both relations are partitioned once (K5, <= 256 slices of <= 4 MB of table) on the hash bits that pick the
+// bucket pair, so the CTAs in flight touch a few L2-resident slices at a time. One partition pass per side instead of the radix layout's
+// two; beyond 1 GB the slices themselves outgrow L2 (round 1: 33 MB slices, 50 % hits) and the radix layout takes over.
+constexpr int64_t SLICED_MAX_BYTES = (int64_t)1 << 30, SLICE_BYTES = (int64_t)2 << 20;
+static bool table_sliceable(int64_t n_rows, int key_bytes) { return table_is_big(n_rows, key_bytes) && preferred_pairs(n_rows, key_bytes) * 64 <= SLICED_MAX_BYTES; }
+static int slice_bits_for(int64_t n_rows, int key_bytes) {
+  int bits = 4;
+  while (bits < 8 && (preferred_pairs(n_rows, key_bytes) * 64 >> bits) > SLICE_BYTES) bits++;
+  return bits;
+}
+// slice-ordered build: a partitioned copy of the build relation behind the table body: [keys][row ids][offsets u32 x 257][partition workspace]
+static int64_t sliced_extra_bytes(int64_t n, int key_bytes) { return round_up(n * key_bytes, 256) + round_up(n * 4, 256) + round_up(257 * 4, 256) + round_up(slice_partition_workspace_bytes(n, 8), 256); }
 int64_t table_bytes(int64_t n_rows, int key_bytes) {
   int64_t body = table_part_bytes(n_rows, key_bytes);
+  if (table_sliceable(n_rows, key_bytes)) body += sliced_extra_bytes(n_rows, key_bytes);
   if (table_is_big(n_rows, key_bytes)) body = std::max(body, round_up(radix_table_bytes(n_rows, key_bytes), 256));
   return HEADER_BYTES + body;
 }
@@ -88,7 +102,7 @@ ScratchView scratch_view(void* scratch, int64_t n_probe, int key_bytes) {
 constexpr int DENSE_MAX_FACTOR = 4;     // direct addressing when (kmax - kmin + 1) <= 4 x build rows and it fits
 
 __global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned long long n_rows, unsigned long long body_bytes, unsigned long long pairs, uint32_t policy) {
-  hdr->policy = policy; hdr->rj_bits1 = hdr->rj_bits2 = 0; hdr->rj_keys_off = hdr->rj_rows_off = hdr->rj_offs_off = 0;
+  hdr->policy = policy; hdr->slice_bits = 0; hdr->rj_bits1 = hdr->rj_bits2 = 0; hdr->rj_keys_off = hdr->rj_rows_off = hdr->rj_offs_off = 0;
   hdr->magic = HJ_MAGIC; hdr->key_bytes = key_bytes; hdr->mode = MODE_HASH; hdr->has_dups = 0; hdr->need_fallback = 0; hdr->all_present = 0;
   hdr->n_pairs = pairs; hdr->n_rows = n_rows; hdr->kmin = 0x7FFFFFFFFFFFFFFFLL; hdr->kmax = -0x7FFFFFFFFFFFFFFFLL - 1;
   hdr->dense_range = 0; hdr->body_bytes = body_bytes; hdr->pairs_cap = body_bytes / 64;
@@ -425,15 +439,17 @@ static int g_allow_dense = 2;   // 0 hash only, 1 direct-address layout with the
 static int g_locality = 1;      // radix join for tables beyond L2 reach
 static int g_dup_sample = 1;    // look at a sample of the build keys for duplicates before trying the inline (unique-key) layout
 static int g_sparse = 1;        // hit lists for selective joins: 0 never, 1 sampled on the device, 2 always (unique layouts)
+static int g_sliced = 1;       // slice-ordered inline layout for tables of 48 MB .. 1 GB of buckets (else: radix layout)
 static int g_tma_count = 0;     // measured on C2: 4.52 ms with TMA-staged streams vs 1.22 ms with LDG/STG (profiles/README.md) -> off
 void set_dup_sample(int on) { g_dup_sample = on; }
 void set_sparse(int policy) { g_sparse = policy; }
 void set_tma_count(int on) { g_tma_count = on; }
 void set_allow_dense(int on) { g_allow_dense = on; }
 void set_locality(int on) { g_locality = on; }
+void set_sliced(int on) { g_sliced = on; }
 uint32_t default_policy() {
   return (uint32_t)(g_allow_dense & 3) | (g_locality ? POLICY_RADIX : 0u) | ((uint32_t)(g_sparse & 3) << POLICY_SPARSE_SHIFT) | (g_dup_sample ? POLICY_DUP_SAMPLE : 0u) |
-         (g_tma_count ? POLICY_TMA_COUNT : 0u);
+         (g_tma_count ? POLICY_TMA_COUNT : 0u) | (g_sliced ? 0u : POLICY_NO_SLICES);
 }
 // Grid of the direct-address probe kernels: 0 = one chunk per CTA, k = at most k resident waves striding over the chunks.
 // Measured on config 2 (20 steps): count 1.231 / 1.248 / 1.233 / 1.231 ms and write 0.536 / 0.597 / 0.591 / 0.555 ms for k = 0 / 1 / 2 / 4.
@@ -466,8 +482,14 @@ static cudaError_t read_header(const void* table, TableHeader* out, cudaStream_t
 cudaError_t read_table_mode(const void* table, uint32_t* mode, uint32_t* all_present, cudaStream_t stream) {
   TableHeader h;
   cudaError_t e = read_header(table, &h, stream);
-  if (e == cudaSuccess) { *mode = h.mode; if (all_present) *all_present = h.all_present; }
+  if (e == cudaSuccess) { *mode = h.mode | (h.slice_bits ? 0x200u : 0u); if (all_present) *all_present = h.all_present; }
   return e;
+}
+
+__global__ void k_set_slices(TableHeader* hdr, uint32_t bits) { hdr->slice_bits = bits; }
+// probe row ids of a slice-ordered copy that carries original indices (the reference's countRows states no row ids): out[j] = id of row idx[j]
+__global__ void __launch_bounds__(BLOCK_THREADS) k_translate_rows(const uint32_t* __restrict__ idx, int64_t n, const uint32_t* __restrict__ payload, uint32_t row_base, uint32_t* __restrict__ out) {
+  for (int64_t j = blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x; j < n; j += (int64_t)gridDim.x * BLOCK_THREADS) out[j] = payload ? payload[idx[j]] : row_base + idx[j];
 }
 
 template <typename K>
@@ -486,7 +508,21 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
     TableHeader h;
     cudaError_t e = read_header(hdr, &h, stream);
     if (e != cudaSuccess) return e;
-    if (h.mode != MODE_DENSE) return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
+    if (h.mode != MODE_DENSE) {
+      if (h.has_dups || (policy & POLICY_NO_SLICES) || !table_sliceable(nR, (int)sizeof(K))) return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
+      // unique as far as the sample can tell, and small enough to slice: reorder (key, row id) by table slice, then the ordinary inline
+      // build runs over the copy (a duplicate it meets still sends it to the grouped layout, in slice order of the inline hash)
+      char* extra = body + table_part_bytes(nR, (int)sizeof(K));
+      K* sk = reinterpret_cast<K*>(extra);
+      uint32_t* sr = reinterpret_cast<uint32_t*>(extra + round_up(nR * (int64_t)sizeof(K), 256));
+      uint32_t* so = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sr) + round_up(nR * 4, 256));
+      void* ws = reinterpret_cast<char*>(so) + round_up(257 * 4, 256);
+      const int bits = slice_bits_for(nR, (int)sizeof(K));
+      e = slice_partition(R, payload, row_base, nR, (int)sizeof(K), bits, sk, sr, so, ws, slice_partition_workspace_bytes(nR, 8), stream);
+      if (e != cudaSuccess) return e;
+      k_set_slices<<<1, 1, 0, stream>>>(hdr, (uint32_t)bits);
+      R = sk; payload = sr; row_base = 0;
+    }
   }
   const bool vec = (reinterpret_cast<uintptr_t>(R) & 15) == 0;
   const int64_t need = (threads + BLOCK_THREADS - 1) / BLOCK_THREADS;
@@ -1125,6 +1161,14 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
   if (h.mode == MODE_RADIX)
     return radix_count(S, nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.scan_sums, sv.counters + CTR_TICKET_RADIX, total_out, sv.mcache, sv.counters + CTR_RADIX_MULTI,
                        carry_rows, probe_payload, probe_row_base, semi, stream);
+  if (h.slice_bits && (h.mode == MODE_HASH || h.mode == MODE_GROUP) && nS > 0) {       // slice-ordered table: the probe passes walk a slice-ordered copy
+    const SliceArea sa = slice_area(sv.radix, nS, key_bytes);
+    cudaError_t e = slice_partition(S, carry_rows ? probe_payload : nullptr, carry_rows ? probe_row_base : 0u, nS, key_bytes, (int)h.slice_bits,
+                                    sa.keys, sa.rows, sa.offsets, sa.ws, sa.ws_bytes, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sv.counters + CTR_SLICED, 1, 1, stream);
+    if (e != cudaSuccess) return e;
+    S = sa.keys;
+  }
   const unsigned long long* sparse_flag = sv.counters + CTR_SPARSE;
   const bool tma = (h.policy & POLICY_TMA_COUNT) != 0;
   const int sparse_policy = (tma || h.mode == MODE_GROUP) ? 0 : (int)((h.policy >> POLICY_SPARSE_SHIFT) & 3);
@@ -1300,6 +1344,16 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
     if (ctr[CTR_CARRIED]) { probe_payload = nullptr; probe_row_base = 0; }           // the partitioned copy already holds the probe row ids
     return radix_write(nS, key_bytes, h, body, sv.radix, sv.chunk_offsets, sv.counters + CTR_TICKET_RADIX_W, sv.counters + CTR_TICKET_RADIX_E, sv.mcache, sv.counters + CTR_RADIX_MULTI,
                        outR, outS, ctr[CTR_CARRIED] != 0, probe_payload, probe_row_base, ctr[CTR_SEMI] != 0, stream);
+  }
+  if (ctr[CTR_SLICED]) {                                             // the match cache / hit lists refer to the slice-ordered copy
+    const SliceArea sa = slice_area(sv.radix, nS, key_bytes);
+    S = sa.keys;
+    if (ctr[CTR_CARRIED]) probe_payload = sa.rows;                   // the copy carries the probe row ids themselves
+    else {                                                           // ... or original indices: translate once per write (the count pass was given no ids)
+      k_translate_rows<<<(unsigned)std::min<int64_t>(148 * 16, (nS + BLOCK_THREADS - 1) / BLOCK_THREADS), BLOCK_THREADS, 0, stream>>>(sa.rows, nS, probe_payload, probe_row_base, sa.rows2);
+      probe_payload = sa.rows2;
+    }
+    probe_row_base = 0;
   }
   const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   const bool grouped = h.mode == MODE_GROUP, lists = !grouped && ctr[CTR_SPARSE] != 0, by_range = !grouped && !lists && h.mode == MODE_DENSE && h.all_present;

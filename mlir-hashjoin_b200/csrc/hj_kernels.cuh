@@ -25,6 +25,7 @@ constexpr uint32_t POLICY_RADIX = 1u << 2;        // tables beyond L2 reach: rad
 constexpr int      POLICY_SPARSE_SHIFT = 3;       // 2 bits: hit lists never / sampled on the device / always
 constexpr uint32_t POLICY_DUP_SAMPLE = 1u << 5;   // sample the build keys for duplicates before trying the unique-key layouts
 constexpr uint32_t POLICY_TMA_COUNT = 1u << 6;    // experimental: TMA-staged streams in the direct-address count kernel
+constexpr uint32_t POLICY_NO_SLICES = 1u << 7;    // never the slice-ordered inline layout: every table beyond L2 reach takes the radix layout
 uint32_t default_policy();                        // what the hjSet* process defaults add up to
 
 int64_t preferred_pairs(int64_t n_rows, int key_bytes);
@@ -40,7 +41,8 @@ bool table_is_big(int64_t n_rows, int key_bytes);
 constexpr int SCRATCH_COUNTERS = 16;
 constexpr int CTR_TICKET_HASH = 0, CTR_TICKET_GROUP = 1, CTR_TICKET_GROUP_W = 2, CTR_SPARSE = 3 /* hit-list flag */, CTR_TICKET_SPARSE = 4,
               CTR_TICKET_RADIX = 5, CTR_CARRIED = 6 /* radix copy carries probe row ids, not indices */, CTR_TOTAL = 7 /* result size */, CTR_TICKET_RADIX_W = 8, CTR_SEMI = 9 /* semi-join: one result row per matching probe row */,
-              CTR_TICKET_RADIX_E = 10, CTR_RADIX_MULTI = 11 /* radix items the match cache cannot describe */;
+              CTR_TICKET_RADIX_E = 10, CTR_RADIX_MULTI = 11 /* radix items the match cache cannot describe */,
+              CTR_SLICED = 12 /* the probe passes run over the slice-ordered copy of the probe relation */;
 struct ScratchView {
   uint32_t* mcache;
   uint2* hit_list;
@@ -60,6 +62,7 @@ void set_sparse(int policy);
 void set_dup_sample(int on);
 void set_dense_waves(int k);    // experiment: grid of the direct-address probe kernels
 void set_tma_count(int on);
+void set_sliced(int on);
 void set_partition_threads(int t);   // experiment: CTA shape of the partition scatter kernel (256 | 512)
 
 cudaError_t readback(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t stream);   // <= 1 KB through the calling thread's pinned block; synchronises
@@ -91,6 +94,10 @@ cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_pa
 cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
                            void* const* peer_keys, uint32_t* const* peer_rows, const unsigned long long* cursors, void* workspace, int64_t workspace_bytes,
                            cudaStream_t stream);
+// One pass on the top `bits` bits of the hash that picks the inline table's bucket pair (slice s = the s-th 2^-bits of the table)
+int64_t slice_partition_workspace_bytes(int64_t n, int bits);
+cudaError_t slice_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int bits,
+                            void* out_keys, uint32_t* out_rows, uint32_t* offsets, void* ws, int64_t ws_bytes, cudaStream_t stream);
 // Two passes on the top bits1 + bits2 bits of radix_hash(key): 2^(bits1 + bits2) partitions, offsets u32[parts + 1] (device).
 int64_t radix_partition2_workspace_bytes(int64_t n, int bits1, int bits2);
 cudaError_t radix_partition2(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int bits1, int bits2,
@@ -102,6 +109,9 @@ void radix_bits(int64_t n_build, int* bits1, int* bits2);
 int64_t radix_max_items(int64_t n_probe);
 int64_t radix_table_bytes(int64_t n_build, int key_bytes);
 int64_t radix_scratch_bytes(int64_t n_probe, int key_bytes);
+// the slice-ordered copy of the probe relation lives in the same scratch area: [keys][row ids][offsets][translated row ids][partition workspace]
+struct SliceArea { void* keys; uint32_t* rows; uint32_t* offsets; uint32_t* rows2; void* ws; int64_t ws_bytes; };
+SliceArea slice_area(char* radix_area, int64_t n, int key_bytes);
 cudaError_t radix_build(const void* R, int64_t nR, int key_bytes, const uint32_t* payload, uint32_t row_base, TableHeader* hdr, char* body, int64_t body_bytes, cudaStream_t stream);
 cudaError_t radix_count(const void* S, int64_t nS, int key_bytes, const TableHeader& hdr_host, const char* body, char* scratch_area,
                         unsigned long long* item_totals, unsigned long long* scan_block_sums, unsigned long long* ticket, unsigned long long* total_out,

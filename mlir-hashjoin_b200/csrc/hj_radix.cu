@@ -73,6 +73,18 @@ static RadixScratch radix_scratch(char* base, int64_t n_probe, int key_bytes, in
   return s;
 }
 
+// The slice-ordered inline layout (hj_kernels.cu) keeps its partitioned copy of the probe relation in the same scratch area: it needs
+// one copy of (key, row id), 257 offsets, one more row-id array and a one-pass workspace — all smaller than what the radix layout has there.
+SliceArea slice_area(char* base, int64_t n, int key_bytes) {
+  SliceArea a;
+  a.keys = base; base += r256(n * key_bytes);
+  a.rows = reinterpret_cast<uint32_t*>(base); base += r256(n * 4);
+  a.offsets = reinterpret_cast<uint32_t*>(base); base += r256(257 * 4);
+  a.rows2 = reinterpret_cast<uint32_t*>(base); base += r256(n * 4);
+  a.ws = base; a.ws_bytes = slice_partition_workspace_bytes(n, 8);
+  return a;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // build: partition the build relation, record the layout in the header
 // ---------------------------------------------------------------------------------------------------------

@@ -391,8 +391,8 @@ def test_mid_size_vs_oracle(lib, cuda, oracle):
 @pytest.mark.parametrize("kb,nR,nS", [(4, 6_000_000, 20_000_003), (8, 4_000_000, 12_000_003)])
 @pytest.mark.parametrize("dups", [False, True])
 def test_big_table_path(lib, cuda, oracle, layout, dups, kb, nR, nS):
-    """Tables beyond L2 reach (> 48 MB of inline buckets): both relations are radix-partitioned first (K5) and joined partition by
-    partition. Sparse build keys (odd multiplier, no dense range), i32 and i64, unique (inline layout) and 3x duplicated (grouped
+    """Tables beyond L2 reach (> 48 MB of inline buckets): both relations are partitioned first (K5) — once, on the bucket hash, for one
+    global table built and probed slice by slice; or twice, for the radix join in shared memory. Sparse build keys (odd multiplier, no dense range), i32 and i64, unique (inline layout) and 3x duplicated (grouped
     layout), with payload columns, against the OpenMP oracle: count + order-independent digest, plus key equality of every pair.
     Also: the same join with the big-table path switched off, and the reference's call sequence (countRows has no probe row ids;
     hash_join states them at count time through hjCountRows)."""
@@ -413,6 +413,16 @@ def test_big_table_path(lib, cuda, oracle, layout, dups, kb, nR, nS):
     assert a.numel() == oa.size
     assert join.pair_digest(a, bb) == oracle.pair_digest(oa * 3 + 1, ob + 77)
     assert bool((dR[((a - 1) // 3).long()] == dS[(bb - 77).long()]).all())
+    lib.hjSetSliced(0)                                             # same join with the radix layout (two partition passes, shared-memory tables)
+    try:
+        ar, br = join.hash_join(dR, dS, buildPayload=pr, probePayload=ps)
+        tr = join.allocateHashTable(nR, None, dR.dtype, cuda)
+        join.buildTable(dR, tr, pr)
+        assert lib.hjTableLayout(tr.storage.data_ptr(), None) == 3
+        del tr
+    finally:
+        lib.hjSetSliced(1)
+    assert join.pair_digest(ar, br) == join.pair_digest(a, bb)
     lib.hjSetLocality(0)                                           # same join in input order: identical multiset
     a2, b2 = join.hash_join(dR, dS, buildPayload=pr, probePayload=ps)
     lib.hjSetLocality(1)
@@ -420,6 +430,9 @@ def test_big_table_path(lib, cuda, oracle, layout, dups, kb, nR, nS):
     # the reference's call sequence: row ids only at write time (payload column), and none at all (row base)
     table = join.allocateHashTable(nR, None, dR.dtype, cuda)
     join.buildTable(dR, table, pr)
+    # unique keys: one hash table built in table-slice order; duplicates: radix layout when the sample sees them, else (sample off) the
+    # grouped layout, rebuilt in slice order after the inline attempt met a duplicate
+    assert lib.hjTableLayout(table.storage.data_ptr(), None) == (0x200 if not dups else (0x202 if layout == "hash" else 3))
     n = join.countRows(dS, table)
     a3 = torch.empty(n, dtype=torch.int32, device=cuda); b3 = torch.empty(n, dtype=torch.int32, device=cuda)
     join.probeRelation(dS, table, a3, b3, ps)
