@@ -110,7 +110,18 @@ def bind_near_gpu(torch, dev) -> str:
         if not use:
             return f"no overlap between the GPU's CPUs and the {len(allowed)} this process may use: unchanged"
         os.sched_setaffinity(0, use)
-        return f"{len(use)} CPUs local to the GPU (of {len(allowed)} allowed)"
+        note = f"{len(use)} CPUs local to the GPU (of {len(allowed)} allowed)"
+        # pinned staging memory on the GPU's own NUMA node even when the container's CPU set spans one socket only
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node_file = Path(f"/sys/bus/pci/devices/{bdf}/numa_node")
+        if node_file.exists():
+            node = int(node_file.read_text().strip())
+            if node >= 0:
+                import ctypes
+                mask = ctypes.c_ulong(1 << node)
+                rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 64)      # set_mempolicy(MPOL_PREFERRED, {node})
+                note += f"; memory policy: prefer NUMA node {node}" + ("" if rc == 0 else f" (refused, errno {ctypes.get_errno()})")
+        return note
     except Exception as e:                                    # noqa: BLE001  (NVML missing / restricted: the run goes on unbound)
         return f"unbound ({type(e).__name__})"
 
