@@ -46,10 +46,11 @@ static int64_t table_part_bytes(int64_t n_rows, int key_bytes) {
 constexpr int64_t LOCALITY_MIN_BYTES = (int64_t)48 << 20;
 bool table_is_big(int64_t n_rows, int key_bytes) { return preferred_pairs(n_rows, key_bytes) * 64 > LOCALITY_MIN_BYTES; }
 // Between "fits L2" and "too big to slice": an inline table of at most 1 GB is still built and probed as ONE hash table in global memory,
-// but in TABLE-SLICE order — both relations are partitioned once (K5, <= 256 slices of <= 4 MB of table) on the hash bits that pick the
-// bucket pair, so the CTAs in flight touch a few L2-resident slices at a time. One partition pass per side instead of the radix layout's
+// but in TABLE-SLICE order — both relations are partitioned once (K5, 16 .. 256 slices of <= 8 MB of table) on the hash bits that pick the
+// bucket pair, so the CTAs in flight touch a few L2-resident slices at a time. (2 MB slices measured no better in the probe kernel — 1.58 ms
+// for 2^28 lookups either way — and cost the partition pass its long runs: 1.23 ms at 128 slices.) One partition pass per side instead of the radix layout's
 // two; beyond 1 GB the slices themselves outgrow L2 (round 1: 33 MB slices, 50 % hits) and the radix layout takes over.
-constexpr int64_t SLICED_MAX_BYTES = (int64_t)1 << 30, SLICE_BYTES = (int64_t)2 << 20;
+constexpr int64_t SLICED_MAX_BYTES = (int64_t)1 << 30, SLICE_BYTES = (int64_t)8 << 20;
 static bool table_sliceable(int64_t n_rows, int key_bytes) { return table_is_big(n_rows, key_bytes) && preferred_pairs(n_rows, key_bytes) * 64 <= SLICED_MAX_BYTES; }
 static int slice_bits_for(int64_t n_rows, int key_bytes) {
   int bits = 4;
