@@ -47,7 +47,7 @@ constexpr int64_t LOCALITY_MIN_BYTES = (int64_t)48 << 20;
 bool table_is_big(int64_t n_rows, int key_bytes) { return preferred_pairs(n_rows, key_bytes) * 64 > LOCALITY_MIN_BYTES; }
 // Between "fits L2" and "too big to slice": an inline table of at most 1 GB is still built and probed as ONE hash table in global memory,
 // but in TABLE-SLICE order — both relations are partitioned once (K5, 16 .. 256 slices of <= 8 MB of table) on the hash bits that pick the
-// bucket pair, so the CTAs in flight touch a few L2-resident slices at a time. (2 MB slices measured no better in the probe kernel — 1.58 ms
+// bucket pair (of the grouped table for duplicate keys), so the CTAs in flight touch a few L2-resident slices at a time. (2 MB slices measured no better in the probe kernel — 1.58 ms
 // for 2^28 lookups either way — and cost the partition pass its long runs: 1.23 ms at 128 slices.) One partition pass per side instead of the radix layout's
 // two; beyond 1 GB the slices themselves outgrow L2 (round 1: 33 MB slices, 50 % hits) and the radix layout takes over.
 constexpr int64_t SLICED_MAX_BYTES = (int64_t)1 << 30, SLICE_BYTES = (int64_t)8 << 20;
@@ -510,16 +510,17 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
     cudaError_t e = read_header(hdr, &h, stream);
     if (e != cudaSuccess) return e;
     if (h.mode != MODE_DENSE) {
-      if (h.has_dups || (policy & POLICY_NO_SLICES) || !table_sliceable(nR, (int)sizeof(K))) return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
-      // unique as far as the sample can tell, and small enough to slice: reorder (key, row id) by table slice, then the ordinary inline
-      // build runs over the copy (a duplicate it meets still sends it to the grouped layout, in slice order of the inline hash)
+      if ((policy & POLICY_NO_SLICES) || !table_sliceable(nR, (int)sizeof(K))) return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
+      // small enough to slice: reorder (key, row id) by table slice — of the grouped table when the sample already proved duplicates, else of
+      // the inline table — then the ordinary build sequence runs over the copy (a duplicate the inline build meets still sends it to the
+      // grouped layout, in the inline hash's slice order: correct, only less local for i32 keys)
       char* extra = body + table_part_bytes(nR, (int)sizeof(K));
       K* sk = reinterpret_cast<K*>(extra);
       uint32_t* sr = reinterpret_cast<uint32_t*>(extra + round_up(nR * (int64_t)sizeof(K), 256));
       uint32_t* so = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sr) + round_up(nR * 4, 256));
       void* ws = reinterpret_cast<char*>(so) + round_up(257 * 4, 256);
       const int bits = slice_bits_for(nR, (int)sizeof(K));
-      e = slice_partition(R, payload, row_base, nR, (int)sizeof(K), bits, sk, sr, so, ws, slice_partition_workspace_bytes(nR, 8), stream);
+      e = slice_partition(R, payload, row_base, nR, (int)sizeof(K), bits, h.has_dups != 0, sk, sr, so, ws, slice_partition_workspace_bytes(nR, 8), stream);
       if (e != cudaSuccess) return e;
       k_set_slices<<<1, 1, 0, stream>>>(hdr, (uint32_t)bits);
       R = sk; payload = sr; row_base = 0;
@@ -1164,7 +1165,7 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
                        carry_rows, probe_payload, probe_row_base, semi, stream);
   if (h.slice_bits && (h.mode == MODE_HASH || h.mode == MODE_GROUP) && nS > 0) {       // slice-ordered table: the probe passes walk a slice-ordered copy
     const SliceArea sa = slice_area(sv.radix, nS, key_bytes);
-    cudaError_t e = slice_partition(S, carry_rows ? probe_payload : nullptr, carry_rows ? probe_row_base : 0u, nS, key_bytes, (int)h.slice_bits,
+    cudaError_t e = slice_partition(S, carry_rows ? probe_payload : nullptr, carry_rows ? probe_row_base : 0u, nS, key_bytes, (int)h.slice_bits, h.mode == MODE_GROUP,
                                     sa.keys, sa.rows, sa.offsets, sa.ws, sa.ws_bytes, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(sv.counters + CTR_SLICED, 1, 1, stream);
     if (e != cudaSuccess) return e;

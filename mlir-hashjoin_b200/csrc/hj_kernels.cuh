@@ -94,9 +94,10 @@ cudaError_t partition_count(const void* keys, int64_t n, int key_bytes, int n_pa
 cudaError_t partition_push(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int n_parts,
                            void* const* peer_keys, uint32_t* const* peer_rows, const unsigned long long* cursors, void* workspace, int64_t workspace_bytes,
                            cudaStream_t stream);
-// One pass on the top `bits` bits of the hash that picks the inline table's bucket pair (slice s = the s-th 2^-bits of the table)
+// One pass on the top `bits` bits of the hash that picks the bucket pair of the inline (or, grouped = true, the grouped) table: slice s =
+// the s-th 2^-bits of the table
 int64_t slice_partition_workspace_bytes(int64_t n, int bits);
-cudaError_t slice_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int bits,
+cudaError_t slice_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int bits, bool grouped,
                             void* out_keys, uint32_t* out_rows, uint32_t* offsets, void* ws, int64_t ws_bytes, cudaStream_t stream);
 // Two passes on the top bits1 + bits2 bits of radix_hash(key): 2^(bits1 + bits2) partitions, offsets u32[parts + 1] (device).
 int64_t radix_partition2_workspace_bytes(int64_t n, int bits1, int bits2);

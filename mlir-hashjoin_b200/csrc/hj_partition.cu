@@ -34,7 +34,7 @@ static inline uint32_t rp_block_tuples(int64_t n) {
   return (uint32_t)(std::min<int64_t>(32, std::max<int64_t>(2, tiles / 2000)) * RP_TILE);
 }
 constexpr int RP_MAX_FAN = 256;
-constexpr int SEL_OWNER = 0, SEL_RADIX = 1, SEL_TABLE = 2;
+constexpr int SEL_OWNER = 0, SEL_RADIX = 1, SEL_TABLE = 2, SEL_GROUP = 3;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 struct RpBlock { uint32_t begin, end, seg, pad; };
@@ -44,6 +44,7 @@ template <typename K, int SEL>
 __device__ __forceinline__ uint32_t rp_digit(K key, const DigitArgs& da) {
   if (SEL == SEL_OWNER) return (uint32_t)(((uint64_t)KeyTraits<K>::part_hash(key) * da.fan) >> 32);      // any fan: which rank owns the key
   if (SEL == SEL_TABLE) return KeyTraits<K>::home_hash32(key) >> da.shift;                               // top bits of the hash that picks the bucket pair: a table slice
+  if (SEL == SEL_GROUP) return KeyTraits<int64_t>::home_hash32((int64_t)key) >> da.shift;                // the grouped layout hashes the sign-extended key
   return (radix_hash<K>(key) >> da.shift) & da.mask;                                                    // a bit field of the radix hash
 }
 
@@ -375,12 +376,13 @@ cudaError_t radix_partition2(const void* keys, const uint32_t* rows, uint32_t ro
 
 // ---- one pass on the TABLE hash: slice s of the output holds the tuples whose bucket pairs lie in the s-th 2^-bits of the inline table ----
 int64_t slice_partition_workspace_bytes(int64_t n, int bits) { return rp_workspace_bytes(n, 1, 1 << bits); }
-cudaError_t slice_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int bits,
+cudaError_t slice_partition(const void* keys, const uint32_t* rows, uint32_t row_base, int64_t n, int key_bytes, int bits, bool grouped,
                             void* out_keys, uint32_t* out_rows, uint32_t* offsets, void* ws, int64_t ws_bytes, cudaStream_t stream) {
   if (bits < 1 || bits > 8 || n < 0 || n > 0xFFFFFFFFLL || ws_bytes < slice_partition_workspace_bytes(n, bits)) return cudaErrorInvalidValue;
   const DigitArgs da{(uint32_t)1 << bits, (uint32_t)(32 - bits), (uint32_t)((1 << bits) - 1)};
-  if (key_bytes == 4) return rp_pass<int32_t, SEL_TABLE>(keys, rows, row_base, n, nullptr, 1, da, out_keys, out_rows, offsets, ws, stream);
-  return rp_pass<int64_t, SEL_TABLE>(keys, rows, row_base, n, nullptr, 1, da, out_keys, out_rows, offsets, ws, stream);
+  if (key_bytes == 4) return grouped ? rp_pass<int32_t, SEL_GROUP>(keys, rows, row_base, n, nullptr, 1, da, out_keys, out_rows, offsets, ws, stream)
+                                     : rp_pass<int32_t, SEL_TABLE>(keys, rows, row_base, n, nullptr, 1, da, out_keys, out_rows, offsets, ws, stream);
+  return rp_pass<int64_t, SEL_TABLE>(keys, rows, row_base, n, nullptr, 1, da, out_keys, out_rows, offsets, ws, stream);      // i64: both layouts hash alike
 }
 
 // ---- one pass on the owner hash: hjPartition / hjPartitionCount / hjPartitionPush -----------------------------

@@ -111,14 +111,16 @@ def test_semi_join_and_count_only(lib, cuda, oracle, policy):
         b = datagen.RelationSpec(1_800_000, 8, datagen.KIND_FK, 7, 0, 600_000, 0, datagen.ODD_MUL64)
         p = datagen.RelationSpec(3_000_001, 8, datagen.KIND_UNIFORM, 8, 0, 1_200_000, 0, datagen.ODD_MUL64)
         dR, dS = datagen.generate(b), datagen.generate(p)
-        table = join.allocateHashTable(b.n, None, dR.dtype, cuda)
-        join.buildTable(dR, table)
-        assert lib.hjTableLayout(table.storage.data_ptr(), None) == 3
-        got = join.semi_join(dS, table).cpu().numpy()
         oa, ob = oracle.join(dR.cpu().numpy(), dS.cpu().numpy(), threads=0)
-        assert np.array_equal(np.sort(got), np.unique(ob))
+        for sliced, want_layout in ((0, 3), (1, 0x202)):                  # radix layout, then the slice-ordered grouped table
+            lib.hjSetSliced(sliced)
+            table = join.allocateHashTable(b.n, None, dR.dtype, cuda)
+            join.buildTable(dR, table)
+            assert lib.hjTableLayout(table.storage.data_ptr(), None) == want_layout
+            got = join.semi_join(dS, table).cpu().numpy()
+            assert np.array_equal(np.sort(got), np.unique(ob))
     finally:
-        lib.hjSetAllowDense(2); lib.hjSetSparse(1)
+        lib.hjSetAllowDense(2); lib.hjSetSparse(1); lib.hjSetSliced(1)
 
 
 def test_two_column_keys(lib, cuda):

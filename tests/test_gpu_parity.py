@@ -430,9 +430,9 @@ def test_big_table_path(lib, cuda, oracle, layout, dups, kb, nR, nS):
     # the reference's call sequence: row ids only at write time (payload column), and none at all (row base)
     table = join.allocateHashTable(nR, None, dR.dtype, cuda)
     join.buildTable(dR, table, pr)
-    # unique keys: one hash table built in table-slice order; duplicates: radix layout when the sample sees them, else (sample off) the
-    # grouped layout, rebuilt in slice order after the inline attempt met a duplicate
-    assert lib.hjTableLayout(table.storage.data_ptr(), None) == (0x200 if not dups else (0x202 if layout == "hash" else 3))
+    # one table built in table-slice order: inline for unique keys, grouped for duplicates (found by the sample, or — sample off — by
+    # the inline attempt)
+    assert lib.hjTableLayout(table.storage.data_ptr(), None) == (0x202 if dups else 0x200)
     n = join.countRows(dS, table)
     a3 = torch.empty(n, dtype=torch.int32, device=cuda); b3 = torch.empty(n, dtype=torch.int32, device=cuda)
     join.probeRelation(dS, table, a3, b3, ps)
