@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restric
       h = (h + 1) & (DUPS_SLOTS - 1);
     }
   }
-  if (__syncthreads_or(dup) && threadIdx.x == 0) hdr->has_dups = 1;
+  // has_dups doubles as the NUMBER of sampled rows that met an equal key among their CTA's 4 096 samples (0 = none seen): with
+  // rows spread at random it estimates the multiplicity of the build keys, m ~ 1 + pairs * n / (DUPS_CTAS * C(4096, 2))
+  const int pairs = __syncthreads_count(dup);
+  if (pairs && threadIdx.x == 0) atomicAdd(&hdr->has_dups, (uint32_t)pairs);
 }
 
 // count_by_range (hjSetAllowDense(2), the default): a unique build whose keys are exactly [kmin, kmax] lets the count pass skip the
@@ -510,7 +513,12 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
     cudaError_t e = read_header(hdr, &h, stream);
     if (e != cudaSuccess) return e;
     if (h.mode != MODE_DENSE) {
-      if ((policy & POLICY_NO_SLICES) || !table_sliceable(nR, (int)sizeof(K))) return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
+      // Heavy duplication (sampled multiplicity >= 32: the reference's published shape 1 has 100 rows per key) is output-bound, and there
+      // the radix join's lockstep walk over long equal-key runs beats the grouped table's run expansion (10M x 10M -> 1e9 pairs: 4.2 vs
+      // 5.4 ms); a few rows per key (config 4: 4) go the other way (6.65 vs 5.63 ms).
+      const double multiplicity = 1.0 + (double)h.has_dups * (double)nR / ((double)DUPS_CTAS * 0.5 * DUPS_SAMPLES * (DUPS_SAMPLES - 1));
+      if ((policy & POLICY_NO_SLICES) || !table_sliceable(nR, (int)sizeof(K)) || (h.has_dups && multiplicity >= 32.0))
+        return radix_build(R, nR, (int)sizeof(K), payload, row_base, hdr, body, body_bytes, stream);
       // small enough to slice: reorder (key, row id) by table slice — of the grouped table when the sample already proved duplicates, else of
       // the inline table — then the ordinary build sequence runs over the copy (a duplicate the inline build meets still sends it to the
       // grouped layout, in the inline hash's slice order: correct, only less local for i32 keys)
