@@ -560,10 +560,13 @@ def main() -> None:
     roofline = head.get("roofline")
     traffic_file = ROOT / "profiles" / "traffic.json"
     if roofline is not None and traffic_file.exists():
-        t = json.loads(traffic_file.read_text())
-        entry = t.get(args.workload, {}).get(head["table_layout_chosen"])
-        if entry:                                             # per-launch DRAM bytes of the dominant kernel from one ncu --set full capture, keyed by workload + layout
-            roofline["traffic"] = entry.get("dram_bytes"); roofline["traffic_source"] = entry.get("source")
+        import hashlib
+        entry = json.loads(traffic_file.read_text()).get(args.workload, {}).get(head["table_layout_chosen"])
+        if entry:        # per-launch DRAM bytes of the dominant kernel from one ncu --set full capture (tools/make_traffic.py), valid for the source it was taken on
+            src = ROOT / entry["source_file"]
+            fresh = src.exists() and hashlib.sha256(src.read_bytes()).hexdigest() == entry["source_sha256"]
+            roofline["traffic"] = entry["dram_bytes"] if fresh else None
+            roofline["traffic_source"] = f'{entry["kernel"]}: {entry["source"]}' + ("" if fresh else " — STALE: the kernel source changed since the capture, figure withheld")
 
     line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong" if (args.workload == "c5" and args.c5_total_log2) or (args.workload == "c3" and world > 1) else "weak",
