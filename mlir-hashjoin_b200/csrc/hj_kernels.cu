@@ -617,8 +617,9 @@ __device__ __forceinline__ const char* home_bucket(const char* __restrict__ body
   return body + probe_bucket(pair, half, 0, n_pairs) * 32;
 }
 
-// One instantiation per table layout (MODE): the count launch queues all three and the two that do not match the header
-// exit at once. Keeping them separate keeps registers per thread (and so occupancy) at what each layout needs.
+// One instantiation per table layout (MODE); the host launches the one the table header names. Keeping them separate keeps registers
+// per thread (and so occupancy) at what each layout needs. (The inline i32 variant holds four 32-byte buckets per thread: 64 registers,
+// 4 CTAs per SM. Capped at 48 registers for a fifth CTA it spills 24 bytes and config 2 with sparse keys gets no faster: 2.69 -> 2.75 ms.)
 template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count(const K* __restrict__ S, int64_t nS, const char* __restrict__ body,
                                                          const TableHeader* __restrict__ hdr, uint32_t* __restrict__ mcache, uint32_t* __restrict__ run_start,
