@@ -114,6 +114,14 @@ __global__ void k_init_header(TableHeader* hdr, uint32_t key_bytes, unsigned lon
 template <typename K>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_minmax(const K* __restrict__ R, int64_t nR, TableHeader* hdr) {
   __shared__ long long smin[32], smax[32];
+  {
+    // k_sample_dups ran first and left the min / max of its 65 536 sampled keys in the header: bounds of a SUBSET, so a sampled range
+    // already too wide for the direct-address layout proves the full range is too (exact, no false negatives) and the scan of the whole
+    // column is skipped (2^28 i64 keys: 0.30 ms)
+    const long long slo = hdr->kmin, shi = hdr->kmax;
+    const unsigned long long srange = (unsigned long long)shi - (unsigned long long)slo + 1ULL;
+    if (slo <= shi && (srange == 0 || srange > (unsigned long long)DENSE_MAX_FACTOR * (unsigned long long)nR)) return;
+  }
   long long lo = 0x7FFFFFFFFFFFFFFFLL, hi = -0x7FFFFFFFFFFFFFFFLL - 1;
   for (int64_t i = blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x; i < nR; i += (int64_t)gridDim.x * BLOCK_THREADS) {
     const long long k = (long long)R[i];
@@ -189,6 +197,14 @@ __global__ void __launch_bounds__(DUPS_THREADS) k_sample_dups(const K* __restric
   // rows spread at random it estimates the multiplicity of the build keys, m ~ 1 + pairs * n / (DUPS_CTAS * C(4096, 2))
   const int pairs = __syncthreads_count(dup);
   if (pairs && threadIdx.x == 0) atomicAdd(&hdr->has_dups, (uint32_t)pairs);
+  long long lo = 0x7FFFFFFFFFFFFFFFLL, hi = -0x7FFFFFFFFFFFFFFFLL - 1;     // sampled key range: lets k_minmax skip its scan when it is already too wide
+  for (int i = threadIdx.x; i < DUPS_SAMPLES; i += DUPS_THREADS) { const long long k = keys_sm[i]; lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+  #pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, lo, d), b = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&hdr->kmin, lo); atomicMax(&hdr->kmax, hi); }
 }
 
 // count_by_range (hjSetAllowDense(2), the default): a unique build whose keys are exactly [kmin, kmax] lets the count pass skip the
@@ -424,18 +440,26 @@ constexpr int PERSIST_GRID = 148 * 8;
 // Slice-ordered kernels walk the relation grid-stride, so the CTAs in flight cover ONE contiguous window of it (and one slice of
 // the table). That only holds while every CTA of the grid is resident: a grid larger than one wave would sweep the table once per
 // wave. resident_grid() = occupancy x SM count for the given kernel, cached.
+// SM count and per-kernel occupancy are looked up once per (kernel, device) and cached; the caches are plain arrays indexed by device
+// ordinal, filled idempotently, so concurrent first calls from several host threads are harmless.
+constexpr int MAX_DEVICES = 64;
+static int current_device() { int dev = 0; cudaGetDevice(&dev); return dev < 0 || dev >= MAX_DEVICES ? 0 : dev; }
 static int num_sms() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-  return n;
+  static int cache[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (!cache[dev]) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); cache[dev] = n > 0 ? n : 148; }
+  return cache[dev];
 }
 template <typename Kern>
 static unsigned resident_grid(Kern kern, int64_t needed_blocks) {
-  int per_sm = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS, 0);
-  if (getenv("HJ_DEBUG")) fprintf(stderr, "[hj] resident_grid: err=%d per_sm=%d sms=%d needed=%lld\n", (int)oe, per_sm, num_sms(), (long long)needed_blocks);
-  if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
-  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(needed_blocks, (int64_t)per_sm * num_sms()));
+  static int cache[MAX_DEVICES] = {0};                     // one array per kernel instantiation (the template makes it so)
+  const int dev = current_device();
+  if (!cache[dev]) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cache[dev] = per_sm;
+  }
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(needed_blocks, (int64_t)cache[dev] * num_sms()));
 }
 
 // ---- policy: process defaults (hjSet*), frozen into the table header by every build (hjBuildEx can state them per table) ----
@@ -503,8 +527,8 @@ static cudaError_t launch_build(const K* R, int64_t nR, const uint32_t* payload,
   const int64_t threads = (nR + KPV - 1) / KPV;
   const unsigned grid = (unsigned)std::min<int64_t>(PERSIST_GRID, (threads + BLOCK_THREADS - 1) / BLOCK_THREADS);
   const unsigned clear_grid = (unsigned)std::min<int64_t>(148 * 16, (pairs * 4 + BLOCK_THREADS - 1) / BLOCK_THREADS);
-  if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   if (nR >= DUPS_MIN_ROWS && (policy & POLICY_DUP_SAMPLE)) k_sample_dups<K><<<DUPS_CTAS, DUPS_THREADS, 0, stream>>>(R, nR, hdr);
+  if (nR > 0) k_minmax<K><<<(unsigned)std::min<int64_t>(148 * 8, grid), BLOCK_THREADS, 0, stream>>>(R, nR, hdr);
   k_decide<<<1, 1, 0, stream>>>(hdr, (int)(policy & POLICY_DENSE_MASK));
   // A table beyond L2 reach that did not get the direct-address layout is not built at all: one host look at the header (the only
   // sync in the build, and only for big tables), then the relation is radix-partitioned and the partitioned copy is the table (K7).

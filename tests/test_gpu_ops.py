@@ -152,3 +152,54 @@ def test_join_host_bounded_window(lib, cuda, oracle):
     oa, ob = oracle.join(R, S, threads=0)
     assert n == oa.size and oracle.pair_digest(a.numpy(), b.numpy()) == oracle.pair_digest(oa, ob)
     assert np.array_equal(R[a.numpy()], S[b.numpy()])                          # every pair joins equal keys
+
+
+def test_per_table_policy_and_concurrent_threads(lib, cuda, oracle):
+    """The policy is a property of the TABLE (hjBuildEx freezes it into the device-resident header), not of the process: two tables built
+    under different policies coexist and each is probed by its own rules whatever hjSet* says later. And the library keeps no per-call
+    state on the host: two host threads drive their own (table, scratch, stream) concurrently and both get the oracle's result."""
+    import threading
+    import torch
+    from mlir_hashjoin_b200 import _lib
+    rng = np.random.default_rng(51)
+    R = rng.permutation(200_000).astype(np.int32)[:120_000]                 # unique keys in a dense range
+    S = rng.integers(0, 250_000, 900_001).astype(np.int32)
+    dR, dS = torch.from_numpy(R).to(cuda), torch.from_numpy(S).to(cuda)
+    oa, ob = oracle.join(R, S)
+    want = sorted_pairs(oa, ob)
+    tb, sb = lib.hjTableBytes(R.size, 4), lib.hjScratchBytes(S.size, 4)
+    POL_HASH = 0 | (1 << 2) | (1 << 3) | (1 << 5)                            # HJ_POLICY_DENSE_OFF | RADIX | LISTS_SAMPLED | DUP_SAMPLE
+    POL_DENSE = 2 | (1 << 2) | (2 << 3) | (1 << 5)                           # HJ_POLICY_DENSE_RANGE | RADIX | LISTS_ALWAYS | DUP_SAMPLE
+    tables = [torch.empty(tb, dtype=torch.uint8, device=cuda) for _ in range(2)]
+    assert lib.hjBuildEx(dR.data_ptr(), R.size, 4, None, 0, tables[0].data_ptr(), tb, POL_HASH, None) == 0
+    assert lib.hjBuildEx(dR.data_ptr(), R.size, 4, None, 0, tables[1].data_ptr(), tb, POL_DENSE, None) == 0
+    lib.hjSetAllowDense(1); lib.hjSetSparse(0)                               # process defaults changed AFTER the builds: must not matter
+    try:
+        assert lib.hjTableLayout(tables[0].data_ptr(), None) == 0 and lib.hjTableLayout(tables[1].data_ptr(), None) & 0xFF == 1
+        results, errors = [None, None], []
+
+        def worker(k):
+            try:
+                with torch.cuda.stream(torch.cuda.Stream(device=cuda)) as _:
+                    st = torch.cuda.current_stream().cuda_stream
+                    scratch = torch.empty(sb, dtype=torch.uint8, device=cuda)
+                    for _rep in range(20):                                   # many small calls: the readbacks of the two threads interleave
+                        n = lib.hjCount(dS.data_ptr(), S.size, 4, tables[k].data_ptr(), scratch.data_ptr(), sb, st)
+                        outR = torch.empty(n, dtype=torch.int32, device=cuda); outS = torch.empty(n, dtype=torch.int32, device=cuda)
+                        _lib.check_status(lib.hjWrite(dS.data_ptr(), S.size, 4, tables[k].data_ptr(), scratch.data_ptr(), outR.data_ptr(), outS.data_ptr(), None, 0, st), "hjWrite")
+                        torch.cuda.current_stream().synchronize()
+                        assert n == oa.size
+                    results[k] = (outR.cpu().numpy(), outS.cpu().numpy(), lib.hjProbePath(scratch.data_ptr(), S.size, 4, st))
+            except Exception as e:                                           # noqa: BLE001
+                errors.append(e)
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        for k in range(2):
+            assert np.array_equal(sorted_pairs(results[k][0], results[k][1]), want)
+        assert results[0][2] == 0 and results[1][2] == 1                     # table 0: sampled (48 % hit -> match cache); table 1: hit lists always
+    finally:
+        lib.hjSetAllowDense(2); lib.hjSetSparse(1)
