@@ -224,6 +224,7 @@ def main() -> None:
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no c2_sparse / hash / c3 / c4 / c5 / ref shapes)")
     ap.add_argument("--extras", default="", help="comma list restricting the extras (names: c2_sparse,hash_layout,match_cache,fused,c3,c4,c5,ref10m,ref100m)")
     ap.add_argument("--c5-total-log2", type=int, default=0, help="c5 only: fix the TOTAL rows per side at 2^k (strong scaling); default 2^28 rows per GPU (weak)")
+    ap.add_argument("--overlap-build", action="store_true", help="c5, N > 1, fused exchange: local build on a second stream while the probe side is pushed")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5, N > 1: peer-store partition kernel vs partition + NCCL all-to-all")
     ap.add_argument("--layout", default="auto", choices=["auto", "cache", "hash"],
                     help="auto = library default (direct-address table for dense key ranges, counted by range test when gap-free and unique); "
@@ -359,6 +360,7 @@ def main() -> None:
             return out["R"][:n], out["S"][:n]
         torch.cuda.synchronize()
         n_out = [0]
+        marks, leg_events = {}, []
 
         def step():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -366,7 +368,10 @@ def main() -> None:
                 ev[0].record(stream)
                 ev[1].record(stream); ev[2].record(stream)              # moved by the `exchanged` hook: partition + exchange | local join
                 if peer_x:
-                    a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x, exchanged=lambda: (ev[1].record(stream), ev[2].record(stream)), table=table)
+                    marks.clear()
+                    a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x, exchanged=lambda: (ev[1].record(stream), ev[2].record(stream)), table=table,
+                                                    marks=marks, overlap_build=args.overlap_build)
+                    leg_events.append(dict(marks))
                 else:
                     a, bb = hjdist.radix_join(dR, blo, dS, plo, table=table)
                 ev[3].record(stream)
@@ -460,6 +465,11 @@ def main() -> None:
                                 "local_join_hbm_frac": 64 * n_loc / (lj / 1e3) / 1e9 / peak,
                                 "note": "nvlink peak = measured peer copy per direction per GPU (B200_PROFILING.md); the exchange phase also holds the owner histograms of both relations, the all-gather of the count matrices and its one host read; local join bytes = 64 per row (SURVEY 8d, C5)"}
             res["gpu_launches_per_step"] = 2 * 4 + launches_per_step(3, False, n_loc, n_loc, kb, args.sparse, DENSE_POLICY[layout])
+            if leg_events:                                          # legs of the exchange phase on this rank, mean over the timed steps
+                legs = leg_events[-steps:]
+                names = ["start", "histograms", "count_matrix", "push_build", "push_probe"]
+                res["c5_phases"]["exchange_legs_ms"] = {b_: sum(l[a_].elapsed_time(l[b_]) for l in legs) / len(legs) for a_, b_ in zip(names, names[1:])}
+                res["c5_phases"]["overlap_build"] = bool(args.overlap_build)
         else:
             by_range = bool(layout_code & 0x100) and not hit_lists
             table_in_hbm = lib.hjTableBytes(b.n, kb) > 96 * 2**20

@@ -117,16 +117,26 @@ class PeerExchange:
 
 
 def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
-                   build_x: PeerExchange, probe_x: PeerExchange) -> tuple[int, int]:
+                   build_x: PeerExchange, probe_x: PeerExchange, marks: dict | None = None, build_landed: torch.cuda.Event | None = None) -> tuple[int, int]:
     """Both relations through the fused partition + exchange with ONE collective (the all-gather of both count rows) and ONE host
     readback (the count matrices, needed to size the local join). Returns the tuples this rank receives (build, probe); they are all
     there after the closing barrier. Raises HashJoinError — on every rank alike — when an owner would receive more than its buffer
-    holds (skew beyond the slack): nothing has been stored then, and radix_join() (NCCL all-to-all, exact sizes) is the fallback."""
+    holds (skew beyond the slack): nothing has been stored then, and radix_join() (NCCL all-to-all, exact sizes) is the fallback.
+    ``marks``: filled with CUDA events after each leg (bench.py times the legs). ``build_landed``: recorded once the build side has
+    landed on every rank, before the probe side is pushed (another stream can wait on it and start the local build)."""
     group = build_x.group
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            marks[name] = ev
     build_x.barrier()                                               # nobody is still reading last step's buffers
+    mark("start")
     cb, wsb = build_x.count(build_shard)
     cp, wsp = probe_x.count(probe_shard)
+    mark("histograms")
     matrix = torch.empty(world, 2 * world, dtype=torch.int64, device=build_shard.device)
     dist.all_gather_into_tensor(matrix.view(-1), torch.cat([cb, cp]), group=group)      # matrix[src] = [build counts per dst | probe counts per dst]
     host = matrix.cpu()                                             # the step's one host sync
@@ -134,20 +144,59 @@ def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: 
     if int(mb.sum(0).max()) > build_x.capacity or int(mp.sum(0).max()) > probe_x.capacity:
         raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
     cursors = torch.cat([mb[:rank].sum(0), mp[:rank].sum(0)]).to(build_shard.device, non_blocking=True)   # first element of my region in every owner's buffer
+    mark("count_matrix")
+    nb, npr = int(mb[:, rank].sum()), int(mp[:, rank].sum())
     build_x.push(build_shard, build_row_base, cursors[:world], wsb)
+    build_x.barrier()                                               # every rank's build tuples have landed
+    mark("push_build")
+    if build_landed is not None:
+        build_landed.record(torch.cuda.current_stream())
     probe_x.push(probe_shard, probe_row_base, cursors[world:], wsp)
-    build_x.barrier()                                               # every rank's stores have landed
-    return int(mb[:, rank].sum()), int(mp[:, rank].sum())
+    probe_x.barrier()                                               # every rank's probe tuples have landed
+    mark("push_probe")
+    return nb, npr
 
 
 def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
-                     build_x: PeerExchange, probe_x: PeerExchange, exchanged=None, table: join.HashTable | None = None):
+                     build_x: PeerExchange, probe_x: PeerExchange, exchanged=None, table: join.HashTable | None = None,
+                     marks: dict | None = None, overlap_build: bool = False):
     """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink).
-    ``exchanged`` (optional callable) runs once every rank's tuples have landed, before the local join (bench.py marks a phase there)."""
-    nb, npr = exchange_fused(build_shard, build_row_base, probe_shard, probe_row_base, build_x, probe_x)
+    ``exchanged`` (optional callable) runs once every rank's tuples have landed, before the probe passes of the local join (bench.py
+    marks a phase there). ``overlap_build``: the local build (hjBuild on the received build tuples) runs on a second stream while the
+    probe side is still crossing NVLink — the push is bound by the links, the build by HBM."""
+    if table is None:
+        table = join.allocateHashTable(build_x.capacity, None, build_shard.dtype, build_shard.device)
+    main = torch.cuda.current_stream()
+    landed = torch.cuda.Event() if overlap_build else None
+    nb, npr = exchange_fused(build_shard, build_row_base, probe_shard, probe_row_base, build_x, probe_x, marks, build_landed=landed)
+    if overlap_build:                                               # everything above is queued, nothing has been waited for: the probe push runs on `main` ...
+        side = _side_stream(build_shard.device)
+        with torch.cuda.stream(side):                               # ... while the build of the received build tuples runs here
+            side.wait_event(landed)
+            join.buildTable(build_x.keys[:nb], table, build_x.rows[:nb])
+        main.wait_stream(side)
     if exchanged is not None:
         exchanged()
-    return join.hash_join(build_x.keys[:nb], probe_x.keys[:npr], table=table, buildPayload=build_x.rows[:nb], probePayload=probe_x.rows[:npr])
+    if not overlap_build:
+        join.initializeHashTable(table)
+        join.buildTable(build_x.keys[:nb], table, build_x.rows[:nb])
+    pk, pr = probe_x.keys[:npr], probe_x.rows[:npr]
+    n = join.countRows(pk, table, pr, 0)
+    outR = torch.empty(n, dtype=torch.int32, device=pk.device)
+    outS = torch.empty(n, dtype=torch.int32, device=pk.device)
+    if n:
+        join.probeRelation(pk, table, outR, outS, pr, 0)
+    return outR, outS
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def radix_join(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int, group=None, table: join.HashTable | None = None):
