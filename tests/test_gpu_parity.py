@@ -491,3 +491,35 @@ def test_cpp_host_driver_main(lib, cuda):
         # init, build, count always print; probe only when the result is not empty (join_v1.mlir:600-601)
         assert len(re.findall(r"For \d+, time taken: \d+ microseconds", r.stdout)) == (4 if int(vals[0]) else 3)
     assert int(vals[0]) > 0
+
+
+def test_partition_push_single_gpu(lib, cuda, oracle):
+    """K5 fused with the exchange, on one GPU: hjPartitionCount + hjPartitionPush with every "peer" buffer in local memory (the kernel
+    cannot tell). Every tuple must land in its owner's buffer, inside the region the cursors gave this "rank", keys and row ids together."""
+    import torch
+    rng = np.random.default_rng(18)
+    for kd, kb, n, parts in ((np.int64, 8, 300_007, 2), (np.int32, 4, 1_000_003, 8), (np.int64, 8, 70_001, 5), (np.int64, 8, 3_000_017, 8)):
+        keys = rng.integers(-2**40, 2**40, n).astype(kd)
+        d = torch.from_numpy(keys).to(cuda)
+        counts = torch.empty(parts, dtype=torch.int64, device=cuda)
+        ws = torch.empty(lib.hjPartitionWorkspaceBytes(n, parts), dtype=torch.uint8, device=cuda)
+        assert lib.hjPartitionCount(d.data_ptr(), n, kb, parts, counts.data_ptr(), ws.data_ptr(), ws.numel(), None) == 0
+        cnt = counts.cpu().numpy()
+        assert cnt.sum() == n
+        lead = 1000                                                             # pretend lower ranks already own the first 1000 slots of every buffer
+        bufs_k = [torch.full((lead + int(c) + 64,), -7, dtype=d.dtype, device=cuda) for c in cnt]
+        bufs_r = [torch.full((lead + int(c) + 64,), -7, dtype=torch.int32, device=cuda) for c in cnt]
+        kp = torch.tensor([b.data_ptr() for b in bufs_k], dtype=torch.int64, device=cuda)
+        rp = torch.tensor([b.data_ptr() for b in bufs_r], dtype=torch.int64, device=cuda)
+        cursors = torch.full((parts,), lead, dtype=torch.int64, device=cuda)
+        assert lib.hjPartitionPush(d.data_ptr(), None, 5, n, kb, parts, kp.data_ptr(), rp.data_ptr(), cursors.data_ptr(), ws.data_ptr(), ws.numel(), None) == 0
+        torch.cuda.synchronize()
+        seen = np.zeros(n, dtype=bool)
+        for p in range(parts):
+            bk, br = bufs_k[p].cpu().numpy(), bufs_r[p].cpu().numpy()
+            assert (bk[:lead] == -7).all() and (bk[lead + cnt[p]:] == -7).all() and (br[:lead] == -7).all() and (br[lead + cnt[p]:] == -7).all()
+            rows = br[lead:lead + cnt[p]] - 5
+            assert np.array_equal(keys[rows], bk[lead:lead + cnt[p]])          # rows travelled with their keys
+            assert not seen[rows].any()
+            seen[rows] = True
+        assert seen.all()
