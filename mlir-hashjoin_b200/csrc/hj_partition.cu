@@ -169,6 +169,7 @@ struct RpSmem {
   uint32_t gcur[RP_MAX_FAN];                  // running destination cursor of each digit for this block
   K* kptr[PUSH ? RP_MAX_FAN : 1];             // per-digit destination buffers: only the push into peers' receive buffers has more than one
   uint32_t* rptr[PUSH ? RP_MAX_FAN : 1];
+  unsigned char sdig[PUSH ? TILE : 1];        // push only: the owner of every staged tuple (the local variants hash again in the output loop)
 };
 
 template <typename K, int SEL, bool PUSH, int THREADS, int ITEMS>
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 1024 / THREADS)
       if (FULL || pr[e] != 0xFFFFFFFFu) {
         const uint32_t d = pr[e] >> 16, pos = sm.lbase[d] + (pr[e] & 0xFFFFu);
         sm.skeys[pos] = key[e]; sm.srows[pos] = row[e];
+        if (PUSH) sm.sdig[pos] = (unsigned char)d;
       }
     }
     __syncthreads();
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 1024 / THREADS)
       const uint32_t i = it * RP_THREADS + threadIdx.x;
       if (FULL || i < count) {
         const K k = sm.skeys[i];
-        const uint32_t r = sm.srows[i], d = rp_digit<K, SEL>(k, da);      // hashed again rather than staged: the kernel is bound by the shared-memory pipe
+        const uint32_t r = sm.srows[i], d = PUSH ? (uint32_t)sm.sdig[i] : rp_digit<K, SEL>(k, da);   // local: hashed again rather than staged (the shared-memory pipe is the limiter)
         const uint32_t idx = sm.delta[d] + i;                            // (ncu: mio_throttle + short_scoreboard 15 warps per issue slot at 25 % issue), ALU is free
         if (PUSH) { sm.kptr[d][idx] = k; sm.rptr[d][idx] = r; }
         else { out_keys[idx] = k; out_rows[idx] = r; }
