@@ -467,7 +467,7 @@ def main() -> None:
             res["gpu_launches_per_step"] = 2 * 4 + launches_per_step(3, False, n_loc, n_loc, kb, args.sparse, DENSE_POLICY[layout])
             if leg_events:                                          # legs of the exchange phase on this rank, mean over the timed steps
                 legs = leg_events[-steps:]
-                names = ["start", "histograms", "count_matrix", "push_build", "push_probe"]
+                names = ["start", "histograms", "count_matrix", "push_build", "push_probe", "local_build", "local_count", "local_write"]
                 res["c5_phases"]["exchange_legs_ms"] = {b_: sum(l[a_].elapsed_time(l[b_]) for l in legs) / len(legs) for a_, b_ in zip(names, names[1:])}
                 res["c5_phases"]["overlap_build"] = bool(args.overlap_build)
         else:

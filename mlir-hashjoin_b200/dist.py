@@ -177,15 +177,23 @@ def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard
         main.wait_stream(side)
     if exchanged is not None:
         exchanged()
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(main)
+            marks[name] = ev
     if not overlap_build:
         join.initializeHashTable(table)
         join.buildTable(build_x.keys[:nb], table, build_x.rows[:nb])
+    mark("local_build")
     pk, pr = probe_x.keys[:npr], probe_x.rows[:npr]
     n = join.countRows(pk, table, pr, 0)
+    mark("local_count")
     outR = torch.empty(n, dtype=torch.int32, device=pk.device)
     outS = torch.empty(n, dtype=torch.int32, device=pk.device)
     if n:
         join.probeRelation(pk, table, outR, outS, pr, 0)
+    mark("local_write")
     return outR, outS
 
 

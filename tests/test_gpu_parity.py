@@ -350,8 +350,7 @@ def test_radix_partition(lib, cuda, oracle):
     """K5: every key lands in exactly one partition, equal keys in the same one, (key,row) pairs preserved."""
     import torch
     rng = np.random.default_rng(8)
-    for kd, kb in ((np.int32, 4), (np.int64, 8)):
-        n, parts = 100003, 8
+    for kd, kb, n, parts in ((np.int32, 4, 100003, 8), (np.int64, 8, 100003, 8), (np.int64, 8, 300_007, 2), (np.int32, 4, 70_001, 5), (np.int64, 8, 3_000_017, 3)):
         keys = rng.integers(0, 5000, n).astype(kd)
         d = torch.from_numpy(keys).to(cuda)
         ok = torch.empty_like(d); orow = torch.empty(n, dtype=torch.int32, device=cuda)
