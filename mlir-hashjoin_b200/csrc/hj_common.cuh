@@ -314,6 +314,27 @@ __device__ __forceinline__ long long ticket_advance(TicketQueue* q, uint32_t it,
   return q->slot[(it + 1) & 1];
 }
 
+// Two tickets ahead: the CTA knows its NEXT work unit while it works on the current one, so every thread can pull that unit's input into L2
+// (the units are a few tens of KB: without this each one starts with a DRAM round trip nobody overlaps).
+//   TicketQueue2 q (shared); ticket2_first(ctr, &q, cur, next); for (it = 0; cur < n; it++) { p = ticket_prefetch(ctr); ...; ticket2_advance(&q, it, p, cur, next); }
+struct TicketQueue2 { long long slot[4]; };
+__device__ __forceinline__ void ticket2_first(unsigned long long* counter, TicketQueue2* q, long long& cur, long long& next) {
+  if (threadIdx.x == 0) { q->slot[0] = (long long)atomicAdd(counter, 1ULL); q->slot[1] = (long long)atomicAdd(counter, 1ULL); }
+  __syncthreads();
+  cur = q->slot[0]; next = q->slot[1];
+}
+__device__ __forceinline__ void ticket2_advance(TicketQueue2* q, uint32_t it, long long pending, long long& cur, long long& next) {
+  if (threadIdx.x == 0) q->slot[(it + 2) & 3] = pending;
+  __syncthreads();                 // slot (it + 2) & 3 was last read two iterations (two barriers) ago
+  cur = next; next = q->slot[(it + 2) & 3];
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// every 32-byte sector of [p, p + bytes), spread over the CTA's threads
+__device__ __forceinline__ void prefetch_l2_range(const void* p, uint32_t bytes, int threads) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (uint32_t o = threadIdx.x * 32u; o < bytes; o += (uint32_t)threads * 32u) prefetch_l2(c + o);
+}
+
 template <typename T>
 __device__ __forceinline__ T block_reduce_sum(T v, T* smem) {            // result valid in every thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;

@@ -806,7 +806,6 @@ __device__ __forceinline__ uint32_t append_hits(const uint32_t (&m)[N], const ui
 
 constexpr int SPARSE_WARPS = BLOCK_THREADS / 32;
 constexpr int PREFETCH_TILES = 2;
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 template <typename K, bool VEC, uint32_t MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count_sparse(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,

@@ -143,15 +143,16 @@ __device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restric
   for (int i = threadIdx.x; i < RJ_DIR_WORDS; i += RJ_THREADS) sm.dir[i] = 0;
   __syncthreads();
   uint32_t br[RJ_R_ITEMS];                                           // bucket << 16 | rank inside the bucket
+  // All loads first, then the atomics: with load -> hash -> atomic per tuple the compiler keeps the loads behind the atomics and every one
+  // of them exposes its own latency (ncu, 2^28 x 2^28 i64: long-scoreboard stalls at each of the unrolled hashes, 24 % of the kernel).
   #pragma unroll
   for (int u = 0; u < RJ_R_ITEMS; u++) {
     const uint32_t i = u * RJ_THREADS + threadIdx.x;
-    br[u] = 0;
-    if (i < nr) {
-      const uint32_t b = bucket_hash<K>(Rk[r0 + i]) >> RJ_BUCKET_SHIFT;            // default cache policy: the second look below must hit L2
-      br[u] = (b << 16) | atomicAdd(&sm.dir[spad(b)], 1u);                         // the count sits in the low half: the returned value is the rank
-    }
+    br[u] = i < nr ? bucket_hash<K>(Rk[r0 + i]) >> RJ_BUCKET_SHIFT : 0xFFFFFFFFu;   // default cache policy: the second look below must hit L2
   }
+  #pragma unroll
+  for (int u = 0; u < RJ_R_ITEMS; u++)
+    if (br[u] != 0xFFFFFFFFu) br[u] = (br[u] << 16) | atomicAdd(&sm.dir[spad(br[u])], 1u);   // the count sits in the low half: the returned value is the rank
   __syncthreads();
   {                                                                   // counts -> first << 16 | count: thread t owns buckets [t * PER, (t + 1) * PER)
     uint32_t v[PER], sum = 0;
@@ -166,7 +167,7 @@ __device__ __forceinline__ void rj_build_round(RjSmem<K>& sm, const K* __restric
   #pragma unroll
   for (int u = 0; u < RJ_R_ITEMS; u++) {
     const uint32_t i = u * RJ_THREADS + threadIdx.x;
-    if (i < nr) {                                                     // second look at the tuple: an L1 / L2 hit (the partition was read a moment ago)
+    if (br[u] != 0xFFFFFFFFu) {                                       // second look at the tuple: an L1 / L2 hit (the partition was read a moment ago)
       const uint32_t pos = (sm.dir[spad(br[u] >> 16)] >> 16) + (br[u] & 0xFFFFu);
       sm.ckey[pos] = ld_stream<K>(Rk + r0 + i, pol);
       sm.crow[pos] = with_rows ? ld_stream<uint32_t>(Rr + r0 + i, pol) : i;   // counting keeps the tuple's position instead: it goes into the match cache
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
                                                            unsigned long long* __restrict__ n_multi) {
   extern __shared__ __align__(16) unsigned char rj_raw[];
   RjSmem<K>& sm = *reinterpret_cast<RjSmem<K>*>(rj_raw);
-  __shared__ TicketQueue tq;
+  __shared__ TicketQueue2 tq;
   __shared__ unsigned long long acc_cnt[2];                        // the item's match count and multi flag, double-buffered over the items
   __shared__ uint32_t acc_multi[2];
   __shared__ uint32_t scan_sm[33];
@@ -197,11 +198,17 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
   const unsigned lt = (1u << lane) - 1u;
   const uint64_t pol = policy_evict_first();
   if (WRITE && *n_multi == 0) return;                             // every item was described by the match cache: k_rj_emit writes them all
-  long long item = ticket_first(tickets, &tq);
+  long long item, next;
+  ticket2_first(tickets, &tq, item, next);
   for (uint32_t it = 0; item < n_items; it++) {
     const long long pending = ticket_prefetch(tickets);
-    if (WRITE && !item_multi[item]) { item = ticket_advance(&tq, it, pending); continue; }      // uniform: k_rj_emit has this item
+    if (WRITE && !item_multi[item]) { ticket2_advance(&tq, it, pending, item, next); continue; }      // uniform: k_rj_emit has this item
     const RjItem w = items[item];
+    // (count pass only: the write join exists for items with several matches per probe tuple, which are bound by their output — there the
+    // extra live registers cost more than the pulls save: 10M x 10M -> 1e9 pairs 2.52 -> 2.73 ms)
+    const bool pull_next = !WRITE && next < n_items;
+    RjItem wn = w;
+    if (pull_next) wn = items[next];                                // in flight during the build below
     unsigned long long cnt = 0;
     unsigned long long obase = 0;
     const bool one_round = w.r1 - w.r0 <= (uint32_t)RJ_CAP;
@@ -210,6 +217,11 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
     for (uint32_t r0 = w.r0; r0 < w.r1; r0 += RJ_CAP) {
       const uint32_t nr = w.r1 - r0 < (uint32_t)RJ_CAP ? w.r1 - r0 : (uint32_t)RJ_CAP;
       rj_build_round<K>(sm, Rk, Rr, r0, nr, WRITE, pol, scan_sm);
+      if (pull_next && r0 == w.r0) {                                // the next item's tuples into L2 while this one is probed
+        const uint32_t nrn = wn.r1 - wn.r0 < (uint32_t)RJ_CAP ? wn.r1 - wn.r0 : (uint32_t)RJ_CAP;
+        if (wn.r0 != w.r0) prefetch_l2_range(Rk + wn.r0, nrn * (uint32_t)sizeof(K), RJ_THREADS);
+        prefetch_l2_range(Sk + wn.s0, (wn.s1 - wn.s0) * (uint32_t)sizeof(K), RJ_THREADS);
+      }
       constexpr int U = 4;
       if (!WRITE) {
         uint32_t c = 0;
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(RJ_THREADS, 3) k_rj_join(const K* __restrict__
       const unsigned wm = __ballot_sync(0xffffffffu, multi);
       if (lane == 0) { atomicAdd(&acc_cnt[it & 1], cnt); if (wm) acc_multi[it & 1] = 1; }
     }
-    item = ticket_advance(&tq, it, pending);
+    ticket2_advance(&tq, it, pending, item, next);
     if (!WRITE && threadIdx.x == 0) {
       item_totals[done] = acc_cnt[it & 1];
       if (acc_multi[it & 1]) { item_multi[done] = 1; atomicAdd(n_multi, 1ULL); }
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(RJ_THREADS) k_rj_emit(const uint32_t* __restri
                                                         const unsigned long long* __restrict__ n_items_ptr, unsigned long long* tickets,
                                                         const unsigned long long* __restrict__ item_offsets, int32_t* __restrict__ outR, int32_t* __restrict__ outS,
                                                         const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base, int carried_rows) {
-  __shared__ TicketQueue tq;
+  __shared__ TicketQueue2 tq;
   __shared__ uint32_t cursor[2];
   const long long n_items = (long long)*n_items_ptr;
   const int lane = threadIdx.x & 31;
@@ -320,9 +332,15 @@ __global__ void __launch_bounds__(RJ_THREADS) k_rj_emit(const uint32_t* __restri
   const uint64_t pol = policy_evict_first();
   constexpr int U = 4;
   if (threadIdx.x < 2) cursor[threadIdx.x] = 0;
-  long long item = ticket_first(tickets, &tq);
+  long long item, next;
+  ticket2_first(tickets, &tq, item, next);
   for (uint32_t it = 0; item < n_items; it++) {
     const long long pending = ticket_prefetch(tickets);
+    if (next < n_items && !item_multi[next]) {                      // the next item's cache words and row ids into L2 while this one streams
+      const RjItem wn = items[next];
+      prefetch_l2_range(mcache + wn.s0, (wn.s1 - wn.s0) * 4u, RJ_THREADS);
+      prefetch_l2_range(Sr + wn.s0, (wn.s1 - wn.s0) * 4u, RJ_THREADS);
+    }
     if (!item_multi[item]) {                                        // uniform
       const RjItem w = items[item];
       const unsigned long long obase = item_offsets[item];
@@ -356,8 +374,8 @@ __global__ void __launch_bounds__(RJ_THREADS) k_rj_emit(const uint32_t* __restri
         }
       }
     }
-    if (threadIdx.x == 0) cursor[(it + 1) & 1] = 0;                  // nobody touches it during this item; ticket_advance's barrier publishes the reset
-    item = ticket_advance(&tq, it, pending);
+    if (threadIdx.x == 0) cursor[(it + 1) & 1] = 0;                  // nobody touches it during this item; ticket2_advance's barrier publishes the reset
+    ticket2_advance(&tq, it, pending, item, next);
   }
 }
 
