@@ -230,7 +230,7 @@ def main() -> None:
                     help="auto = library default (direct-address table for dense key ranges, counted by range test when gap-free and unique); "
                          "cache = direct-address table with the match cache only; hash = never the direct-address layout")
     ap.add_argument("--sparse", type=int, default=1, choices=[0, 1, 2], help="hit lists for selective joins (0 never, 1 sampled on the device, 2 always)")
-    ap.add_argument("--partition-threads", type=int, default=0, choices=[0, 1, 256, 512, 1024], help="experiment: CTA shape of the partition scatter kernel (1 = warp-specialised)")
+    ap.add_argument("--partition-threads", type=int, default=0, choices=[0, 256, 512, 1024], help="experiment: CTA shape of the partition scatter kernel")
     ap.add_argument("--no-sliced", action="store_true", help="tables of 48 MB .. 1 GB of buckets: radix layout instead of one slice-ordered hash table")
     ap.add_argument("--no-radix", action="store_true", help="tables beyond L2 reach: one hash table in global memory instead of the radix join")
     args = ap.parse_args()

@@ -271,144 +271,11 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 1024 / THREADS)
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// scatter, warp-specialised: the same tile algorithm split over two halves of a 1 024-thread CTA. Warps 0-15 (producers) load a tile of
-// 8 192 tuples (16 per thread), rank it and stage it digit-sorted into one of TWO shared-memory buffers; warps 16-31 (consumers) write the
-// other buffer's runs to their destinations. In k_rp_scatter those phases follow each other behind CTA-wide barriers and, at one CTA per
-// SM, nothing fills the gaps (ncu, 2^28 i64 tuples: 19 % of the warp samples wait at a barrier, the stores of the output loop and the
-// shared-memory atomics of the rank step never overlap). Hand-over by named barriers (bar.arrive / bar.sync with 1 024 participants:
-// FULL[buf] producers -> consumers, EMPTY[buf] back); the producers' own two barriers count 512. setmaxnreg moves registers from the
-// consumers (32) to the producers (96: 16 tuples of key, row id and rank live at once).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int WS_THREADS = 1024, WS_PROD = 512, WS_CONS = 512, WS_ITEMS = 16, WS_TILE = WS_PROD * WS_ITEMS;
-constexpr int WS_BAR_PROD = 1, WS_BAR_FULL = 2, WS_BAR_EMPTY = 4;
-template <typename K, bool PUSH>
-struct WsSmem {
-  K skeys[2][WS_TILE];
-  uint32_t srows[2][WS_TILE];
-  uint32_t delta[2][RP_MAX_FAN];              // per buffer: destination index of staged position i of digit d = delta[d] + i
-  uint32_t cnt[RP_MAX_FAN], lbase[RP_MAX_FAN], gcur[RP_MAX_FAN], dnext[RP_MAX_FAN];   // producers only
-  K* kptr[PUSH ? RP_MAX_FAN : 1];
-  uint32_t* rptr[PUSH ? RP_MAX_FAN : 1];
-  unsigned char sdig[2][PUSH ? WS_TILE : 1];
-};
-__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-
-template <typename K, int SEL, bool PUSH>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_rp_scatter_ws(const K* __restrict__ keys, const uint32_t* __restrict__ rows, uint32_t row_base,
-                                                                 const RpBlock* __restrict__ blocks, const uint32_t* __restrict__ n_blocks, DigitArgs da,
-                                                                 K* __restrict__ out_keys, uint32_t* __restrict__ out_rows,
-                                                                 K* const* __restrict__ dst_keys, uint32_t* const* __restrict__ dst_rows,
-                                                                 const uint32_t* __restrict__ mat) {
-  extern __shared__ __align__(16) unsigned char rp_raw[];
-  WsSmem<K, PUSH>& sm = *reinterpret_cast<WsSmem<K, PUSH>*>(rp_raw);
-  const uint32_t b = blockIdx.x;
-  if (b >= *n_blocks) return;
-  const RpBlock blk = blocks[b];
-  const uint32_t fan = da.fan;
-  for (uint32_t d = threadIdx.x; d < RP_MAX_FAN; d += WS_THREADS) {
-    sm.cnt[d] = 0;
-    sm.gcur[d] = d < fan ? mat[(size_t)b * fan + d] : 0u;
-    if (PUSH && d < fan) { sm.kptr[d] = dst_keys[d]; sm.rptr[d] = dst_rows[d]; }
-  }
-  __syncthreads();
-  const uint32_t n_tiles = (blk.end - blk.begin + WS_TILE - 1) / WS_TILE;
-  if (threadIdx.x < WS_PROD) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-    const uint64_t pol = policy_evict_first();
-    K key[WS_ITEMS]; uint32_t row[WS_ITEMS];
-    auto load_tile = [&](uint32_t base, auto full_tag) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      #pragma unroll
-      for (int e = 0; e < WS_ITEMS; e++) {
-        const uint32_t i = base + e * WS_PROD + threadIdx.x;
-        key[e] = (FULL || i < blk.end) ? ld_stream<K>(keys + i, pol) : K(0);
-        row[e] = rows ? ((FULL || i < blk.end) ? ld_stream<uint32_t>(rows + i, pol) : 0u) : row_base + i;
-      }
-      constexpr int KEYS_PER_SECTOR = 32 / sizeof(K), KEY_SECTORS = WS_TILE / KEYS_PER_SECTOR;   // the tile after: one L2 prefetch per sector
-      #pragma unroll
-      for (int q = 0; q < KEY_SECTORS / WS_PROD; q++) {
-        const uint32_t ahead = base + WS_TILE + (q * WS_PROD + threadIdx.x) * KEYS_PER_SECTOR;
-        if (ahead < blk.end) prefetch_l2(keys + ahead);
-      }
-      if (rows) {
-        #pragma unroll
-        for (int q = 0; q < WS_TILE / 8 / WS_PROD; q++) {
-          const uint32_t ahead = base + WS_TILE + (q * WS_PROD + threadIdx.x) * 8;
-          if (ahead < blk.end) prefetch_l2(rows + ahead);
-        }
-      }
-    };
-    auto load_any = [&](uint32_t base) {
-      if (base + WS_TILE <= blk.end) load_tile(base, std::true_type{}); else load_tile(base, std::false_type{});
-    };
-    auto tile_body = [&](uint32_t t, uint32_t base, uint32_t count, auto full_tag) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      const uint32_t buf = t & 1u;
-      uint32_t pr[WS_ITEMS / 2];                               // rank inside the digit, two per register (the digit is hashed again when staging)
-      #pragma unroll
-      for (int e = 0; e < WS_ITEMS; e++) {
-        uint32_t rank = 0;
-        if (FULL || e * WS_PROD + threadIdx.x < count) rank = atomicAdd(&sm.cnt[rp_digit<K, SEL>(key[e], da)], 1u);
-        pr[e >> 1] = (e & 1) ? (pr[e >> 1] | (rank << 16)) : rank;
-      }
-      named_sync(WS_BAR_PROD, WS_PROD);
-      if (threadIdx.x < 32) {
-        uint32_t v[RP_MAX_FAN / 32], sum = 0;
-        #pragma unroll
-        for (int q = 0; q < RP_MAX_FAN / 32; q++) { v[q] = sm.cnt[threadIdx.x * (RP_MAX_FAN / 32) + q]; sum += v[q]; }
-        uint32_t run = warp_inclusive_scan(sum) - sum;
-        #pragma unroll
-        for (int q = 0; q < RP_MAX_FAN / 32; q++) {
-          const int d = threadIdx.x * (RP_MAX_FAN / 32) + q;
-          sm.lbase[d] = run; const uint32_t g = sm.gcur[d]; sm.dnext[d] = g - run; sm.gcur[d] = g + v[q]; sm.cnt[d] = 0;
-          run += v[q];
-        }
-      }
-      named_sync(WS_BAR_PROD, WS_PROD);
-      if (t >= 2) named_sync(WS_BAR_EMPTY + buf, WS_THREADS);   // the consumers are done with this buffer (tile t - 2)
-      if (threadIdx.x < RP_MAX_FAN) sm.delta[buf][threadIdx.x] = sm.dnext[threadIdx.x];
-      #pragma unroll
-      for (int e = 0; e < WS_ITEMS; e++) {
-        if (FULL || e * WS_PROD + threadIdx.x < count) {
-          const uint32_t d = rp_digit<K, SEL>(key[e], da), pos = sm.lbase[d] + ((pr[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-          sm.skeys[buf][pos] = key[e]; sm.srows[buf][pos] = row[e];
-          if (PUSH) sm.sdig[buf][pos] = (unsigned char)d;
-        }
-      }
-      named_arrive(WS_BAR_FULL + buf, WS_THREADS);
-    };
-    load_any(blk.begin);
-    for (uint32_t t = 0; t < n_tiles; t++) {
-      const uint32_t base = blk.begin + t * WS_TILE;
-      if (blk.end - base >= (uint32_t)WS_TILE) tile_body(t, base, (uint32_t)WS_TILE, std::true_type{});
-      else tile_body(t, base, blk.end - base, std::false_type{});
-      if (t + 1 < n_tiles) load_any(base + WS_TILE);
-    }
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    const uint32_t ctid = threadIdx.x - WS_PROD;
-    for (uint32_t t = 0; t < n_tiles; t++) {
-      const uint32_t base = blk.begin + t * WS_TILE, buf = t & 1u;
-      const uint32_t count = blk.end - base >= (uint32_t)WS_TILE ? (uint32_t)WS_TILE : blk.end - base;
-      named_sync(WS_BAR_FULL + buf, WS_THREADS);
-      #pragma unroll 4
-      for (int it = 0; it < WS_TILE / WS_CONS; it++) {         // digit-sorted: consecutive i -> consecutive destination addresses
-        const uint32_t i = it * WS_CONS + ctid;
-        if (i < count) {
-          const K k = sm.skeys[buf][i];
-          const uint32_t r = sm.srows[buf][i], d = PUSH ? (uint32_t)sm.sdig[buf][i] : rp_digit<K, SEL>(k, da);
-          const uint32_t idx = sm.delta[buf][d] + i;
-          if (PUSH) { sm.kptr[d][idx] = k; sm.rptr[d][idx] = r; }
-          else { out_keys[idx] = k; out_rows[idx] = r; }
-        }
-      }
-      if (t + 2 < n_tiles) named_arrive(WS_BAR_EMPTY + buf, WS_THREADS);
-    }
-  }
-}
-
+// (Measured and removed — git history has the kernel: a warp-specialised variant, 512 producer threads that load / rank / stage 8 192-tuple
+// tiles into two shared-memory buffers and 512 consumer threads that write the other buffer's runs, named-barrier hand-over, setmaxnreg
+// 96 / 32. Overlapping the phases buys nothing because the shared-memory pipe is busy in ALL of them — rank atomics, conflicting stage
+// stores, output loads (tools/membench5.cu: rank + stage alone are 5 400 of a tile's 14 600 cycles): 2^28 x 2^28 i64 join 11.8 -> 12.8 ms,
+// configs 2-sparse and 4 unchanged. Ballot / match_any ranking instead of the returning atomic: 2.6x / 4x slower, same microbenchmark.)
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
@@ -455,21 +322,9 @@ static cudaError_t rp_launch_scatter_t(const void* keys, const uint32_t* rows, u
 static int g_rp_threads = 0;
 void set_partition_threads(int t) { g_rp_threads = t; }
 template <typename K, int SEL, bool PUSH>
-static cudaError_t rp_launch_scatter_ws(const void* keys, const uint32_t* rows, uint32_t row_base, const RpWorkspace& w, DigitArgs da, void* out_keys, uint32_t* out_rows,
-                                        void* const* dst_keys, uint32_t* const* dst_rows, cudaStream_t stream) {
-  auto kern = k_rp_scatter_ws<K, SEL, PUSH>;
-  using Smem = WsSmem<K, PUSH>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-  if (e != cudaSuccess) return e;
-  kern<<<(unsigned)w.max_blocks, WS_THREADS, sizeof(Smem), stream>>>((const K*)keys, rows, row_base, w.blocks, w.n_blocks, da, (K*)out_keys, out_rows,
-                                                                   (K* const*)dst_keys, dst_rows, w.mat);
-  return cudaGetLastError();
-}
-template <typename K, int SEL, bool PUSH>
 static cudaError_t rp_launch_scatter(const void* keys, const uint32_t* rows, uint32_t row_base, const RpWorkspace& w, DigitArgs da, void* out_keys, uint32_t* out_rows,
                                      void* const* dst_keys, uint32_t* const* dst_rows, cudaStream_t stream) {
   const int threads = g_rp_threads ? g_rp_threads : (da.fan > 128 ? 1024 : 512);
-  if (threads == 1) return rp_launch_scatter_ws<K, SEL, PUSH>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
   if (threads == 1024) return rp_launch_scatter_t<K, SEL, PUSH, 1024>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
   if (threads == 256) return rp_launch_scatter_t<K, SEL, PUSH, 256>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);
   return rp_launch_scatter_t<K, SEL, PUSH, 512>(keys, rows, row_base, w, da, out_keys, out_rows, dst_keys, dst_rows, stream);

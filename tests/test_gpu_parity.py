@@ -348,13 +348,13 @@ def test_pair_digest_matches_oracle(lib, cuda, oracle):
 
 @pytest.fixture
 def scatter_shape(lib, request):
-    """CTA shape of the partition scatter kernel: 0 = chosen by fan, 512 / 1024 threads, 1 = warp-specialised (producer / consumer halves)."""
+    """CTA shape of the partition scatter kernel: 0 = chosen by fan, else 256 / 512 / 1024 threads."""
     lib.hjSetPartitionThreads(request.param)
     yield request.param
     lib.hjSetPartitionThreads(0)
 
 
-@pytest.mark.parametrize("scatter_shape", [0, 512, 1024, 1], indirect=True)
+@pytest.mark.parametrize("scatter_shape", [0, 256, 512, 1024], indirect=True)
 def test_radix_partition(lib, cuda, oracle, scatter_shape):
     """K5: every key lands in exactly one partition, equal keys in the same one, (key,row) pairs preserved."""
     import torch
