@@ -9,3 +9,9 @@ tail -4 gpurun_out/${tag}_dist_pytest.log
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 "$@" \
   > gpurun_out/${tag}_bench_${n}gpu.json 2> gpurun_out/${tag}_bench_${n}gpu.err
 echo "bench exit $?"; tail -3 gpurun_out/${tag}_bench_${n}gpu.err; head -c 600 gpurun_out/${tag}_bench_${n}gpu.json
+# what the host side gives all ranks at once (ceiling of the e2e leg), with and without the NUMA binding
+for b in "" "--no-bind"; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 tools/pcie_probe.py $b \
+    >> gpurun_out/${tag}_pcie_${n}gpu.jsonl 2>> gpurun_out/${tag}_pcie_${n}gpu.err
+done
+tail -2 gpurun_out/${tag}_pcie_${n}gpu.jsonl | cut -c1-400
