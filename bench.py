@@ -225,7 +225,7 @@ def main() -> None:
     ap.add_argument("--extras", default="", help="comma list restricting the extras (names: c2_sparse,hash_layout,match_cache,fused,c3,c4,c5,ref10m,ref100m)")
     ap.add_argument("--c5-total-log2", type=int, default=0, help="c5 only: fix the TOTAL rows per side at 2^k (strong scaling); default 2^28 rows per GPU (weak)")
     ap.add_argument("--overlap-build", action="store_true", help="c5, N > 1, fused exchange: local build on a second stream while the probe side is pushed")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="c5, N > 1: peer-store partition kernel vs partition + NCCL all-to-all")
+    ap.add_argument("--exchange", default="staged", choices=["fused", "staged", "nccl"], help="c5, N > 1: parts staged locally and carried by the copy engines (default), peer-store partition kernel, or partition + NCCL all-to-all")
     ap.add_argument("--layout", default="auto", choices=["auto", "cache", "hash"],
                     help="auto = library default (direct-address table for dense key ranges, counted by range test when gap-free and unique); "
                          "cache = direct-address table with the match cache only; hash = never the direct-address layout")
@@ -334,7 +334,7 @@ def main() -> None:
             dR = datagen.generate(b, dev, blo, bhi - blo)
             dS = datagen.generate(p, dev, plo, phi - plo)
             nR_job, nS_job, nS_rank = b.n, p.n, phi - plo
-            peer_x = (hjdist.PeerExchange(int(1.25 * b.n / world) + 65536, b.dtype, dev), hjdist.PeerExchange(int(1.25 * p.n / world) + 65536, p.dtype, dev)) if args.exchange == "fused" else None
+            peer_x = (hjdist.PeerExchange(int(1.25 * b.n / world) + 65536, b.dtype, dev), hjdist.PeerExchange(int(1.25 * p.n / world) + 65536, p.dtype, dev)) if args.exchange in ("fused", "staged") else None
             table = join.allocateHashTable(int(1.25 * b.n / world) + 65536, None, b.dtype, dev)
         else:
             if strong:                                          # the config's probe relation split over the ranks (config 3: "1M x 1B at 1/2/4/8 GPUs")
@@ -369,8 +369,12 @@ def main() -> None:
                 ev[1].record(stream); ev[2].record(stream)              # moved by the `exchanged` hook: partition + exchange | local join
                 if peer_x:
                     marks.clear()
-                    a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x, exchanged=lambda: (ev[1].record(stream), ev[2].record(stream)), table=table,
-                                                    marks=marks, overlap_build=args.overlap_build)
+                    hook = lambda: (ev[1].record(stream), ev[2].record(stream))      # noqa: E731
+                    if args.exchange == "staged":
+                        a, bb = hjdist.radix_join_staged(dR, blo, dS, plo, *peer_x, exchanged=hook, table=table, marks=marks, result=result_columns)
+                    else:
+                        a, bb = hjdist.radix_join_fused(dR, blo, dS, plo, *peer_x, exchanged=hook, table=table, marks=marks, overlap_build=args.overlap_build,
+                                                        result=result_columns)
                     leg_events.append(dict(marks))
                 else:
                     a, bb = hjdist.radix_join(dR, blo, dS, plo, table=table)
@@ -450,7 +454,8 @@ def main() -> None:
                 del sR
             del local
         res = {"workload": workload_name(cfg, world, {"single": "single GPU", "broadcast": "broadcast build, probe sharded" + (" (strong)" if strong else " (weak)"),
-                                                     "radix": "radix partition, " + ("exchange fused into the partition kernel (NVLink peer stores)" if args.exchange == "fused" else "NCCL all-to-all")}[plan]),
+                                                     "radix": "radix partition, " + {"fused": "exchange fused into the partition kernel (NVLink peer stores)", "nccl": "NCCL all-to-all",
+                                                                                    "staged": "parts staged locally and carried by the copy engines beside the partition / build kernels"}[args.exchange]}[plan]),
                "ms_per_step": ms, "wall_ms_per_step": wall_ms, "value": (nR_job + nS_job) / (ms / 1e3), "unit": UNIT, "phases_ms": phases,
                "build_rows": nR_job, "probe_rows": nS_job, "result_pairs": tot_out, "pairs_per_s": tot_out / (ms / 1e3), "parity": parity,
                "table_layout_chosen": LAYOUT_NAMES.get(layout_code & 0xFF, "?") + (", slice-ordered" if layout_code & 0x200 else "") + (", count by range test" if layout_code & 0x100 and not hit_lists else "") + (", hit lists" if hit_lists else ""),
@@ -467,9 +472,25 @@ def main() -> None:
             res["gpu_launches_per_step"] = 2 * 4 + launches_per_step(3, False, n_loc, n_loc, kb, args.sparse, DENSE_POLICY[layout])
             if leg_events:                                          # legs of the exchange phase on this rank, mean over the timed steps
                 legs = leg_events[-steps:]
-                names = ["start", "histograms", "count_matrix", "push_build", "push_probe", "local_build", "local_count", "local_write"]
-                res["c5_phases"]["exchange_legs_ms"] = {b_: sum(l[a_].elapsed_time(l[b_]) for l in legs) / len(legs) for a_, b_ in zip(names, names[1:])}
-                res["c5_phases"]["overlap_build"] = bool(args.overlap_build)
+                mean = lambda a_, b_: sum(l[a_].elapsed_time(l[b_]) for l in legs) / len(legs)      # noqa: E731
+                if os.environ.get("HJ_BENCH_DEBUG_LEGS"):
+                    for l in legs:
+                        ks = list(l)
+                        print("legs", {k: round(l["start"].elapsed_time(l[k]), 2) for k in ks}, file=sys.stderr)
+                if args.exchange == "staged":
+                    names = ["start", "histograms", "count_matrix", "scatter_build", "scatter_probe", "local_build", "local_count", "local_write"]   # the SM stream
+                    res["c5_phases"]["exchange_legs_ms"] = {b_: mean(a_, b_) for a_, b_ in zip(names, names[1:])}
+                    ce_ms = {"build": mean("copy_build_start", "copy_build_end"), "probe": mean("copy_probe_start", "copy_probe_end")}
+                    res["c5_phases"]["copy_engine_ms"] = ce_ms      # second stream, beside the legs above: copies + the landing barrier
+                    res["c5_phases"]["exchange_done_ms"] = mean("start", "copy_probe_end")
+                    gbs = sent / ((ce_ms["build"] + ce_ms["probe"]) / 1e3) / 1e9
+                    res["c5_phases"].update({"nvlink_achieved_gbs": gbs, "nvlink_frac": gbs / 770.0,
+                                             "note": "staged plan: partition_exchange_ms runs until the probe side has landed and INCLUDES the local build that runs beside the probe side's copies; "
+                                                     "nvlink figures = bytes sent / time of the copy legs on the second stream; local join bytes = 64 per row (SURVEY 8d, C5)"})
+                else:
+                    names = ["start", "histograms", "count_matrix", "push_build", "push_probe", "local_build", "local_count", "local_write"]
+                    res["c5_phases"]["exchange_legs_ms"] = {b_: mean(a_, b_) for a_, b_ in zip(names, names[1:])}
+                    res["c5_phases"]["overlap_build"] = bool(args.overlap_build)
         else:
             by_range = bool(layout_code & 0x100) and not hit_lists
             table_in_hbm = lib.hjTableBytes(b.n, kb) > 96 * 2**20

@@ -184,6 +184,10 @@ int32_t hjMaterializeRows(const int32_t* dTableX, int32_t xCols, const int32_t* 
 int32_t hjExtractColumn(const int32_t* dTable, int64_t rows, int32_t cols, int32_t col, int32_t* dOut, void* stream);
 /* Multi-column keys (projectDescription.md:28): two i32 key columns become one i64 key (a bijection), joined with keyBytes = 8. */
 int32_t hjPackKeys2x32(const int32_t* dA, const int32_t* dB, int64_t n, int64_t* dOut, void* stream);
+/* Non-integer keys (projectDescription.md:28): an f32 / f64 key column (elemBytes 4 / 8) becomes an i32 / i64 key column with IEEE
+ * equality — equal numbers get equal keys (-0.0 joins +0.0) and a NaN joins nothing (probeSide != 0 marks the probe relation's column:
+ * its NaNs get a pattern that differs from the build side's). Join the encoded columns with keyBytes = elemBytes. */
+int32_t hjEncodeFloatKeys(const void* dColumn, int32_t elemBytes, int64_t n, int32_t probeSide, void* dOut, void* stream);
 /* Selection (Experiments/selection.mlir:34-155): rows with `value OP constant`, count -> scan -> compacted write; output in input
  * order. dtype: 0 i32, 1 i64, 2 f32, 3 f64 (constant in iconst for integers, fconst for floats; comparisons are ordered: NaN fails).
  * op: 0 <, 1 <=, 2 >, 3 >=, 4 ==, 5 !=. hjSelectCount is synchronous and returns the size; hjSelectWrite fills dOutValues (same

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "hjMaterializeRows": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "hjExtractColumn": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "hjPackKeys2x32": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "hjEncodeFloatKeys": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "hjSelectScratchBytes": (_i64, [_i64]),
     "hjSelectCount": (_i64, [_vp, _i64, _i32, _i32, _i64, C.c_double, _vp, _i64, _vp]),
     "hjSelectWrite": (_i32, [_vp, _i64, _i32, _i32, _i64, C.c_double, _vp, _vp, _vp, _u32, _vp]),

@@ -275,6 +275,12 @@ int32_t hjPackKeys2x32(const int32_t* dA, const int32_t* dB, int64_t n, int64_t*
   return HJ_OK;
 }
 
+int32_t hjEncodeFloatKeys(const void* dColumn, int32_t elemBytes, int64_t n, int32_t probeSide, void* dOut, void* stream) {
+  if (n < 0 || (elemBytes != 4 && elemBytes != 8) || (n > 0 && (!dColumn || !dOut))) return fail(HJ_ERR_ARG, "hjEncodeFloatKeys", "bad argument (elemBytes is 4 for f32 -> i32 keys or 8 for f64 -> i64 keys)");
+  HJ_CUDA("hjEncodeFloatKeys", hj::encode_float_keys(dColumn, n, elemBytes, probeSide ? 1 : 0, dOut, S_(stream)));
+  return HJ_OK;
+}
+
 // ---- selection (Experiments/selection.mlir:34-155): count -> scan -> write ----------------------------------------------------
 int64_t hjSelectScratchBytes(int64_t n) { return n < 0 ? HJ_ERR_ARG : hj::select_scratch_bytes(n); }
 static bool select_args_ok(const void* col, int64_t n, int32_t dtype, int32_t op, const void* scratch) {

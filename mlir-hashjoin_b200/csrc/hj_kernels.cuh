@@ -127,6 +127,7 @@ cudaError_t materialize_rows(const int32_t* tx, int x_cols, const int32_t* ty, i
                              int32_t* result, cudaStream_t stream);
 cudaError_t extract_column(const int32_t* table, int64_t rows, int cols, int col, int32_t* out, cudaStream_t stream);
 cudaError_t pack_keys(const int32_t* a, const int32_t* b, int64_t n, long long* out, cudaStream_t stream);
+cudaError_t encode_float_keys(const void* in, int64_t n, int elem_bytes, int probe_side, void* out, cudaStream_t stream);
 int64_t select_scratch_bytes(int64_t n);
 unsigned long long* select_total_ptr(void* scratch, int64_t n);
 cudaError_t select_count(const void* col, int64_t n, int dtype, int op, long long iconst, double fconst, void* scratch, cudaStream_t stream);

@@ -90,6 +90,29 @@ cudaError_t pack_keys(const int32_t* a, const int32_t* b, int64_t n, long long* 
   return cudaGetLastError();
 }
 
+// floating-point key columns -> integer keys with IEEE equality: equal numbers get equal keys (-0.0 joins +0.0), a NaN joins nothing
+// (build-side NaNs become the positive quiet-NaN pattern, probe-side NaNs the negative one: no number has either, and they differ)
+template <typename F, typename I>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_encode_float_keys(const F* __restrict__ in, int64_t n, int probe_side, I* __restrict__ out) {
+  constexpr I QNAN = sizeof(F) == 4 ? (I)0x7FC00000 : (I)0x7FF8000000000000LL;
+  constexpr I SIGN = sizeof(F) == 4 ? (I)0x80000000u : (I)0x8000000000000000ULL;
+  for (int64_t i = blockIdx.x * (int64_t)BLOCK_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * BLOCK_THREADS) {
+    const F v = in[i];
+    I bits;
+    if (v != v) bits = probe_side ? (I)(QNAN | SIGN) : QNAN;
+    else if (v == F(0)) bits = 0;
+    else if (sizeof(F) == 4) bits = (I)__float_as_int((float)v);
+    else bits = (I)__double_as_longlong((double)v);
+    out[i] = bits;
+  }
+}
+cudaError_t encode_float_keys(const void* in, int64_t n, int elem_bytes, int probe_side, void* out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  if (elem_bytes == 4) k_encode_float_keys<float, int32_t><<<stream_grid(n, BLOCK_THREADS), BLOCK_THREADS, 0, stream>>>((const float*)in, n, probe_side, (int32_t*)out);
+  else k_encode_float_keys<double, long long><<<stream_grid(n, BLOCK_THREADS), BLOCK_THREADS, 0, stream>>>((const double*)in, n, probe_side, (long long*)out);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // selection: rows whose value satisfies `value OP constant`, count -> scan (K3) -> write. A warp owns 512 consecutive rows in both
 // passes and compacts them with ballots, so the output keeps the input order (the reference's order depends on which block's

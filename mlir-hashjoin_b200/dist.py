@@ -116,6 +116,121 @@ class PeerExchange:
         _lib.check_status(rc, "hjPartitionPush")
 
 
+    # ---- staged plan: partition into a local staging copy, copy engines carry the parts to their owners ----
+    def scatter_local(self, keys: torch.Tensor, row_base: int, counts_row, ws: torch.Tensor) -> list[int]:
+        """The push kernel with every destination pointing at this rank's own staging buffers: (key, row_base + i) tuples of ``keys``
+        grouped by owner, part d at [offsets[d], offsets[d + 1]). ``counts_row``: this rank's row of the count matrix (host ints).
+        Follows count() on the same keys and workspace. Returns the offsets (host)."""
+        lib = _lib.load()
+        world = dist.get_world_size(self.group)
+        n = keys.numel()
+        if getattr(self, "stage_keys", None) is None or self.stage_keys.numel() < n:
+            self.stage_keys = torch.empty(n, dtype=keys.dtype, device=keys.device)
+            self.stage_rows = torch.empty(n, dtype=torch.int32, device=keys.device)
+            self.stage_key_ptrs = torch.tensor([self.stage_keys.data_ptr()] * world, dtype=torch.int64, device=keys.device)
+            self.stage_row_ptrs = torch.tensor([self.stage_rows.data_ptr()] * world, dtype=torch.int64, device=keys.device)
+        offsets = [0]
+        for c in counts_row:
+            offsets.append(offsets[-1] + int(c))
+        cursors = torch.tensor(offsets[:-1], dtype=torch.int64).to(keys.device, non_blocking=True)
+        rc = lib.hjPartitionPush(keys.data_ptr(), None, row_base & 0xFFFFFFFF, n, keys.element_size(), world, self.stage_key_ptrs.data_ptr(), self.stage_row_ptrs.data_ptr(),
+                                 cursors.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        _lib.check_status(rc, "hjPartitionPush")
+        return offsets
+
+    def send(self, offsets: list[int], first_at_owner: list[int]) -> None:
+        """Device-to-device copies (copy engines, current stream) of every staged part into its owner's receive buffer at
+        ``first_at_owner[d]``. Owners are visited starting with the next rank, so that at any time every owner receives from one sender."""
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if getattr(self, "peer_views", None) is None:
+            self.peer_views = [(self.hk.get_buffer(d, (self.capacity,), self.keys.dtype), self.hr.get_buffer(d, (self.capacity,), torch.int32)) for d in range(world)]
+        for step in range(1, world + 1):
+            d = (rank + step) % world
+            a, z = offsets[d], offsets[d + 1]
+            if z > a:
+                pk, pr = self.peer_views[d]
+                at = first_at_owner[d]
+                pk[at:at + (z - a)].copy_(self.stage_keys[a:z], non_blocking=True)
+                pr[at:at + (z - a)].copy_(self.stage_rows[a:z], non_blocking=True)
+
+
+def radix_join_staged(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
+                      build_x: PeerExchange, probe_x: PeerExchange, exchanged=None, table: join.HashTable | None = None, marks: dict | None = None,
+                      result=None):
+    """Radix-partitioned join whose exchange runs on the COPY ENGINES: each relation is partitioned by owner into a local staging copy
+    (the push kernel, every destination local), the parts cross NVLink as device-to-device copies on a second stream — 770 GB/s per
+    direction beside SM work (tools/peer_bench.py) — and the SMs go on meanwhile: the probe side is partitioned while the build side
+    travels, the received build side is partitioned for the local join (hjBuild) while the probe side travels. One collective (count
+    rows), one host read; overflow behaves as in exchange_fused. ``marks``: CUDA events after each leg, both streams. ``result``:
+    optional callable n -> (outR, outS) int32 tensors of n elements (a caller that keeps its result columns across joins)."""
+    group = build_x.group
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if table is None:
+        table = join.allocateHashTable(build_x.capacity, None, build_shard.dtype, build_shard.device)
+    main = torch.cuda.current_stream()
+    ce = _side_stream(build_shard.device)
+
+    def mark(name, stream=None):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else main)
+            marks[name] = ev
+    build_x.barrier()                                               # nobody is still reading last step's buffers
+    mark("start")
+    cb, wsb = build_x.count(build_shard)
+    cp, wsp = probe_x.count(probe_shard)
+    mark("histograms")
+    matrix = torch.empty(world, 2 * world, dtype=torch.int64, device=build_shard.device)
+    dist.all_gather_into_tensor(matrix.view(-1), torch.cat([cb, cp]), group=group)
+    host = matrix.cpu()                                             # the exchange's one host sync
+    mb, mp = host[:, :world], host[:, world:]
+    if int(mb.sum(0).max()) > build_x.capacity or int(mp.sum(0).max()) > probe_x.capacity:
+        raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
+    nb, npr = int(mb[:, rank].sum()), int(mp[:, rank].sum())
+    at_b, at_p = mb[:rank].sum(0).tolist(), mp[:rank].sum(0).tolist()    # first element of my region in every owner's buffer
+    mark("count_matrix")
+    staged_b, landed_b, staged_p, landed_p = (torch.cuda.Event() for _ in range(4))
+    off_b = build_x.scatter_local(build_shard, build_row_base, mb[rank].tolist(), wsb)
+    staged_b.record(main)
+    mark("scatter_build")
+    with torch.cuda.stream(ce):
+        ce.wait_event(staged_b)
+        mark("copy_build_start", ce)
+        build_x.send(off_b, at_b)
+        build_x.barrier()                                           # every rank's build tuples have landed
+        landed_b.record(ce)
+        mark("copy_build_end", ce)
+    off_p = probe_x.scatter_local(probe_shard, probe_row_base, mp[rank].tolist(), wsp)
+    staged_p.record(main)
+    mark("scatter_probe")
+    with torch.cuda.stream(ce):
+        ce.wait_event(staged_p)
+        mark("copy_probe_start", ce)
+        probe_x.send(off_p, at_p)
+        probe_x.barrier()                                           # every rank's probe tuples have landed
+        landed_p.record(ce)
+        mark("copy_probe_end", ce)
+    main.wait_event(landed_b)
+    join.initializeHashTable(table)
+    join.buildTable(build_x.keys[:nb], table, build_x.rows[:nb])    # beside the probe side's copies
+    mark("local_build")
+    main.wait_event(landed_p)
+    if exchanged is not None:
+        exchanged()
+    pk, pr = probe_x.keys[:npr], probe_x.rows[:npr]
+    n = join.countRows(pk, table, pr, 0)
+    mark("local_count")
+    if result is not None:
+        outR, outS = result(n)
+    else:
+        outR = torch.empty(n, dtype=torch.int32, device=pk.device)
+        outS = torch.empty(n, dtype=torch.int32, device=pk.device)
+    if n:
+        join.probeRelation(pk, table, outR, outS, pr, 0)
+    mark("local_write")
+    return outR, outS
+
+
 def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
                    build_x: PeerExchange, probe_x: PeerExchange, marks: dict | None = None, build_landed: torch.cuda.Event | None = None) -> tuple[int, int]:
     """Both relations through the fused partition + exchange with ONE collective (the all-gather of both count rows) and ONE host
@@ -159,7 +274,7 @@ def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: 
 
 def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: torch.Tensor, probe_row_base: int,
                      build_x: PeerExchange, probe_x: PeerExchange, exchanged=None, table: join.HashTable | None = None,
-                     marks: dict | None = None, overlap_build: bool = False):
+                     marks: dict | None = None, overlap_build: bool = False, result=None):
     """Radix-partitioned join with the exchange fused into the partition kernel (peer stores over NVLink).
     ``exchanged`` (optional callable) runs once every rank's tuples have landed, before the probe passes of the local join (bench.py
     marks a phase there). ``overlap_build``: the local build (hjBuild on the received build tuples) runs on a second stream while the
@@ -189,8 +304,11 @@ def radix_join_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard
     pk, pr = probe_x.keys[:npr], probe_x.rows[:npr]
     n = join.countRows(pk, table, pr, 0)
     mark("local_count")
-    outR = torch.empty(n, dtype=torch.int32, device=pk.device)
-    outS = torch.empty(n, dtype=torch.int32, device=pk.device)
+    if result is not None:
+        outR, outS = result(n)
+    else:
+        outR = torch.empty(n, dtype=torch.int32, device=pk.device)
+        outS = torch.empty(n, dtype=torch.int32, device=pk.device)
     if n:
         join.probeRelation(pk, table, outR, outS, pr, 0)
     mark("local_write")

@@ -258,6 +258,17 @@ def pack_keys(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def encode_float_keys(column: torch.Tensor, probe_side: bool) -> torch.Tensor:
+    """f32 / f64 key column -> i32 / i64 keys with IEEE equality (hjEncodeFloatKeys): -0.0 joins +0.0, NaN joins nothing."""
+    _require_cuda(column, "column")
+    if column.dtype not in (torch.float32, torch.float64):
+        raise _lib.HashJoinError("encode_float_keys takes a float32 or float64 column")
+    eb = column.element_size()
+    out = torch.empty(column.numel(), dtype=torch.int32 if eb == 4 else torch.int64, device=column.device)
+    _lib.check_status(_lib.load().hjEncodeFloatKeys(_ptr(column), eb, column.numel(), 1 if probe_side else 0, _ptr(out), _stream_ptr()), "hjEncodeFloatKeys")
+    return out
+
+
 _SELECT_DTYPES = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
 SELECT_OPS = {"<": 0, "<=": 1, ">": 2, ">=": 3, "==": 4, "!=": 5}
 

@@ -20,4 +20,4 @@ def test_two_gpu_plans_match_oracle(lib):
            "--master-port", "29533", str(ROOT / "tools" / "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)         # >= 2 GPUs: this must RUN and pass, never skip
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("parity=OK") == 3 * 6 and "FAIL" not in r.stdout, r.stdout[-3000:]
+    assert r.stdout.count("parity=OK") == 3 * 8 and "FAIL" not in r.stdout, r.stdout[-3000:]

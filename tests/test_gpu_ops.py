@@ -137,6 +137,25 @@ def test_two_column_keys(lib, cuda):
     assert np.array_equal(sorted_pairs(outR.cpu().numpy(), outS.cpu().numpy()), sorted_pairs(i, j))
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_float_keys(lib, cuda, dt):
+    """Non-integer keys (projectDescription.md:28): float columns encoded by hjEncodeFloatKeys join exactly where IEEE `==` holds —
+    -0.0 with +0.0, NaN with nothing (not even the same NaN), infinities and denormals with themselves."""
+    import torch
+    from mlir_hashjoin_b200 import join
+    rng = np.random.default_rng(53)
+    special = np.array([0.0, -0.0, np.nan, -np.nan, np.inf, -np.inf, np.finfo(dt).tiny / 4, 1.5, -1.5], dtype=dt)
+    R = np.concatenate([special, rng.integers(-50, 50, 3000).astype(dt) / 4]).astype(dt)
+    S = np.concatenate([rng.integers(-60, 60, 5000).astype(dt) / 4, special, special]).astype(dt)
+    rng.shuffle(R); rng.shuffle(S)
+    kR = join.encode_float_keys(torch.from_numpy(R).to(cuda), probe_side=False)
+    kS = join.encode_float_keys(torch.from_numpy(S).to(cuda), probe_side=True)
+    assert kR.dtype == (torch.int32 if dt == np.float32 else torch.int64)
+    outR, outS = join.hash_join(kR, kS)
+    i, j = np.nonzero(R[:, None] == S[None, :])                       # numpy's == is IEEE: NaN != NaN, -0.0 == 0.0
+    assert np.array_equal(sorted_pairs(outR.cpu().numpy(), outS.cpu().numpy()), sorted_pairs(i, j))
+
+
 def test_join_host_bounded_window(lib, cuda, oracle):
     """hjJoinHost keeps only three probe chunks and two result slots on the device: many small chunks (ring wrap-around, growing result
     slots, duplicate build keys so chunk results differ in size) give the oracle's multiset."""

@@ -46,6 +46,11 @@ def main():
         a3, b3 = hjdist.radix_join_fused(dRs, blo, dS, plo, bx, px)
         a3, b3 = a3.clone(), b3.clone()
         a4, b4 = hjdist.radix_join_fused(dRs, blo, dS, plo, bx, px)      # buffers are reusable step after step
+        a4, b4 = a4.clone(), b4.clone()
+        # plan 4: parts staged locally, carried by the copy engines beside the partition / build kernels (twice: staging reused)
+        a6, b6 = hjdist.radix_join_staged(dRs, blo, dS, plo, bx, px)
+        a6, b6 = a6.clone(), b6.clone()
+        a7, b7 = hjdist.radix_join_staged(dRs, blo, dS, plo, bx, px)
         # receive buffers too small for the key distribution: every rank raises alike, nothing was stored, and the NCCL all-to-all
         # plan (exact sizes) gives the oracle's result
         from mlir_hashjoin_b200._lib import HashJoinError
@@ -59,7 +64,8 @@ def main():
         if rank == 0:
             print(f"{name:22s} overflow   world={world} raised={overflow_raised} parity={'OK' if overflow_raised else 'FAIL'}", flush=True)
             ok = ok and overflow_raised
-        for plan, (a, bb) in (("broadcast", (a1, b1)), ("radix", (a2, b2)), ("radix-fused", (a3, b3)), ("radix-fused#2", (a4, b4)), ("radix-after-overflow", (a5, b5))):
+        for plan, (a, bb) in (("broadcast", (a1, b1)), ("radix", (a2, b2)), ("radix-fused", (a3, b3)), ("radix-fused#2", (a4, b4)), ("radix-staged", (a6, b6)), ("radix-staged#2", (a7, b7)),
+                               ("radix-after-overflow", (a5, b5))):
             n = torch.tensor([a.numel()], device=dev)
             sizes = [torch.zeros_like(n) for _ in range(world)]
             dist.all_gather(sizes, n)
