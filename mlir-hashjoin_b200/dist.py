@@ -117,22 +117,27 @@ class PeerExchange:
 
 
     # ---- staged plan: partition into a local staging copy, copy engines carry the parts to their owners ----
-    def scatter_local(self, keys: torch.Tensor, row_base: int, counts_row, ws: torch.Tensor) -> list[int]:
-        """The push kernel with every destination pointing at this rank's own staging buffers: (key, row_base + i) tuples of ``keys``
-        grouped by owner, part d at [offsets[d], offsets[d + 1]). ``counts_row``: this rank's row of the count matrix (host ints).
-        Follows count() on the same keys and workspace. Returns the offsets (host)."""
+    def scatter_local(self, keys: torch.Tensor, row_base: int, counts_row, ws: torch.Tensor, own_at: int) -> list[int]:
+        """The push kernel with every destination on this GPU: (key, row_base + i) tuples of ``keys`` grouped by owner — part d at
+        [offsets[d], offsets[d + 1]) of the staging buffers, except this rank's own part, which goes straight to its place in the
+        receive buffer (from element ``own_at``). ``counts_row``: this rank's row of the count matrix (host ints). Follows count() on the
+        same keys and workspace. Returns the offsets (host)."""
         lib = _lib.load()
-        world = dist.get_world_size(self.group)
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         n = keys.numel()
         if getattr(self, "stage_keys", None) is None or self.stage_keys.numel() < n:
             self.stage_keys = torch.empty(n, dtype=keys.dtype, device=keys.device)
             self.stage_rows = torch.empty(n, dtype=torch.int32, device=keys.device)
-            self.stage_key_ptrs = torch.tensor([self.stage_keys.data_ptr()] * world, dtype=torch.int64, device=keys.device)
-            self.stage_row_ptrs = torch.tensor([self.stage_rows.data_ptr()] * world, dtype=torch.int64, device=keys.device)
+            kp, rp = [self.stage_keys.data_ptr()] * world, [self.stage_rows.data_ptr()] * world
+            kp[rank], rp[rank] = self.keys.data_ptr(), self.rows.data_ptr()
+            self.stage_key_ptrs = torch.tensor(kp, dtype=torch.int64, device=keys.device)
+            self.stage_row_ptrs = torch.tensor(rp, dtype=torch.int64, device=keys.device)
         offsets = [0]
         for c in counts_row:
             offsets.append(offsets[-1] + int(c))
-        cursors = torch.tensor(offsets[:-1], dtype=torch.int64).to(keys.device, non_blocking=True)
+        first = offsets[:-1]
+        first[rank] = own_at
+        cursors = torch.tensor(first, dtype=torch.int64).to(keys.device, non_blocking=True)
         rc = lib.hjPartitionPush(keys.data_ptr(), None, row_base & 0xFFFFFFFF, n, keys.element_size(), world, self.stage_key_ptrs.data_ptr(), self.stage_row_ptrs.data_ptr(),
                                  cursors.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         _lib.check_status(rc, "hjPartitionPush")
@@ -144,7 +149,7 @@ class PeerExchange:
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if getattr(self, "peer_views", None) is None:
             self.peer_views = [(self.hk.get_buffer(d, (self.capacity,), self.keys.dtype), self.hr.get_buffer(d, (self.capacity,), torch.int32)) for d in range(world)]
-        for step in range(1, world + 1):
+        for step in range(1, world):                                # (this rank's own part is already in place: scatter_local)
             d = (rank + step) % world
             a, z = offsets[d], offsets[d + 1]
             if z > a:
@@ -190,7 +195,7 @@ def radix_join_staged(build_shard: torch.Tensor, build_row_base: int, probe_shar
     at_b, at_p = mb[:rank].sum(0).tolist(), mp[:rank].sum(0).tolist()    # first element of my region in every owner's buffer
     mark("count_matrix")
     staged_b, landed_b, staged_p, landed_p = (torch.cuda.Event() for _ in range(4))
-    off_b = build_x.scatter_local(build_shard, build_row_base, mb[rank].tolist(), wsb)
+    off_b = build_x.scatter_local(build_shard, build_row_base, mb[rank].tolist(), wsb, at_b[rank])
     staged_b.record(main)
     mark("scatter_build")
     with torch.cuda.stream(ce):
@@ -200,7 +205,7 @@ def radix_join_staged(build_shard: torch.Tensor, build_row_base: int, probe_shar
         build_x.barrier()                                           # every rank's build tuples have landed
         landed_b.record(ce)
         mark("copy_build_end", ce)
-    off_p = probe_x.scatter_local(probe_shard, probe_row_base, mp[rank].tolist(), wsp)
+    off_p = probe_x.scatter_local(probe_shard, probe_row_base, mp[rank].tolist(), wsp, at_p[rank])
     staged_p.record(main)
     mark("scatter_probe")
     with torch.cuda.stream(ce):
