@@ -202,7 +202,7 @@ def launches_per_step(layout: int, by_range: bool, nR: int, nS: int, kb: int, sp
         n += 2 * 4 + 1                                                        # two partition passes (blocks, hist, scan, scatter) + k_rj_header
         n += 2 * 4 + 1 + scan(parts) + 1 + 1 + scan(nS // 16384 + 65537) + 1  # probe side: partition, item counts, scan, items, count join, scan; write join
         return n
-    n += 1 + (3 if dense_policy else 0) + 6                                   # k_clear, [dense, fallback_prepare, clear], hash, group_prepare, clear, group count/offsets/fill
+    n += 1 + (4 if dense_policy else 0) + 6                                   # k_clear, [dense, dense_verify, fallback_prepare, clear], hash, group_prepare, clear, group count/offsets/fill
     chunks = -(-nS // (16384 if kb == 4 else 1024))
     n += (1 if sparse and nS >= (1 << 20) and layout != 2 else 0) + 1 + (1 if sparse and layout != 2 else 0) + scan(chunks) + 1
     return n

@@ -45,6 +45,7 @@ struct TableHeader {
   uint32_t rj_bits1, rj_bits2;    // radix layout: 2^(bits1 + bits2) partitions of the build relation, partition id = top bits of radix_hash(key)
   uint32_t slice_bits;            // inline layout built in table-slice order: the probe relation is partitioned into 2^slice_bits slices first (0 = no)
   unsigned long long rj_keys_off, rj_rows_off, rj_offs_off;   // radix layout: byte offsets (inside the body) of the partitioned keys, row ids, u32 offsets[parts + 1]
+  unsigned long long dense_filled;// direct-address build: slots taken after all rows were stored (k_dense_verify); < n_rows proves a duplicate key
 };
 static_assert(sizeof(TableHeader) <= HEADER_BYTES, "header too large");
 
