@@ -1038,21 +1038,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count_dense_tma(const int32_t
 // =========================================================================================================
 template <typename K, bool VEC>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_count_range(const K* __restrict__ S, int64_t nS, const TableHeader* __restrict__ hdr,
-                                                               unsigned long long* __restrict__ chunk_totals, int64_t nchunks,
+                                                               unsigned long long* __restrict__ chunk_totals, uint32_t* __restrict__ warp_first, int64_t nchunks,
                                                                const unsigned long long* __restrict__ sparse_flag) {
   using T = KeyTraits<K>;
   using UK = typename std::make_unsigned<K>::type;
   if (hdr->mode != MODE_DENSE || !hdr->all_present || *sparse_flag) return;     // few rows hit: hit lists read the keys once, this path twice
   constexpr int KPV = T::KEYS_PER_VEC, CHUNK_ROWS = chunk_keys((int)sizeof(K)), NV = CHUNK_ROWS / (BLOCK_THREADS * KPV);   // vectors per thread and chunk: 16 (i32) / 2 (i64)
   constexpr int UNROLL = NV < 8 ? NV : 8;
-  __shared__ unsigned long long red[33];
+  constexpr int WARPS = BLOCK_THREADS / 32;
+  __shared__ uint32_t wsum[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const UK kmin = (UK)hdr->kmin, drange = (UK)hdr->dense_range;
   const uint64_t pol_s = policy_evict_first();
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int64_t chunk_base = chunk * CHUNK_ROWS;
     const uint32_t lim = (uint32_t)(nS - chunk_base < CHUNK_ROWS ? nS - chunk_base : CHUNK_ROWS);
     const K* __restrict__ Sc = S + chunk_base;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0;                                          // hits among THIS thread's elements — the same elements it has in k_write_range
     if (VEC && lim == CHUNK_ROWS) {
       #pragma unroll 1
       for (int v0 = 0; v0 < NV; v0 += UNROLL) {
@@ -1067,16 +1069,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_count_range(const K* __restri
         }
       }
     } else {
-      for (uint32_t i = threadIdx.x; i < lim; i += BLOCK_THREADS) cnt += ((UK)Sc[i] - kmin) < drange;
+      for (int v = 0; v < NV; v++) {
+        #pragma unroll
+        for (int e = 0; e < KPV; e++) { const uint32_t i = (uint32_t)(v * BLOCK_THREADS + threadIdx.x) * KPV + e; cnt += i < lim && ((UK)Sc[i] - kmin) < drange; }
+      }
     }
-    const unsigned long long total = block_reduce_sum((unsigned long long)cnt, red);
-    if (threadIdx.x == 0) chunk_totals[chunk] = total;
+    // per chunk: its total (scanned by K3 into the chunk's first output element) and, per warp, the first output element of the warp's
+    // hits relative to the chunk — with it every warp of k_write_range owns a contiguous output run and needs no block barrier
+    cnt = warp_reduce_sum(cnt);
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (lane == 0) {
+      uint32_t first = 0, total = 0;
+      #pragma unroll
+      for (int w = 0; w < WARPS; w++) { const uint32_t x = wsum[w]; first += w < warp ? x : 0u; total += x; }
+      warp_first[chunk * WARPS + warp] = first;
+      if (warp == 0) chunk_totals[chunk] = total;
+    }
+    __syncthreads();                                           // wsum is reused by the next chunk
   }
 }
 
 template <typename K, bool VEC>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restrict__ S, int64_t nS, const char* __restrict__ body, const TableHeader* __restrict__ hdr,
-                                                               const unsigned long long* __restrict__ chunk_offsets, int64_t nchunks,
+                                                               const unsigned long long* __restrict__ chunk_offsets, const uint32_t* __restrict__ warp_first, int64_t nchunks,
                                                                int32_t* __restrict__ outR, int32_t* __restrict__ outS,
                                                                const uint32_t* __restrict__ probe_payload, uint32_t probe_row_base,
                                                                const unsigned long long* __restrict__ sparse_flag) {
@@ -1085,21 +1101,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restri
   if (hdr->mode != MODE_DENSE || !hdr->all_present || *sparse_flag) return;
   constexpr int KPV = T::KEYS_PER_VEC, KPT = VECS_PER_THREAD * KPV, TILE = BLOCK_THREADS * KPT, WARPS = BLOCK_THREADS / 32;
   constexpr int CHUNK_ROWS = chunk_keys((int)sizeof(K));
-  __shared__ uint32_t warp_totals[2][WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const UK kmin = (UK)hdr->kmin, drange = (UK)hdr->dense_range;
   const uint32_t* __restrict__ tab = reinterpret_cast<const uint32_t*>(body);
   const uint64_t pol_s = policy_evict_first(), pol_t = policy_evict_last();
   const unsigned lt = (1u << lane) - 1u;
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    unsigned long long out_base = chunk_offsets[chunk];
-    if (chunk_offsets[chunk + 1] == out_base) continue;                        // nothing to emit for this chunk (uniform)
+    unsigned long long o = chunk_offsets[chunk];
+    if (chunk_offsets[chunk + 1] == o) continue;                               // nothing to emit for this chunk (uniform)
+    o += warp_first[chunk * WARPS + warp];                                     // this warp's own output run (k_count_range): no block barrier below
     const int64_t chunk_base = chunk * CHUNK_ROWS;
     const uint32_t lim = (uint32_t)(nS - chunk_base < CHUNK_ROWS ? nS - chunk_base : CHUNK_ROWS);
     const K* __restrict__ Sc = S + chunk_base;
-    int par = 0;
     #pragma unroll 1
-    for (uint32_t tile_off = 0; tile_off < lim; tile_off += TILE, par ^= 1) {
+    for (uint32_t tile_off = 0; tile_off < lim; tile_off += TILE) {
       K key[KPT]; uint32_t pos[KPT], m[KPT]; bool hit[KPT];
       #pragma unroll
       for (int k = 0; k < KPT; k++) pos[k] = tile_off + ((k / KPV) * BLOCK_THREADS + threadIdx.x) * KPV + (k % KPV);
@@ -1111,30 +1126,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_write_range(const K* __restri
         hit[k] = off < drange && pos[k] < lim;
         m[k] = hit[k] ? ld_keep_u32(tab + off, pol_t) : ROW_NONE;              // in flight while the hits are ranked below
       }
-      unsigned mask[KPT];
-      uint32_t wtotal = 0;
-      #pragma unroll
-      for (int k = 0; k < KPT; k++) { mask[k] = __ballot_sync(0xffffffffu, hit[k]); wtotal += __popc(mask[k]); }
-      uint32_t* wt = warp_totals[par];
-      if (lane == 0) wt[warp] = wtotal;
-      __syncthreads();
-      uint32_t wbase = 0, ttotal = 0;
-      #pragma unroll
-      for (int w = 0; w < WARPS; w++) { const uint32_t x = wt[w]; wbase += w < warp ? x : 0u; ttotal += x; }
-      unsigned long long o = out_base + wbase;
       #pragma unroll
       for (int k = 0; k < KPT; k++) {
+        const unsigned mask = __ballot_sync(0xffffffffu, hit[k]);
         if (hit[k]) {
-          const unsigned long long dst = o + __popc(mask[k] & lt);
+          const unsigned long long dst = o + __popc(mask & lt);
           const uint32_t j = (uint32_t)chunk_base + pos[k];
           if (outR) st_stream_u32(outR + dst, m[k], pol_s);
           st_stream_u32(outS + dst, probe_payload ? probe_payload[j] : probe_row_base + j, pol_s);
         }
-        o += __popc(mask[k]);
+        o += __popc(mask);
       }
-      out_base += ttotal;
     }
-    __syncthreads();                                                            // warp_totals is reused by the next chunk
   }
 }
 
@@ -1231,7 +1234,7 @@ cudaError_t count_rows_async(const void* S, int64_t nS, int key_bytes, const voi
       k_count<K, V, MODE_HASH><<<resident_grid(k_count<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_HASH, sparse_flag, 0);  \
       if (sparse_policy) k_count_sparse<K, V, MODE_HASH><<<resident_grid(k_count_sparse<K, V, MODE_HASH>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_SPARSE, sparse_flag); \
     } else { \
-      if (by_range) k_count_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.nchunks, sparse_flag); \
+      if (by_range) k_count_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, hdr, sv.chunk_offsets, sv.mcache, sv.nchunks, sparse_flag); \
       else if (tma && sizeof(K) == 4 && V) k_count_dense_tma<<<(unsigned)sv.nchunks, BLOCK_THREADS, 0, stream>>>((const int32_t*)S, nS, body, hdr, sv.mcache, sv.chunk_offsets); \
       else k_count<K, V, MODE_DENSE><<<dense_grid(k_count<K, V, MODE_DENSE>, sv.nchunks, g_count_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters, sparse_flag, 0); \
       if (sparse_policy) k_count_sparse<K, V, MODE_DENSE><<<resident_grid(k_count_sparse<K, V, MODE_DENSE>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.hit_list, sv.warp_counts, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_SPARSE, sparse_flag); \
@@ -1410,7 +1413,7 @@ cudaError_t write_pairs(const void* S, int64_t nS, int key_bytes, const void* ta
   }
 #define HJ_LAUNCH_WRITE(K, V) \
   if (grouped) k_write<K, V, true><<<resident_grid(k_write<K, V, true>, sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP_W, outR, outS, probe_payload, probe_row_base, sparse_flag); \
-  else if (by_range) k_write_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.chunk_offsets, sv.nchunks, outR, outS, probe_payload, probe_row_base, sparse_flag); \
+  else if (by_range) k_write_range<K, V><<<range_grid(sv.nchunks), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.chunk_offsets, sv.mcache, sv.nchunks, outR, outS, probe_payload, probe_row_base, sparse_flag); \
   else k_write<K, V, false><<<dense_grid(k_write<K, V, false>, sv.nchunks, g_write_waves), BLOCK_THREADS, 0, stream>>>((const K*)S, nS, body, hdr, sv.mcache, sv.run_start, sv.chunk_offsets, sv.nchunks, sv.counters + CTR_TICKET_GROUP_W, outR, outS, probe_payload, probe_row_base, sparse_flag);
   if (key_bytes == 4) { if (vec) { HJ_LAUNCH_WRITE(int32_t, true) } else { HJ_LAUNCH_WRITE(int32_t, false) } }
   else                { if (vec) { HJ_LAUNCH_WRITE(int64_t, true) } else { HJ_LAUNCH_WRITE(int64_t, false) } }
