@@ -11,10 +11,13 @@
 //   k_rp_hist     per block: digit counts in shared memory -> mat[block][digit]; totals[segment][digit] by one atomic per (block, digit)
 //   k_rp_scan     per (segment, 32 digits): first destination of every (block, digit) = segment base + exclusive scan of the digit
 //                 totals + prefix over the segment's blocks   (coalesced 128-byte rows, two looks at the matrix)
-//   k_rp_scatter  per block: 8 tiles of 4 096 tuples; a tile is ranked with ONE shared-memory atomic per tuple (ATOMS.ADD returns the
-//                 rank inside the digit), staged digit-sorted in shared memory and written out run by run, so HBM / NVLink see
-//                 contiguous stores (16 tuples per run at 256 digits). Three barriers per tile; the next tile's loads are issued
-//                 before the output loop. No global atomics on the data path, no host round trip.
+//   k_rp_scatter  per block: tiles of 4 096 tuples (512 threads, 2 CTAs / SM) or 8 192 tuples (1 024 threads, more than 128 digits); a
+//                 tile is ranked with ONE shared-memory atomic per tuple (ATOMS.ADD returns the rank inside the digit), staged
+//                 digit-sorted in shared memory and written out run by run, so HBM / NVLink see contiguous stores (32 tuples per
+//                 run at 256 digits). Three barriers per tile; the next tile's loads are issued before the output loop. No global
+//                 atomics on the data path, no host round trip.
+// The multi-GPU plans use hjPartitionPush twice over: with the peers' receive buffers as destinations (the exchange fused into this
+// kernel), or with local staging buffers as destinations, the parts then crossing NVLink on the copy engines (dist.py).
 // Indices are 32-bit (relations hold < 2^32 rows, join_v1.mlir:604-605: row ids are i32).
 #include <algorithm>
 #include <cstdio>
