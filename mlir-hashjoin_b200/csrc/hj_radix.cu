@@ -10,8 +10,13 @@
 //           stays legal, and no probe-sequence clustering, so duplicate keys cost exactly their multiplicity — streams its probe
 //           tuples through it and writes the item's match count; K3 (the same scan as the other layouts) turns item counts into
 //           offsets and the total;
-//   write   the same items again: the table is rebuilt with row ids, every warp ranks the matches of its 32 probe tuples with a ballot,
-//           claims a run of the item's output range with one shared-memory atomic and stores the pairs (order is free: shared.cpp:168-171).
+//           the count pass also leaves a MATCH CACHE word per partitioned probe tuple (position of its matched build tuple, or none)
+//           and flags the items where some probe tuple matched more than once;
+//   write   items whose probe tuples match at most once (unique build keys, semi-joins) are a pure stream: k_rj_emit reads cache words
+//           and row ids, ranks the hits of 32 tuples with a ballot and claims a run of the item's output range with one shared-memory
+//           atomic — no table, no keys. The flagged items are joined again (k_rj_join<write>: table rebuilt with row ids, matches of a
+//           warp's 32 tuples pre-counted so that one atomic claims their run). Order is free (shared.cpp:168-171).
+// Work items are handed out by ticket two ahead, so that a CTA pulls its next item's tuples into L2 while it joins the current one.
 // Duplicate build keys need nothing special (equal keys share a bucket and every entry of it is compared); a partition larger than the
 // table (heavy skew) is joined in rounds of RJ_CAP build tuples; a hot probe key only makes more items.
 #include <algorithm>
