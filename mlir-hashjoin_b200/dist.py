@@ -73,6 +73,26 @@ def exchange(parts: torch.Tensor, plan: ExchangePlan, group=None) -> torch.Tenso
     return out
 
 
+@dataclass
+class LandingPlan:
+    """Where this rank's parts land in the owners' receive buffers (peer-store and copy-engine exchanges)."""
+    received: int                # tuples this rank will hold once every rank's parts have landed
+    fullest: int                 # tuples the fullest owner will hold (capacity check, identical on every rank)
+    first_at_owner: list[int]    # per owner: first element of this rank's region in that owner's buffer (the lower ranks' parts precede it)
+    offsets: list[int]           # per owner (+ end): this rank's parts in its own staging copy, grouped by owner
+
+
+def landing_plan(matrix: torch.Tensor, rank: int) -> LandingPlan:
+    """``matrix[src][dst]`` (host, int64) = tuples rank ``src`` sends to owner ``dst``. Senders fill an owner's buffer in rank order, so the
+    regions tile [0, received) without gaps; pure host arithmetic, the same on every backend."""
+    m = matrix.to(torch.int64)
+    per_owner = m.sum(0)
+    offsets = [0]
+    for c in m[rank].tolist():
+        offsets.append(offsets[-1] + int(c))
+    return LandingPlan(int(per_owner[rank]), int(per_owner.max()) if per_owner.numel() else 0, [int(x) for x in m[:rank].sum(0).tolist()], offsets)
+
+
 class PeerExchange:
     """Peer-mapped receive buffers for the fused partition + exchange (K5 ``hjPartitionPush``): every rank allocates the
     same symmetric buffers (torch symmetric memory = CUDA VMM handles exchanged once at rendezvous; plumbing only) and
@@ -189,10 +209,11 @@ def radix_join_staged(build_shard: torch.Tensor, build_row_base: int, probe_shar
     dist.all_gather_into_tensor(matrix.view(-1), torch.cat([cb, cp]), group=group)
     host = matrix.cpu()                                             # the exchange's one host sync
     mb, mp = host[:, :world], host[:, world:]
-    if int(mb.sum(0).max()) > build_x.capacity or int(mp.sum(0).max()) > probe_x.capacity:
+    lb, lp = landing_plan(mb, rank), landing_plan(mp, rank)
+    if lb.fullest > build_x.capacity or lp.fullest > probe_x.capacity:
         raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
-    nb, npr = int(mb[:, rank].sum()), int(mp[:, rank].sum())
-    at_b, at_p = mb[:rank].sum(0).tolist(), mp[:rank].sum(0).tolist()    # first element of my region in every owner's buffer
+    nb, npr = lb.received, lp.received
+    at_b, at_p = lb.first_at_owner, lp.first_at_owner              # first element of my region in every owner's buffer
     mark("count_matrix")
     staged_b, landed_b, staged_p, landed_p = (torch.cuda.Event() for _ in range(4))
     off_b = build_x.scatter_local(build_shard, build_row_base, mb[rank].tolist(), wsb, at_b[rank])
@@ -261,11 +282,12 @@ def exchange_fused(build_shard: torch.Tensor, build_row_base: int, probe_shard: 
     dist.all_gather_into_tensor(matrix.view(-1), torch.cat([cb, cp]), group=group)      # matrix[src] = [build counts per dst | probe counts per dst]
     host = matrix.cpu()                                             # the step's one host sync
     mb, mp = host[:, :world], host[:, world:]
-    if int(mb.sum(0).max()) > build_x.capacity or int(mp.sum(0).max()) > probe_x.capacity:
+    lb, lp = landing_plan(mb, rank), landing_plan(mp, rank)
+    if lb.fullest > build_x.capacity or lp.fullest > probe_x.capacity:
         raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
-    cursors = torch.cat([mb[:rank].sum(0), mp[:rank].sum(0)]).to(build_shard.device, non_blocking=True)   # first element of my region in every owner's buffer
+    cursors = torch.tensor(lb.first_at_owner + lp.first_at_owner, dtype=torch.int64).to(build_shard.device, non_blocking=True)   # first element of my region in every owner's buffer
     mark("count_matrix")
-    nb, npr = int(mb[:, rank].sum()), int(mp[:, rank].sum())
+    nb, npr = lb.received, lp.received
     build_x.push(build_shard, build_row_base, cursors[:world], wsb)
     build_x.barrier()                                               # every rank's build tuples have landed
     mark("push_build")

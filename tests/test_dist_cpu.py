@@ -40,6 +40,11 @@ def _worker(rank, world, port, nR, nS, out_dir):
         k, r, off = _np_partition(arr[lo:hi], np.arange(lo, hi, dtype=np.int32), world)
         plan = hjdist.exchange_plan(torch.from_numpy(off), None)
         assert sum(plan.send_counts) == hi - lo
+        counts = torch.from_numpy(np.diff(off).astype(np.int64))
+        rows_ = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(rows_, counts)
+        land = hjdist.landing_plan(torch.stack(rows_), rank)
+        assert land.received == sum(plan.recv_counts) and land.offsets == off.tolist()
         mk = hjdist.exchange(torch.from_numpy(k), plan).numpy(); mr = hjdist.exchange(torch.from_numpy(r), plan).numpy()
         assert mk.size == sum(plan.recv_counts) == mr.size
         assert np.array_equal(arr[mr], mk)                                       # rows still carry their keys
@@ -62,6 +67,28 @@ def test_shard_range():
             assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_landing_plan_tiles_every_owner_buffer():
+    """Peer-store / copy-engine exchanges: the regions the ranks claim in an owner's receive buffer tile [0, received) exactly, in rank
+    order, and every rank computes the same capacity verdict from the same count matrix."""
+    from mlir_hashjoin_b200 import dist as hjdist
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 8):
+        for _ in range(5):
+            m = torch.from_numpy(rng.integers(0, 1000, (world, world)) * rng.integers(0, 2, (world, world)))      # some empty parts
+            plans = [hjdist.landing_plan(m, r) for r in range(world)]
+            assert len({p.fullest for p in plans}) == 1 and plans[0].fullest == int(m.sum(0).max())
+            for owner in range(world):
+                regions = sorted((plans[src].first_at_owner[owner], int(m[src, owner])) for src in range(world))
+                end = 0
+                for first, count in regions:
+                    assert first == end or count == 0
+                    end = max(end, first + count)
+                assert end == plans[owner].received == int(m[:, owner].sum())
+            for src in range(world):
+                assert plans[src].offsets[0] == 0 and plans[src].offsets[-1] == int(m[src].sum())
+                assert [b - a for a, b in zip(plans[src].offsets, plans[src].offsets[1:])] == m[src].tolist()
 
 
 @pytest.mark.timeout(180)
