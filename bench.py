@@ -478,7 +478,8 @@ def main() -> None:
                         ks = list(l)
                         print("legs", {k: round(l["start"].elapsed_time(l[k]), 2) for k in ks}, file=sys.stderr)
                 if args.exchange == "staged":
-                    names = ["start", "histograms", "count_matrix", "scatter_build", "scatter_probe", "local_build", "local_count", "local_write"]   # the SM stream
+                    names = ["start", "histogram_build", "count_matrix_build", "scatter_build", "histogram_probe", "count_matrix_probe", "scatter_probe",
+                             "local_build", "local_count", "local_write"]   # the SM stream
                     res["c5_phases"]["exchange_legs_ms"] = {b_: mean(a_, b_) for a_, b_ in zip(names, names[1:])}
                     ce_ms = {"build": mean("copy_build_start", "copy_build_end"), "probe": mean("copy_probe_start", "copy_probe_end")}
                     res["c5_phases"]["copy_engine_ms"] = ce_ms      # second stream, beside the legs above: copies + the landing barrier

@@ -186,7 +186,8 @@ def radix_join_staged(build_shard: torch.Tensor, build_row_base: int, probe_shar
     (the push kernel, every destination local), the parts cross NVLink as device-to-device copies on a second stream — 770 GB/s per
     direction beside SM work (tools/peer_bench.py) — and the SMs go on meanwhile: the probe side is partitioned while the build side
     travels, the received build side is partitioned for the local join (hjBuild) while the probe side travels. One collective (count
-    rows), one host read; overflow behaves as in exchange_fused. ``marks``: CUDA events after each leg, both streams. ``result``:
+    rows) and one host read per relation; a receive buffer that would overflow raises HashJoinError on every rank alike (radix_join()
+    is the fallback; when it is the probe side that overflows, the build side has been exchanged already — into buffers nobody reads). ``marks``: CUDA events after each leg, both streams. ``result``:
     optional callable n -> (outR, outS) int32 tensors of n elements (a caller that keeps its result columns across joins)."""
     group = build_x.group
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -202,40 +203,45 @@ def radix_join_staged(build_shard: torch.Tensor, build_row_base: int, probe_shar
             marks[name] = ev
     build_x.barrier()                                               # nobody is still reading last step's buffers
     mark("start")
-    cb, wsb = build_x.count(build_shard)
-    cp, wsp = probe_x.count(probe_shard)
-    mark("histograms")
-    matrix = torch.empty(world, 2 * world, dtype=torch.int64, device=build_shard.device)
-    dist.all_gather_into_tensor(matrix.view(-1), torch.cat([cb, cp]), group=group)
-    host = matrix.cpu()                                             # the exchange's one host sync
-    mb, mp = host[:, :world], host[:, world:]
-    lb, lp = landing_plan(mb, rank), landing_plan(mp, rank)
-    if lb.fullest > build_x.capacity or lp.fullest > probe_x.capacity:
-        raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
-    nb, npr = lb.received, lp.received
-    at_b, at_p = lb.first_at_owner, lp.first_at_owner              # first element of my region in every owner's buffer
-    mark("count_matrix")
     staged_b, landed_b, staged_p, landed_p = (torch.cuda.Event() for _ in range(4))
-    off_b = build_x.scatter_local(build_shard, build_row_base, mb[rank].tolist(), wsb, at_b[rank])
+
+    def plan_of(x: PeerExchange, shard: torch.Tensor, side: str):
+        """Histogram, all-gather of the count rows, host read (one sync per relation: the build side's parts are on the links while the
+        probe side is still being counted)."""
+        counts, ws = x.count(shard)
+        mark("histogram_" + side)
+        matrix = torch.empty(world, world, dtype=torch.int64, device=shard.device)
+        dist.all_gather_into_tensor(matrix.view(-1), counts, group=group)
+        m = matrix.cpu()
+        land = landing_plan(m, rank)
+        if land.fullest > x.capacity:                               # the same verdict on every rank
+            raise _lib.HashJoinError("receive buffer too small for this key distribution (skew): use radix_join()")
+        mark("count_matrix_" + side)
+        return m, ws, land
+
+    mb, wsb, lb = plan_of(build_x, build_shard, "build")
+    off_b = build_x.scatter_local(build_shard, build_row_base, mb[rank].tolist(), wsb, lb.first_at_owner[rank])
     staged_b.record(main)
     mark("scatter_build")
     with torch.cuda.stream(ce):
         ce.wait_event(staged_b)
         mark("copy_build_start", ce)
-        build_x.send(off_b, at_b)
+        build_x.send(off_b, lb.first_at_owner)
         build_x.barrier()                                           # every rank's build tuples have landed
         landed_b.record(ce)
         mark("copy_build_end", ce)
-    off_p = probe_x.scatter_local(probe_shard, probe_row_base, mp[rank].tolist(), wsp, at_p[rank])
+    mp, wsp, lp = plan_of(probe_x, probe_shard, "probe")
+    off_p = probe_x.scatter_local(probe_shard, probe_row_base, mp[rank].tolist(), wsp, lp.first_at_owner[rank])
     staged_p.record(main)
     mark("scatter_probe")
     with torch.cuda.stream(ce):
         ce.wait_event(staged_p)
         mark("copy_probe_start", ce)
-        probe_x.send(off_p, at_p)
+        probe_x.send(off_p, lp.first_at_owner)
         probe_x.barrier()                                           # every rank's probe tuples have landed
         landed_p.record(ce)
         mark("copy_probe_end", ce)
+    nb, npr = lb.received, lp.received
     main.wait_event(landed_b)
     join.initializeHashTable(table)
     join.buildTable(build_x.keys[:nb], table, build_x.rows[:nb])    # beside the probe side's copies
