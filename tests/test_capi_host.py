@@ -128,6 +128,8 @@ def test_argument_validation_of_native_entry_points(lib):
     # row ids are 32-bit and 0xFFFFFFFF is the EMPTY marker: a row base that would reach it is refused
     assert lib.hjBuild(base, 16, 4, None, 0xFFFFFFF0, base + 1024, 2048, None) == -22
     assert lib.hjJoinHost(p, 16, p, 1 << 32, 4, None, None, 0) == -22                      # probe rows beyond 32-bit row ids
+    assert lib.hjEncodeFloatKeys(p, 2, 10, 0, p, None) == -22 and lib.hjEncodeFloatKeys(None, 4, 10, 0, p, None) == -22   # f32 / f64 only; null column
+    assert lib.hjEncodeFloatKeys(None, 8, 0, 1, None, None) == 0                           # nothing to encode: no CUDA call
     assert lib.hjDefaultPolicy() & 3 in (0, 1, 2)
     assert lib.hjProbePath(None, 10, 4, None) < 0
     assert lib.hjPartitionWorkspaceBytes(1 << 20, 8) > 0
