@@ -39,8 +39,6 @@ def main():
                 res[f"{tname} {name} x{ctas}"] = round(n / best / 1e6, 1)
         h.barrier()
         torch.cuda.synchronize()
-        if tname == "peer":                                  # what the neighbour wrote into my buffer must be its source
-            pass
     # copy engine: the same 1 GiB as one device-to-device copy into the peer's buffer — alone, and while the SMs are kept busy by a local
     # streaming kernel on another stream (does the copy run beside SM work?)
     peer_t = h.get_buffer((rank + 1) % world, (n,), torch.uint8)
